@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- PBS/s of the batched programmable bootstrap (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--preset P1] [--batch 4096] [--impl reference]
+
+A "step" is one pass of the hot path (blind rotation + sample extract + key switch) over one batch of
+synthetic LWE ciphertexts.  Default workload = BASELINE.json configs[1]: batch 4096 PBS, N=1024,
+n=630, identity test vector, one B200 (preset P1 of SURVEY.md 8(d)).  With N>1 (torchrun, one rank
+per GPU) every rank bootstraps its own 4096-ciphertext shard with a replica of the keys (weak
+scaling, no data-path collective); `value` = all ranks' PBS / max-over-ranks device time.
+
+value  : inputs resident in HBM (CUDA torch tensors handed to the C-ABI as device pointers).
+e2e    : the same call with pinned HOST buffers, H2D and D2H copies inside the timed region.
+roofline: integer pipe (IMAD-class lane-ops, SURVEY 8(d) W_int) against the IMAD peak measured live
+         on this GPU by tfhe_measure_int_peak; the HBM side is reported in roofline.hbm.
+cpu_baseline / --impl reference: the C restatement of the reference's Rust path (oracle/, faithful
+         Toeplitz O(N^2) algorithm, one PBS per host thread) -- the Rust crate cannot be built here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def w_int_per_pbs(p):
+    """IMAD-class multiply instructions per PBS (algorithmic, kernel independent)."""
+    P, l, N, R = p.k + 1, p.pbs_levels, p.N, 2
+    bf = (N // 2) * p.glwe_poly_degree
+    c_cmux = 3 * R * bf * (P * l + P) + R * P * P * l * N + 8 * P * N
+    c_ks = p.k * N * p.ks_levels * (p.n + 1)
+    return p.n * c_cmux + c_ks, c_cmux, c_ks
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(p_fields, seconds_hint, threads, bsk, ksk, cts, tv):  # seconds_hint: number of PBS (0 = one per thread)
+    """PBS/s of the oracle (faithful reference algorithm), one PBS per host thread."""
+    from oracle import orc
+    o = orc.params(**p_fields)
+    orc.lib().orc_set_faithful_toeplitz(1)
+    t0 = time.perf_counter()
+    n_ct = seconds_hint or threads
+    out = orc.bootstrap_batch(o, cts[:n_ct], bsk, ksk, tv, threads)
+    dt = time.perf_counter() - t0
+    orc.lib().orc_set_faithful_toeplitz(0)
+    return n_ct / dt, dt, out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--preset", default="P1")
+    ap.add_argument("--batch", type=int, default=4096, help="ciphertexts per GPU per step")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    import tfhe_research_b200 as T
+    p = T.TfheParams.preset(args.preset)
+    fields = {f: getattr(p, f) for f, _ in T.TfheParams._fields_}
+    w_int, c_cmux, c_ks = w_int_per_pbs(p)
+    workload = (f"{args.preset}: batch {args.batch} PBS per GPU, k={p.k} N={p.N} n={p.n} pbs(logB={p.pbs_log_base},l={p.pbs_levels}) "
+                f"ks(logB={p.ks_log_base},l={p.ks_levels}) log_p={p.log_p}, identity test vector")
+    cores = args.cpu_threads or (os.cpu_count() or 1)
+
+    # synthetic inputs: real keys (seeded keygen) and real encryptions so results can be decrypted
+    lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 0xB200)
+    tv = T.construct_identity_test_vector(p)
+    pm = 1 << p.log_p
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_ct = cores
+        cts = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(n_ct)])
+        times = []
+        for s in range(args.warmup + args.steps):
+            rate, dt, out = cpu_reference_rate(fields, 0, cores, bsk, ksk, cts, tv)
+            if s >= args.warmup:
+                times.append(dt)
+            if s == 0:
+                assert all(T.decode_rounded(p, T.decrypt_lwe(lwe_sk, out[i])) == i % pm for i in range(n_ct))
+        total = sum(times)
+        value = n_ct * len(times) / total
+        line = {"impl": "reference", "metric": "PBS/sec", "value": value, "unit": "PBS/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": workload, "note": "CPU arm: each step bootstraps `cores` ciphertexts of the same workload, one per host thread"},
+                "cpu_baseline": {"value": value, "unit": "PBS/s", "cores": cores, "kind": "port",
+                                 "sample": f"{n_ct} PBS per step (one per host thread), C restatement of the reference's Rust path, Toeplitz O(N^2) algorithm"},
+                "e2e": {"value": value, "unit": "PBS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the PBS path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ctx = T.Context(p, local_rank)
+    stream = torch.cuda.Stream()        # a real (non-default) stream shared by torch events and the C-ABI ctx
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)  # so torch CUDA events bracket exactly the kernels of this ctx
+    bk = ctx.upload_key(bsk, ksk)
+
+    B = args.batch
+    base = rank * B
+    n_unique = min(B, 256)  # encrypt 256 distinct ciphertexts, tile to the batch (timing is data independent)
+    uniq = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, (base + i) % pm), 1, base + i) for i in range(n_unique)])
+    host_in = torch.from_numpy(np.tile(uniq, ((B + n_unique - 1) // n_unique, 1))[:B].view(np.int32).copy()).pin_memory()
+    host_out = torch.empty((B, p.n + 1), dtype=torch.int32).pin_memory()
+    host_tv = torch.from_numpy(tv.view(np.int32).copy()).pin_memory()
+    d_in, d_tv = host_in.cuda(), host_tv.cuda()
+    d_out = torch.empty((B, p.n + 1), dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    peaks = ctx.measure_int_peak()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(kind, nsteps, timed):
+        evs, kern_ms = [], []
+        for _ in range(nsteps):
+            flush.zero_()  # L2 flush between iterations (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if kind == "device":
+                ctx.bootstrap(bk, d_in, d_tv, out=d_out)
+            else:
+                ctx.bootstrap(bk, host_in, host_tv, out=host_out)
+            e1.record(stream)
+            evs.append((e0, e1))
+            kern_ms.append(ctx.last_timing())
+        torch.cuda.synchronize()
+        return [a.elapsed_time(b) for a, b in evs], kern_ms
+
+    # ---- device-resident (value)
+    run("device", args.warmup, False)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = ctx.launch_count
+    sampler.start()
+    step_ms, kern = run("device", args.steps, True)
+    barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    # ---- end to end through the C-ABI with pinned host buffers
+    run("host", 1, False)
+    barrier()
+    e2e_ms, _ = run("host", args.steps, True)
+    barrier()
+
+    # correctness of what was timed: decrypt a sample of the last outputs on this rank
+    res = d_out.cpu().numpy().view(np.uint32)
+    res_h = host_out.numpy().view(np.uint32)
+    assert np.array_equal(res, res_h), "device-pointer and host-pointer paths disagree"
+    for i in range(0, B, max(1, B // 64)):
+        assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, res[i])) == (base + i % n_unique) % pm, f"PBS {i} decrypts wrongly"
+
+    t_dev, t_e2e = sum(step_ms), sum(e2e_ms)
+    t_br = sum(k["blind_rotate_ms"] for k in kern) / len(kern)
+    t_ks = sum(k["key_switch_ms"] for k in kern) / len(kern)
+    if world > 1:
+        tt = torch.tensor([t_dev, t_e2e, t_br], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e, t_br = tt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_pbs = world * B * args.steps
+    value = total_pbs / (t_dev * 1e-3)
+    e2e_value = total_pbs / (t_e2e * 1e-3)
+    # roofline of the dominant kernel (blind rotation): algorithmic IMAD-class ops per launch / its device time
+    ops_per_launch = B * p.n * c_cmux
+    achieved = ops_per_launch / (t_br * 1e-3)
+    bsk_bytes = 2 * p.bsk_words * 4
+    waves = -(-B // (148 * 4))
+    hbm_alg = bsk_bytes * waves + B * (p.n + 1) * 4 + B * p.glwe_words * 4
+    roofline = {"bound": "int32-imad", "achieved": achieved / 1e12, "peak": peaks["imad"] / 1e12, "unit": "T IMAD-class lane-ops/s",
+                "frac": achieved / peaks["imad"], "traffic": None, "kernel": "pbs_kernel (blind rotation)", "kernel_ms": t_br,
+                "peak_source": "measured live: tfhe_measure_int_peak (dependent-free IMAD loop); imad_hi / imad_wide alongside",
+                "peaks": {k: v / 1e12 for k, v in peaks.items()},
+                "algorithmic_ops_per_launch": ops_per_launch,
+                "hbm": {"algorithmic_bytes_per_launch": hbm_alg, "achieved_gbs": hbm_alg / (t_br * 1e-3) / 1e9, "peak_gbs": 6548.5,
+                        "frac": hbm_alg / (t_br * 1e-3) / 1e9 / 6548.5, "note": "not the binding roofline (integer pipe binds by >100x)"}}
+    line = {"metric": "PBS/sec", "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+            "data": "synthetic",
+            "config": {"workload": workload, "l2": "256 MB flush write between timed iterations", "keys": "replicated per GPU",
+                       "latency_ms_per_pbs_batch": t_dev / args.steps, "key_switch_ms": t_ks},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "PBS/s", "h2d_bytes_per_step": int(host_in.numel() * 4 + host_tv.numel() * 4),
+                    "d2h_bytes_per_step": int(host_out.numel() * 4)},
+            "roofline": roofline}
+    if world == 1 and not args.no_cpu_baseline:
+        n_ct = 3 * cores
+        cts = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(n_ct)])
+        rate, dt, out = cpu_reference_rate(fields, n_ct, cores, bsk, ksk, cts, tv)
+        gpu_same = ctx.bootstrap(bk, cts, tv)
+        assert np.array_equal(gpu_same, out), "GPU result differs from the CPU oracle on the baseline sample"
+        line["cpu_baseline"] = {"value": rate, "unit": "PBS/s", "cores": cores, "kind": "port",
+                                "sample": f"{n_ct} PBS of the same workload, one per host thread, {dt:.1f} s; C restatement of the reference's "
+                                          "Rust path (Toeplitz O(N^2)); GPU output verified bit-identical on this sample"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

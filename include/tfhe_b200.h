@@ -1,0 +1,151 @@
+/*
+ * tfhe_b200.h -- C ABI of the B200-native TFHE programmable-bootstrapping path.
+ *
+ * Drop-in boundary for the hot path of Janmajayamall/tfhe-research (a Rust crate with no FFI of its
+ * own): every entry point below replaces one crate-internal function and keeps its
+ * argument meaning, data layout (flat little-endian u32, row-major, exactly the ndarray layouts of
+ * the reference) and bit-exact results.  Citations are `file:line` into the reference's src/.
+ * INTEGRATION.md shows the Rust `extern "C"` shim a maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative tfhe_status; nothing unwinds across the ABI
+ *    (the reference panics via assert!/unwrap -- those sites map to TFHE_E_ASSERT);
+ *  - a tfhe_ctx is bound to ONE CUDA device and is single-caller, like the reference's synchronous
+ *    single-threaded calls; multi-GPU = one process (one ctx) per GPU, batches sharded by the caller;
+ *  - pointer arguments of the batched device entry points may be host OR device pointers (queried
+ *    with cudaPointerGetAttributes); host buffers are staged through the ctx's pinned buffers;
+ *  - there is NO CPU fallback: device entry points fail with TFHE_E_CUDA when no GPU is present.
+ *
+ * Layouts:  N = 2^log_poly_degree, k = glwe_dimension, n = lwe_dimension,
+ *  l = pbs_levels, l_ks = ks_levels.
+ *   LWE  ciphertext  u32[n+1]                 (a_0..a_{n-1}, b)  body LAST        lwe.rs:110-115
+ *   GLWE ciphertext  u32[k+1][N]              rows 0..k-1 masks, row k body       glwe.rs:186-188
+ *   GGSW ciphertext  u32[(k+1)*l][k+1][N]     row = poly*l + level                ggsw.rs:37-41
+ *   BSK              u32[n][(k+1)*l][k+1][N]                                      bootstrapping.rs:18-21
+ *   KSK              u32[k*N*l_ks][n+1]       row = s_index*l_ks + level          key_switching.rs:13-15
+ */
+#ifndef TFHE_B200_H
+#define TFHE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum tfhe_status {
+    TFHE_OK = 0,
+    TFHE_E_PARAM = -1,   /* invalid / unsupported parameter set or argument */
+    TFHE_E_CUDA = -2,    /* CUDA runtime error, or no CUDA device (there is no CPU fallback) */
+    TFHE_E_OOM = -3,
+    TFHE_E_ASSERT = -4,  /* a reference assert! would have fired (glwe.rs:144, lwe.rs:84, test_vector.rs:41, bootstrapping.rs:127) */
+    TFHE_E_NCCL = -5
+} tfhe_status;
+
+/* lib.rs:23-34 TfheParams (glwe_poly_degree holds log2 N exactly like the reference's field) */
+typedef struct tfhe_params {
+    uint32_t glwe_dimension;
+    uint32_t glwe_poly_degree; /* log2 N */
+    uint32_t lwe_dimension;
+    uint32_t padding_bits;
+    uint32_t log_p;
+    uint32_t log_q;            /* must be 32 */
+    uint32_t ks_log_base, ks_levels;
+    uint32_t pbs_log_base, pbs_levels;
+    double lwe_std_dev, glwe_std_dev;
+} tfhe_params;
+
+/* lib.rs:76-124 `impl Default for TfheParams`; test_cfg != 0 gives the cfg(test) variant (n = 4). */
+int tfhe_params_default(int test_cfg, tfhe_params *out);
+/* Named presets of SURVEY 8(d): "P0" (= default), "P0t" (= cfg(test)), "P1", "P2". */
+int tfhe_params_preset(const char *name, tfhe_params *out);
+/* TFHE_E_PARAM unless: log_q == 32, log_base | 32, log_base*levels <= 32 (decomposer.rs, H2),
+ * 2^log_p | N, and (N, k, l, log_base) is one of the instantiated kernel configurations. */
+int tfhe_params_validate(const tfhe_params *p);
+
+/* gate opcodes for tfhe_gate_batch / tfhe_test_vector_boolean.  AND, OR follow boolean.rs:9-53; XOR is
+ * the same construction with f = l ^ r; NAND/NOR/XNOR are trivial(1) - gate. */
+typedef enum tfhe_gate { TFHE_AND = 0, TFHE_OR = 1, TFHE_XOR = 2, TFHE_NAND = 3, TFHE_NOR = 4, TFHE_XNOR = 5 } tfhe_gate;
+
+/* ------------------------------------------------------------------ host-side (C++) mirror */
+/* test_vector.rs:38-67 / :23-35 / :5-20 */
+int tfhe_test_vector_from_lut(const tfhe_params *p, const uint32_t *lut, size_t lut_len, uint32_t *tv_out /* N */);
+int tfhe_test_vector_identity(const tfhe_params *p, uint32_t *tv_out /* N */);
+int tfhe_test_vector_boolean(const tfhe_params *p, int gate /* AND, OR or XOR */, uint32_t *tv_out /* N */);
+/* lwe.rs:83-88 / :102-107 (decode is the reference's floor shift, H5) / :138-160 / :162-173 */
+int tfhe_lwe_encode(const tfhe_params *p, uint32_t message, uint32_t *plaintext_out);
+int tfhe_lwe_decode(const tfhe_params *p, uint32_t plaintext, uint32_t *message_out);
+int tfhe_lwe_encrypt(const tfhe_params *p, const uint32_t *lwe_sk, size_t sk_len, uint32_t plaintext, uint64_t seed,
+                     uint64_t index, uint32_t *ct_out /* sk_len+1 */);
+int tfhe_lwe_decrypt(const uint32_t *lwe_sk, size_t sk_len, const uint32_t *ct, uint32_t *plaintext_out);
+/* bootstrapping.rs:23-56 bootstrapping_key_gen (+ LweSecretKey::random lwe.rs:54-58, GlweSecretKey::random
+ * glwe.rs:177-181).  Seeded (thread_rng is not reproducible); multi-threaded on the host. */
+int tfhe_keygen(const tfhe_params *p, uint64_t seed, uint32_t *lwe_sk /* n */, uint32_t *glwe_sk /* k*N */,
+                uint32_t *bsk, uint32_t *ksk);
+
+/* ------------------------------------------------------------------ device context and keys */
+typedef struct tfhe_ctx tfhe_ctx;
+typedef struct tfhe_bk tfhe_bk; /* device-resident BootstrappingKey (bootstrapping.rs:18-21) */
+
+int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out);
+void tfhe_ctx_destroy(tfhe_ctx *ctx);
+const char *tfhe_last_error(const tfhe_ctx *ctx);
+/* Run all subsequent work of this ctx on an existing CUDA stream (cudaStream_t as void*); NULL = own stream. */
+int tfhe_ctx_set_stream(tfhe_ctx *ctx, void *cuda_stream);
+/* Kernels launched by this ctx since creation (the bench's gpu_launches claim). */
+uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx);
+
+/* Copies BSK+KSK (host or device pointers) to the ctx's device and transforms the BSK into the 2-prime
+ * NTT domain (kernel K0).  The caller keeps ownership of the inputs. */
+int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe_bk **out);
+void tfhe_bk_free(tfhe_bk *bk);
+
+/* ------------------------------------------------------------------ the hot path */
+/* bootstrapping.rs:58-120 `bootstrap`, batched.  luts = T unencoded test vectors [T][N] (values < 2^log_p,
+ * else TFHE_E_ASSERT like glwe.rs:144); lut_idx[b] selects the test vector of ciphertext b (NULL: all 0). */
+int tfhe_bootstrap_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in /* [B][n+1] */,
+                         const uint32_t *luts /* [T][N] */, size_t n_luts, const uint32_t *lut_idx /* [B] or NULL */,
+                         size_t batch, uint32_t *lwe_out /* [B][n+1] */);
+/* boolean.rs:9-53 `and`/`or` (+ XOR/NAND/NOR/XNOR), batched: ct_in = 2*ct1 + ct0, then bootstrap. */
+int tfhe_gate_batch(tfhe_ctx *ctx, const tfhe_bk *bk, int gate, const uint32_t *ct0, const uint32_t *ct1, size_t batch,
+                    uint32_t *out);
+/* Same with one opcode per ciphertext (mixed-gate circuit level). gates[b] in tfhe_gate. */
+int tfhe_gates_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint8_t *gates /* [B], host */, const uint32_t *ct0,
+                     const uint32_t *ct1, size_t batch, uint32_t *out);
+
+/* ------------------------------------------------------------------ sub-operations (parity tests) */
+/* utils.rs:23-33 switch_modulus(values, 32, log2(N)+1) */
+int tfhe_switch_modulus(tfhe_ctx *ctx, const uint32_t *values, size_t len, uint32_t *out);
+/* decomposer.rs:42-80 with the PBS (which=0) or KS (which=1) decomposer: out[len][levels], wrapped u32 digits */
+int tfhe_decompose(tfhe_ctx *ctx, int which, const uint32_t *values, size_t len, uint32_t *out);
+/* glwe.rs:20-34: out[b] = glwe[b] * X^{index[b]} (index as in Monomial, may be negative) */
+int tfhe_glwe_mul_monomial(tfhe_ctx *ctx, const uint32_t *glwe /* [B][k+1][N] */, const int64_t *index /* [B], host */,
+                           size_t batch, uint32_t *out);
+/* ggsw.rs:132-161: out[b] = external_product(BSK[ggsw_index[b]], glwe[b]) */
+int tfhe_external_product(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *ggsw_index /* [B], host */,
+                          const uint32_t *glwe, size_t batch, uint32_t *out);
+/* ggsw.rs:164-178: out[b] = cmux(BSK[ggsw_index[b]], ct0[b], ct1[b]); unlike the reference ct1 is NOT clobbered (H8) */
+int tfhe_cmux(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *ggsw_index /* [B], host */, const uint32_t *ct0,
+              const uint32_t *ct1, size_t batch, uint32_t *out);
+/* bootstrapping.rs:67-105: mod switch, X^{-b} v(X), n CMUXes; returns the accumulator GLWEs [B][k+1][N] */
+int tfhe_blind_rotate(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, const uint32_t *luts, size_t n_luts,
+                      const uint32_t *lut_idx, size_t batch, uint32_t *glwe_out);
+/* bootstrapping.rs:122-156 with sample_index 0: [B][k+1][N] -> [B][kN+1] */
+int tfhe_sample_extract(tfhe_ctx *ctx, const uint32_t *glwe, size_t batch, uint32_t *lwe_out);
+/* key_switching.rs:63-103: [B][kN+1] -> [B][n+1] */
+int tfhe_key_switch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, size_t batch, uint32_t *lwe_out);
+/* lwe.rs:9-23 as used by boolean.rs:18: out = 2*ct1 + ct0 */
+int tfhe_gate_linear(tfhe_ctx *ctx, const uint32_t *ct0, const uint32_t *ct1, size_t batch, uint32_t *out);
+
+/* ------------------------------------------------------------------ measurement helpers */
+/* Measures the integer-pipe peaks of this device with dependent-free unrolled loops:
+ * out[0] = 32-bit IMAD lane-ops/s, out[1] = IMAD.HI (mul.hi.u32), out[2] = IMAD.WIDE (mad.wide.u32). */
+int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[3]);
+/* Device time (ms, CUDA events on the ctx stream) of the last tfhe_bootstrap_batch / tfhe_gate(s)_batch:
+ * out[0] blind rotation kernel, out[1] key-switch kernels, out[2] whole call incl. copies. */
+int tfhe_last_timing(const tfhe_ctx *ctx, double out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,190 @@
+"""GPU parity tests: every entry point of the C-ABI vs the CPU oracle, bit for bit (-m gpu).
+
+Sizes are chosen so the oracle (reference algorithm, O(N^2) products) finishes in seconds: full
+polynomial sizes, small LWE dimension n (every CMUX step runs the same code; n only sets the loop
+count), plus a few full-n cases.  Full-size batches are covered by size-independent properties
+(decrypt-level correctness, batch-invariance, determinism) in test_gpu_fullsize.py.
+"""
+import numpy as np
+import pytest
+
+import tfhe_research_b200 as T
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+FIELDS = [f for f, _ in T.TfheParams._fields_]
+
+
+def oparams(p):
+    return orc.params(**{f: getattr(p, f) for f in FIELDS})
+
+
+class Env:
+    def __init__(self, preset, n, seed=0xB200):
+        self.p = T.TfheParams.preset(preset, lwe_dimension=n)
+        self.o = oparams(self.p)
+        self.lwe_sk, self.glwe_sk, self.bsk, self.ksk = T.bootstrapping_key_gen(self.p, seed)
+        self.ctx = T.Context(self.p, 0)
+        self.bk = self.ctx.upload_key(self.bsk, self.ksk)
+
+    def enc(self, m, idx, seed=1):
+        return T.encrypt_lwe_plaintext(self.p, self.lwe_sk, T.encode_message(self.p, m), seed, idx)
+
+    def dec(self, ct):
+        return T.decode_rounded(self.p, T.decrypt_lwe(self.lwe_sk, ct))
+
+
+_envs = {}
+
+
+def env(preset, n):
+    key = (preset, n)
+    if key not in _envs:
+        _envs[key] = Env(preset, n)
+    return _envs[key]
+
+
+CASES = [("P0", 4), ("P1", 3), ("P2", 2)]
+
+
+def r32(rng, *shape):
+    return rng.integers(0, 1 << 32, shape, dtype=np.uint64).astype(np.uint32)
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_switch_modulus_decompose_monomial(preset, n):
+    e = env(preset, n)
+    rng = np.random.default_rng(1)
+    L = orc.lib()
+    import ctypes as C
+    edge = np.array([0, 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF, 0x0000F800, 0x0FF80000, 0xF8F8F8F8, 0x7FFFFF80, 0x80, 0xABCDEF12,
+                     0x001FFFFF, 0x00200000, 0xFFDFFFFF, 0xFFE00000], dtype=np.uint32)
+    v = np.concatenate([edge, r32(rng, 5000)])
+    exp = orc.z(len(v))
+    L.orc_switch_modulus(v, len(v), 32, e.p.glwe_poly_degree + 1, exp)
+    assert np.array_equal(e.ctx.switch_modulus(v), exp)
+    for which, (lb, lv) in enumerate(((e.p.pbs_log_base, e.p.pbs_levels), (e.p.ks_log_base, e.p.ks_levels))):
+        got = e.ctx.decompose(v, which)
+        d = orc.z(lv)
+        for i in range(0, len(v), 7):
+            L.orc_decompose(int(v[i]), lb, lv, d)
+            assert np.array_equal(got[i], d), hex(int(v[i]))
+    N = e.p.N
+    glwe = r32(rng, 6, e.p.k + 1, N)
+    idx = np.array([0, 1, N, 2 * N - 1, -1, -(N + 3)], dtype=np.int64)
+    got = e.ctx.glwe_mul_monomial(glwe, idx)
+    for b in range(6):
+        o = orc.z((e.p.k + 1) * N)
+        L.orc_glwe_mul_monomial(C.byref(e.o), glwe[b].reshape(-1), int(idx[b]), o)
+        assert np.array_equal(got[b].reshape(-1), o)
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_external_product_and_cmux(preset, n):
+    import ctypes as C
+    e = env(preset, n)
+    rng = np.random.default_rng(2)
+    L = orc.lib()
+    B, gsz, gg = 5, e.p.glwe_words, e.p.ggsw_words
+    glwe0, glwe1 = r32(rng, B, e.p.k + 1, e.p.N), r32(rng, B, e.p.k + 1, e.p.N)
+    glwe0[0, 0, :8] = [0xFFFFFFFF, 0x7FFFFF80, 0x0000F800, 0xF8F8F8F8, 0, 0x80000000, 0x0FF80000, 0x00FFFFFF]
+    gi = np.array([i % n for i in range(B)], dtype=np.uint32)
+    got = e.ctx.external_product(e.bk, gi, glwe0)
+    for b in range(B):
+        o = orc.z(gsz)
+        L.orc_external_product(C.byref(e.o), e.bsk[int(gi[b]) * gg:(int(gi[b]) + 1) * gg], glwe0[b].reshape(-1), o)
+        assert np.array_equal(got[b].reshape(-1), o), b
+    got = e.ctx.cmux(e.bk, gi, glwe0, glwe1)
+    for b in range(B):
+        o = orc.z(gsz)
+        c1 = glwe1[b].copy().reshape(-1)
+        L.orc_cmux(C.byref(e.o), e.bsk[int(gi[b]) * gg:(int(gi[b]) + 1) * gg], glwe0[b].reshape(-1), c1, o)
+        assert np.array_equal(got[b].reshape(-1), o), b
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_blind_rotate_extract_keyswitch_bootstrap(preset, n):
+    import ctypes as C
+    e = env(preset, n)
+    L = orc.lib()
+    rng = np.random.default_rng(3)
+    pm = 1 << e.p.log_p
+    B = 9
+    cts = np.stack([e.enc(i % pm, i) for i in range(B)])
+    cts[B - 1] = r32(rng, n + 1)                    # arbitrary (non-ciphertext) words are legal inputs too
+    cts[B - 2, :n] = 0                               # every a~_i == 0: all CMUX steps skipped
+    tvs = np.stack([T.construct_identity_test_vector(e.p), rng.integers(0, pm, e.p.N).astype(np.uint32)])
+    idx = np.array([b % 2 for b in range(B)], dtype=np.uint32)
+    acc = e.ctx.blind_rotate(e.bk, cts, tvs, idx)
+    ext = e.ctx.sample_extract(acc)
+    ks = e.ctx.key_switch(e.bk, ext)
+    out = e.ctx.bootstrap(e.bk, cts, tvs, idx)
+    for b in range(B):
+        exp_acc = orc.blind_rotate(e.o, cts[b], e.bsk, tvs[idx[b]])
+        assert np.array_equal(acc[b], exp_acc), b
+        exp_ext = orc.z(e.p.k * e.p.N + 1)
+        L.orc_sample_extract(C.byref(e.o), exp_acc.reshape(-1), 0, exp_ext)
+        assert np.array_equal(ext[b], exp_ext), b
+        exp_ks = orc.z(n + 1)
+        L.orc_key_switch_lwe(C.byref(e.o), exp_ext, e.ksk, exp_ks)
+        assert np.array_equal(ks[b], exp_ks), b
+        assert np.array_equal(out[b], orc.bootstrap(e.o, cts[b], e.bsk, e.ksk, tvs[idx[b]])), b
+    for b in range(0, B - 2, 2):                     # identity LUT ciphertexts decrypt to their message
+        assert e.dec(out[b]) == b % pm
+
+
+@pytest.mark.parametrize("preset,n", [("P0", 4), ("P1", 3)])
+def test_gates_boolean_rs(preset, n):
+    e = env(preset, n)
+    fs = [lambda a, b: a & b, lambda a, b: a | b, lambda a, b: a ^ b,
+          lambda a, b: 1 - (a & b), lambda a, b: 1 - (a | b), lambda a, b: 1 - (a ^ b)]
+    ct0 = np.stack([e.enc(i & 1, 100 + i) for i in range(4)])
+    ct1 = np.stack([e.enc((i >> 1) & 1, 200 + i) for i in range(4)])
+    lin = e.ctx.gate_linear(ct0, ct1)
+    assert np.array_equal(lin, (ct1 * np.uint32(2) + ct0).astype(np.uint32))
+    for op, f in enumerate(fs):
+        out = e.ctx.gate(e.bk, op, ct0, ct1)
+        for i in range(4):
+            assert np.array_equal(out[i], orc.gate(e.o, op, ct0[i], ct1[i], e.bsk, e.ksk)), (op, i)
+            assert e.dec(out[i]) == f((i >> 1) & 1, i & 1), (op, i)
+    ops = np.array([0, 3, 2, 5], dtype=np.uint8)     # mixed gates in one batch
+    out = e.ctx.gate(e.bk, ops, ct0, ct1)
+    for i in range(4):
+        assert np.array_equal(out[i], orc.gate(e.o, int(ops[i]), ct0[i], ct1[i], e.bsk, e.ksk))
+
+
+def test_encode_assert_and_errors():
+    e = env("P0", 4)
+    bad = np.full(e.p.N, 4, dtype=np.uint32)        # >= 2^log_p: assert! glwe.rs:144
+    with pytest.raises(T.TfheError) as ei:
+        e.ctx.bootstrap(e.bk, np.zeros((1, 5), dtype=np.uint32), bad)
+    assert ei.value.code == T.TFHE_E_ASSERT
+    with pytest.raises(T.TfheError) as ei:
+        e.ctx.external_product(e.bk, np.array([99], dtype=np.uint32), np.zeros((1, 3, 512), dtype=np.uint32))
+    assert ei.value.code == T.TFHE_E_PARAM
+    # empty batch is a no-op
+    out = e.ctx.bootstrap(e.bk, np.zeros((0, 5), dtype=np.uint32), T.construct_identity_test_vector(e.p))
+    assert out.shape == (0, 5)
+
+
+def test_device_pointers_torch():
+    import torch
+    e = env("P0", 4)
+    cts = np.stack([e.enc(i % 4, 300 + i) for i in range(8)])
+    tv = T.construct_identity_test_vector(e.p)
+    ref = e.ctx.bootstrap(e.bk, cts, tv)
+    d_in = torch.from_numpy(cts.view(np.int32)).cuda()
+    d_tv = torch.from_numpy(tv.view(np.int32)).cuda()
+    d_out = e.ctx.bootstrap(e.bk, d_in, d_tv)
+    assert d_out.is_cuda
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), ref)
+
+
+def test_reference_defaults_full_n_one_gate():
+    """BASELINE config #1: one bootstrapped NAND with the reference's non-test defaults (n = 722)."""
+    e = env("P0", 722)
+    ct0, ct1 = e.enc(1, 1)[None], e.enc(1, 2)[None]
+    out = e.ctx.gate(e.bk, T.NAND, ct0, ct1)
+    assert np.array_equal(out[0], orc.gate(e.o, 3, ct0[0], ct1[0], e.bsk, e.ksk))
+    assert e.dec(out[0]) == 0

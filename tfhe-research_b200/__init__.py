@@ -1,0 +1,410 @@
+"""tfhe-research_b200 -- host-side mirror of the reference's API over the C-ABI library.
+
+The Rust toolchain is absent from this image, so the host side above `include/tfhe_b200.h` is this
+thin ctypes layer; function names and argument meaning follow the reference crate
+(bootstrapping.rs, boolean.rs, test_vector.rs, lwe.rs).  All arithmetic happens inside
+`libtfhe_b200.so` (hand-written CUDA for sm_100a + C++ host code).  There is NO CPU fallback: if the
+library is missing, or no GPU is visible, the device entry points raise.
+
+Import it as `tfhe_research_b200` (the root-level shim module) -- a directory name with a hyphen is
+not importable directly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libtfhe_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"]
+_SOURCES = ["tfhe_b200.cu", "host_api.cpp"]
+_DEPS = _SOURCES + ["kernels.cuh", "pbs_team.cuh", "tfhe_core.cuh", "host_tables.hpp", "api_internal.hpp",
+                    os.path.join("..", "..", "include", "tfhe_b200.h")]
+
+TFHE_OK, TFHE_E_PARAM, TFHE_E_CUDA, TFHE_E_OOM, TFHE_E_ASSERT, TFHE_E_NCCL = 0, -1, -2, -3, -4, -5
+AND, OR, XOR, NAND, NOR, XNOR = range(6)
+
+
+class TfheError(RuntimeError):
+    def __init__(self, code, msg=""):
+        names = {-1: "TFHE_E_PARAM", -2: "TFHE_E_CUDA", -3: "TFHE_E_OOM", -4: "TFHE_E_ASSERT", -5: "TFHE_E_NCCL"}
+        super().__init__(f"{names.get(code, code)}: {msg}")
+        self.code = code
+
+
+class TfheParams(C.Structure):
+    """lib.rs:23-34 (glwe_poly_degree holds log2 N, as in the reference)."""
+    _fields_ = [("glwe_dimension", C.c_uint32), ("glwe_poly_degree", C.c_uint32), ("lwe_dimension", C.c_uint32),
+                ("padding_bits", C.c_uint32), ("log_p", C.c_uint32), ("log_q", C.c_uint32),
+                ("ks_log_base", C.c_uint32), ("ks_levels", C.c_uint32), ("pbs_log_base", C.c_uint32),
+                ("pbs_levels", C.c_uint32), ("lwe_std_dev", C.c_double), ("glwe_std_dev", C.c_double)]
+
+    @classmethod
+    def default(cls, test_cfg: bool = False):
+        p = cls()
+        _check(lib().tfhe_params_default(1 if test_cfg else 0, C.byref(p)))
+        return p
+
+    @classmethod
+    def preset(cls, name: str, **over):
+        p = cls()
+        _check(lib().tfhe_params_preset(name.encode(), C.byref(p)), f"unknown preset {name}")
+        for k, v in over.items():
+            setattr(p, k, v)
+        return p
+
+    N = property(lambda s: 1 << s.glwe_poly_degree)
+    k = property(lambda s: s.glwe_dimension)
+    n = property(lambda s: s.lwe_dimension)
+    glwe_words = property(lambda s: (s.k + 1) * s.N)
+    ggsw_words = property(lambda s: (s.k + 1) * s.pbs_levels * (s.k + 1) * s.N)
+    bsk_words = property(lambda s: s.n * s.ggsw_words)
+    ksk_words = property(lambda s: s.k * s.N * s.ks_levels * (s.n + 1))
+
+    def validate(self):
+        _check(lib().tfhe_params_validate(C.byref(self)), "unsupported parameter set")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libtfhe_b200.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    deps = [os.path.join(_CSRC, d) for d in _DEPS]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_PATH) for d in deps):
+        return LIB_PATH
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + [os.path.join(_CSRC, s) for s in _SOURCES]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB_PATH
+
+
+_LIB = None
+u32p = C.c_void_p  # host numpy pointer or device pointer
+
+
+def lib():
+    """Load the C-ABI library; fails loudly when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    PP, VP, SZ = C.POINTER(TfheParams), C.c_void_p, C.c_size_t
+    sig = {
+        "tfhe_params_default": [C.c_int, PP], "tfhe_params_preset": [C.c_char_p, PP], "tfhe_params_validate": [PP],
+        "tfhe_test_vector_from_lut": [PP, VP, SZ, VP], "tfhe_test_vector_identity": [PP, VP],
+        "tfhe_test_vector_boolean": [PP, C.c_int, VP],
+        "tfhe_lwe_encode": [PP, C.c_uint32, C.POINTER(C.c_uint32)], "tfhe_lwe_decode": [PP, C.c_uint32, C.POINTER(C.c_uint32)],
+        "tfhe_lwe_encrypt": [PP, VP, SZ, C.c_uint32, C.c_uint64, C.c_uint64, VP],
+        "tfhe_lwe_decrypt": [VP, SZ, VP, C.POINTER(C.c_uint32)],
+        "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP],
+        "tfhe_ctx_create": [PP, C.c_int, C.POINTER(VP)], "tfhe_ctx_set_stream": [VP, VP],
+        "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)],
+        "tfhe_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP],
+        "tfhe_gate_batch": [VP, VP, C.c_int, VP, VP, SZ, VP], "tfhe_gates_batch": [VP, VP, VP, VP, VP, SZ, VP],
+        "tfhe_switch_modulus": [VP, VP, SZ, VP], "tfhe_decompose": [VP, C.c_int, VP, SZ, VP],
+        "tfhe_glwe_mul_monomial": [VP, VP, VP, SZ, VP],
+        "tfhe_external_product": [VP, VP, VP, VP, SZ, VP], "tfhe_cmux": [VP, VP, VP, VP, VP, SZ, VP],
+        "tfhe_blind_rotate": [VP, VP, VP, VP, SZ, VP, SZ, VP],
+        "tfhe_sample_extract": [VP, VP, SZ, VP], "tfhe_key_switch": [VP, VP, VP, SZ, VP],
+        "tfhe_gate_linear": [VP, VP, VP, SZ, VP],
+        "tfhe_measure_int_peak": [VP, C.POINTER(C.c_double * 3)], "tfhe_last_timing": [VP, C.POINTER(C.c_double * 3)],
+    }
+    for name, args in sig.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = C.c_int
+    L.tfhe_ctx_destroy.argtypes = [VP]; L.tfhe_ctx_destroy.restype = None
+    L.tfhe_bk_free.argtypes = [VP]; L.tfhe_bk_free.restype = None
+    L.tfhe_last_error.argtypes = [VP]; L.tfhe_last_error.restype = C.c_char_p
+    L.tfhe_ctx_launch_count.argtypes = [VP]; L.tfhe_ctx_launch_count.restype = C.c_uint64
+    _LIB = L
+    return L
+
+
+EXPORTS = [
+    "tfhe_params_default", "tfhe_params_preset", "tfhe_params_validate", "tfhe_test_vector_from_lut",
+    "tfhe_test_vector_identity", "tfhe_test_vector_boolean", "tfhe_lwe_encode", "tfhe_lwe_decode", "tfhe_lwe_encrypt",
+    "tfhe_lwe_decrypt", "tfhe_keygen", "tfhe_ctx_create", "tfhe_ctx_destroy", "tfhe_last_error", "tfhe_ctx_set_stream",
+    "tfhe_ctx_launch_count", "tfhe_bk_upload", "tfhe_bk_free", "tfhe_bootstrap_batch", "tfhe_gate_batch",
+    "tfhe_gates_batch", "tfhe_switch_modulus", "tfhe_decompose", "tfhe_glwe_mul_monomial", "tfhe_external_product",
+    "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
+    "tfhe_measure_int_peak", "tfhe_last_timing",
+]
+
+
+def _check(rc, msg=""):
+    if rc != 0:
+        raise TfheError(rc, msg)
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    """host numpy array or CUDA torch tensor -> raw pointer (kept alive by the caller)."""
+    if x is None:
+        return None
+    if _is_torch(x):
+        assert x.is_contiguous() and x.element_size() == 4
+        return x.data_ptr()
+    assert x.dtype == np.uint32 and x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data
+
+
+def _u32(x):
+    if _is_torch(x):
+        return x if x.is_contiguous() else x.contiguous()
+    return np.ascontiguousarray(x, dtype=np.uint32)
+
+
+def _like(x, shape):
+    if _is_torch(x):
+        import torch
+        return torch.empty(shape, dtype=x.dtype, device=x.device)
+    return np.empty(shape, dtype=np.uint32)
+
+
+# ------------------------------------------------------------------ host-side mirror (no GPU needed)
+def construct_test_from_lut(params: TfheParams, lut) -> np.ndarray:
+    """test_vector.rs:38-67."""
+    lut = np.ascontiguousarray(lut, dtype=np.uint32)
+    tv = np.empty(params.N, dtype=np.uint32)
+    _check(lib().tfhe_test_vector_from_lut(C.byref(params), lut.ctypes.data, len(lut), tv.ctypes.data),
+           "assert!(lut.len() == plaintext_modulus) test_vector.rs:41")
+    return tv
+
+
+def construct_identity_test_vector(params: TfheParams) -> np.ndarray:
+    """test_vector.rs:23-35."""
+    tv = np.empty(params.N, dtype=np.uint32)
+    _check(lib().tfhe_test_vector_identity(C.byref(params), tv.ctypes.data))
+    return tv
+
+
+def construct_test_vector_boolean(params: TfheParams, gate: int) -> np.ndarray:
+    """test_vector.rs:5-20 with f in {AND, OR, XOR}."""
+    tv = np.empty(params.N, dtype=np.uint32)
+    _check(lib().tfhe_test_vector_boolean(C.byref(params), gate, tv.ctypes.data))
+    return tv
+
+
+def encode_message(params: TfheParams, m: int) -> int:
+    """LweCleartext::encode_message lwe.rs:83-88."""
+    out = C.c_uint32()
+    _check(lib().tfhe_lwe_encode(C.byref(params), m, C.byref(out)), "assert!(m < 1 << log_p) lwe.rs:84")
+    return out.value
+
+
+def decode(params: TfheParams, plaintext: int) -> int:
+    """LwePlaintext::decode lwe.rs:102-107 (floor shift, no mask -- reference behaviour, H5)."""
+    out = C.c_uint32()
+    _check(lib().tfhe_lwe_decode(C.byref(params), plaintext, C.byref(out)))
+    return out.value
+
+
+def decode_rounded(params: TfheParams, plaintext: int) -> int:
+    """Harness decoder: round to the nearest message and mask (NOT the reference's decode)."""
+    shift = params.log_q - (params.log_p + params.padding_bits)
+    return ((plaintext + (1 << (shift - 1))) >> shift) & ((1 << (params.log_p + params.padding_bits)) - 1)
+
+
+def encrypt_lwe_plaintext(params: TfheParams, sk, plaintext: int, seed: int, index: int) -> np.ndarray:
+    """lwe.rs:138-160 with a seeded RNG (stream = (seed, index))."""
+    sk = np.ascontiguousarray(sk, dtype=np.uint32)
+    ct = np.empty(len(sk) + 1, dtype=np.uint32)
+    _check(lib().tfhe_lwe_encrypt(C.byref(params), sk.ctypes.data, len(sk), plaintext, seed, index, ct.ctypes.data))
+    return ct
+
+
+def decrypt_lwe(sk, ct) -> int:
+    """lwe.rs:162-173."""
+    sk = np.ascontiguousarray(sk, dtype=np.uint32)
+    ct = np.ascontiguousarray(ct, dtype=np.uint32)
+    out = C.c_uint32()
+    _check(lib().tfhe_lwe_decrypt(sk.ctypes.data, len(sk), ct.ctypes.data, C.byref(out)))
+    return out.value
+
+
+def bootstrapping_key_gen(params: TfheParams, seed: int):
+    """bootstrapping.rs:23-56 (+ the two secret keys): returns (lwe_sk, glwe_sk, bsk, ksk) flat u32 arrays."""
+    lwe_sk = np.empty(params.n, dtype=np.uint32)
+    glwe_sk = np.empty(params.k * params.N, dtype=np.uint32)
+    bsk = np.empty(params.bsk_words, dtype=np.uint32)
+    ksk = np.empty(params.ksk_words, dtype=np.uint32)
+    _check(lib().tfhe_keygen(C.byref(params), seed, lwe_sk.ctypes.data, glwe_sk.ctypes.data, bsk.ctypes.data, ksk.ctypes.data))
+    return lwe_sk, glwe_sk, bsk, ksk
+
+
+# ------------------------------------------------------------------ device side
+class BootstrappingKey:
+    """Device-resident BootstrappingKey (bootstrapping.rs:18-21): NTT-domain BSK + KSK."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self._h = ctx, handle
+
+    def free(self):
+        if self._h:
+            lib().tfhe_bk_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One CUDA device.  Inputs may be numpy arrays (host, copied in/out) or CUDA torch tensors (in place)."""
+
+    def __init__(self, params: TfheParams, device: int = 0):
+        self.params = params
+        h = C.c_void_p()
+        rc = lib().tfhe_ctx_create(C.byref(params), device, C.byref(h))
+        if rc == TFHE_E_CUDA:
+            raise TfheError(rc, "no usable CUDA device: the PBS path has no CPU fallback")
+        _check(rc, "tfhe_ctx_create")
+        self._h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TfheError(rc, (lib().tfhe_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            lib().tfhe_ctx_destroy(self._h)
+            self._h = None
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(lib().tfhe_ctx_set_stream(self._h, cuda_stream_ptr))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().tfhe_ctx_launch_count(self._h))
+
+    def upload_key(self, bsk, ksk) -> BootstrappingKey:
+        bsk, ksk = _u32(bsk), _u32(ksk)
+        h = C.c_void_p()
+        self._ck(lib().tfhe_bk_upload(self._h, _ptr(bsk), _ptr(ksk), C.byref(h)))
+        return BootstrappingKey(self, h)
+
+    # -- bootstrapping.rs:58-120, batched
+    def bootstrap(self, bk: BootstrappingKey, lwe_in, test_vectors, lut_idx=None, out=None):
+        p = self.params
+        lwe_in, tvs = _u32(lwe_in), _u32(test_vectors)
+        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
+        T = tvs.shape[0] if tvs.ndim == 2 else 1
+        idx = None if lut_idx is None else _u32(lut_idx)
+        out = _like(lwe_in, (B, p.n + 1)) if out is None else out
+        self._ck(lib().tfhe_bootstrap_batch(self._h, bk._h, _ptr(lwe_in), _ptr(tvs), T, _ptr(idx), B, _ptr(out)))
+        return out
+
+    # -- boolean.rs:9-53, batched
+    def gate(self, bk: BootstrappingKey, op, ct0, ct1, out=None):
+        p = self.params
+        ct0, ct1 = _u32(ct0), _u32(ct1)
+        B = ct0.shape[0] if ct0.ndim == 2 else 1
+        out = _like(ct0, (B, p.n + 1)) if out is None else out
+        if isinstance(op, (int, np.integer)):
+            self._ck(lib().tfhe_gate_batch(self._h, bk._h, int(op), _ptr(ct0), _ptr(ct1), B, _ptr(out)))
+        else:
+            ops = np.ascontiguousarray(op, dtype=np.uint8)
+            assert len(ops) == B
+            self._ck(lib().tfhe_gates_batch(self._h, bk._h, ops.ctypes.data, _ptr(ct0), _ptr(ct1), B, _ptr(out)))
+        return out
+
+    def and_(self, bk, ct0, ct1):
+        """boolean.rs:9-30"""
+        return self.gate(bk, AND, ct0, ct1)
+
+    def or_(self, bk, ct0, ct1):
+        """boolean.rs:32-53"""
+        return self.gate(bk, OR, ct0, ct1)
+
+    # -- sub-operations
+    def switch_modulus(self, values):
+        values = _u32(values)
+        out = _like(values, values.shape)
+        self._ck(lib().tfhe_switch_modulus(self._h, _ptr(values), values.size if not _is_torch(values) else values.numel(), _ptr(out)))
+        return out
+
+    def decompose(self, values, which=0):
+        values = _u32(values)
+        lv = self.params.ks_levels if which else self.params.pbs_levels
+        n = values.size if not _is_torch(values) else values.numel()
+        out = _like(values, (n, lv))
+        self._ck(lib().tfhe_decompose(self._h, which, _ptr(values), n, _ptr(out)))
+        return out
+
+    def glwe_mul_monomial(self, glwe, index):
+        glwe = _u32(glwe)
+        index = np.ascontiguousarray(index, dtype=np.int64)
+        out = _like(glwe, glwe.shape)
+        self._ck(lib().tfhe_glwe_mul_monomial(self._h, _ptr(glwe), index.ctypes.data, len(index), _ptr(out)))
+        return out
+
+    def external_product(self, bk, ggsw_index, glwe):
+        glwe = _u32(glwe)
+        gi = np.ascontiguousarray(ggsw_index, dtype=np.uint32)
+        out = _like(glwe, glwe.shape)
+        self._ck(lib().tfhe_external_product(self._h, bk._h, gi.ctypes.data, _ptr(glwe), len(gi), _ptr(out)))
+        return out
+
+    def cmux(self, bk, ggsw_index, ct0, ct1):
+        ct0, ct1 = _u32(ct0), _u32(ct1)
+        gi = np.ascontiguousarray(ggsw_index, dtype=np.uint32)
+        out = _like(ct0, ct0.shape)
+        self._ck(lib().tfhe_cmux(self._h, bk._h, gi.ctypes.data, _ptr(ct0), _ptr(ct1), len(gi), _ptr(out)))
+        return out
+
+    def blind_rotate(self, bk, lwe_in, test_vectors, lut_idx=None):
+        p = self.params
+        lwe_in, tvs = _u32(lwe_in), _u32(test_vectors)
+        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
+        T = tvs.shape[0] if tvs.ndim == 2 else 1
+        idx = None if lut_idx is None else _u32(lut_idx)
+        out = _like(lwe_in, (B, p.k + 1, p.N))
+        self._ck(lib().tfhe_blind_rotate(self._h, bk._h, _ptr(lwe_in), _ptr(tvs), T, _ptr(idx), B, _ptr(out)))
+        return out
+
+    def sample_extract(self, glwe):
+        p = self.params
+        glwe = _u32(glwe)
+        B = glwe.shape[0] if glwe.ndim == 3 else 1
+        out = _like(glwe, (B, p.k * p.N + 1))
+        self._ck(lib().tfhe_sample_extract(self._h, _ptr(glwe), B, _ptr(out)))
+        return out
+
+    def key_switch(self, bk, lwe_in):
+        p = self.params
+        lwe_in = _u32(lwe_in)
+        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
+        out = _like(lwe_in, (B, p.n + 1))
+        self._ck(lib().tfhe_key_switch(self._h, bk._h, _ptr(lwe_in), B, _ptr(out)))
+        return out
+
+    def gate_linear(self, ct0, ct1):
+        ct0, ct1 = _u32(ct0), _u32(ct1)
+        B = ct0.shape[0] if ct0.ndim == 2 else 1
+        out = _like(ct0, ct0.shape)
+        self._ck(lib().tfhe_gate_linear(self._h, _ptr(ct0), _ptr(ct1), B, _ptr(out)))
+        return out
+
+    def measure_int_peak(self):
+        out = (C.c_double * 3)()
+        self._ck(lib().tfhe_measure_int_peak(self._h, C.byref(out)))
+        return {"imad": out[0], "imad_hi": out[1], "imad_wide": out[2]}
+
+    def last_timing(self):
+        out = (C.c_double * 3)()
+        self._ck(lib().tfhe_last_timing(self._h, C.byref(out)))
+        return {"blind_rotate_ms": out[0], "key_switch_ms": out[1], "total_ms": out[2]}

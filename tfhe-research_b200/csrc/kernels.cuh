@@ -1,0 +1,342 @@
+// kernels.cuh -- sm_100a kernels of the PBS path.  No tensor cores: this is modular integer
+// arithmetic (IMAD / IMAD.HI / IMAD.WIDE on the FMA pipe, IADD3/LOP3/VIMNMX on the ALU pipe).
+//
+//   K2 pbs_kernel           blind rotation = n fused CMUX steps per ciphertext, accumulator resident
+//                           in shared memory (bootstrapping.rs:58-105, ggsw.rs:132-178); also runs a
+//                           single external product / CMUX for the sub-operation entry points
+//   K0 bsk_transform_kernel raw BSK -> 2-prime NTT domain, pre-scaled by N^-1 (one-off at upload)
+//   K3+K4 ks_digits_kernel / ks_gemm_kernel   sample extract + KS decomposition, then the wrapping
+//                           u32 accumulation against the KSK (bootstrapping.rs:122-156,
+//                           key_switching.rs:63-103)
+//   K5 small element-wise kernels (gate linear part lwe.rs:9-23, NAND-style negation, sub-ops)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pbs_team.cuh"
+
+namespace tfhe {
+
+// ------------------------------------------------------------------------------------------ K2
+struct PbsArgs {
+    const uint32_t *bsk_ntt;   // [n][2][ROWS][P][N] slot order, residues < q, pre-scaled by N^-1
+    TwTables tw[2];
+    // mode 0 (blind rotate)
+    const uint32_t *lwe_in;    // [B][n+1]
+    const uint32_t *luts;      // [T][N] unencoded
+    const uint32_t *lut_idx;   // [B] or nullptr
+    // mode 1 (external product: out = ExtProd(G, in0)) / mode 2 (cmux: out = ExtProd(G, in1-in0)+in0)
+    const uint32_t *in0, *in1; // [B][P][N]
+    const uint32_t *ggsw_index;  // [B]
+    uint32_t *glwe_out;        // [B][P][N]
+    uint32_t *err_flag;        // set to 1 when a test-vector entry >= 2^log_p (glwe.rs:144)
+    uint32_t n, batch, mode, log_p, enc_shift;
+};
+
+__device__ __forceinline__ void team_bar(int pr, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(pr + 1), "r"(nthreads) : "memory");
+}
+
+template <class K, int PR>
+__device__ __forceinline__ void team_cmux(TeamRegs<K> &R, uint32_t t, uint32_t jbB, const TwTables &tw, const uint8_t *dig,
+                                          uint32_t *buf0, uint32_t *buf1, uint32_t *res_pr, const uint32_t *g) {
+    team_zero_acc<K>(R);
+#pragma unroll 1
+    for (int r = 0; r < K::ROWS; r++) {
+        phase_F1<K, PR>(R, t, dig, r, buf0);
+        team_bar(PR, K::T);
+        phase_F2<K, PR>(R, jbB, tw, buf0, buf1);
+        team_bar(PR, K::T);
+        phase_F3<K, PR>(R, t, buf1, g + (size_t)r * K::P * K::N);
+    }
+}
+template <class K, int PR>
+__device__ __forceinline__ void team_inverse(TeamRegs<K> &R, uint32_t t, uint32_t jbB, const TwTables &tw, uint32_t *buf0,
+                                             uint32_t *buf1, uint32_t *res_pr) {
+    static_for<0, K::P>([&](auto ci) {
+        constexpr int c = decltype(ci)::value;
+        phase_I1<K, PR>(R, t, c, tw, buf0);
+        team_bar(PR, K::T);
+        phase_I2<K, PR>(R, jbB, tw, buf0, buf1);
+        team_bar(PR, K::T);
+        phase_I3<K, PR>(R, t, buf1, res_pr + c * K::N);
+    });
+}
+
+template <class K, int MINB>
+__global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const PbsArgs a) {
+    using C = typename K::Ntt;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem + K::SM_ACC);
+    uint8_t *dig = smem + K::SM_DIG;
+    uint32_t *res = reinterpret_cast<uint32_t *>(smem + K::SM_DIG);  // aliases dig (barrier-separated)
+    uint32_t *buf = reinterpret_cast<uint32_t *>(smem + K::SM_BUF);
+    uint16_t *at = reinterpret_cast<uint16_t *>(smem + K::SM_AT);
+
+    const uint32_t tid = threadIdx.x;
+    const uint32_t pr = tid / K::T, t = tid % K::T;  // warp-uniform: T is a multiple of 32
+    const uint32_t ct = blockIdx.x;
+    const uint32_t jbB = jbase_B<C>(t);
+    uint32_t *buf0 = buf + (pr * 2 + 0) * C::NPAD, *buf1 = buf + (pr * 2 + 1) * C::NPAD;
+    uint32_t *res_pr = res + pr * K::P * K::N;
+    constexpr size_t GGSW_WORDS = (size_t)2 * K::ROWS * K::P * K::N;
+
+    TeamRegs<K> R;
+    team_init<K>(R, a.tw[pr], t);
+
+    uint32_t n_steps;
+    if (a.mode == 0) {
+        // utils.rs:23-33 mod switch of (a_0..a_{n-1}, b) to 2N
+        const uint32_t *lwe = a.lwe_in + (size_t)ct * (a.n + 1);
+        for (uint32_t i = tid; i <= a.n; i += K::THREADS) at[i] = (uint16_t)mod_switch(__ldg(lwe + i), K::LOGN);
+        __syncthreads();
+        // acc = trivial GLWE of the encoded test vector times X^{-b~}  (bootstrapping.rs:79-86)
+        const uint32_t b = at[a.n];
+        const uint32_t *lut = a.luts + (size_t)(a.lut_idx ? __ldg(a.lut_idx + ct) : 0u) * K::N;
+        for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += K::THREADS) {
+            const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
+            uint32_t v = 0;
+            if (p == (uint32_t)K::K) {
+                const uint32_t src = (j + b) & (2u * K::N - 1u);
+                const uint32_t m = __ldg(lut + (src & (K::N - 1u)));
+                if (m >> a.log_p) atomicOr(a.err_flag, 1u);
+                v = m << a.enc_shift;
+                if (src & K::N) v = 0u - v;
+            }
+            acc[idx] = v;
+        }
+        n_steps = a.n;
+    } else {
+        const uint32_t *base = a.in0 + (size_t)ct * K::P * K::N;
+        for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += K::THREADS) acc[idx] = (a.mode == 2) ? __ldg(base + idx) : 0u;
+        n_steps = 1;
+    }
+    __syncthreads();
+
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_steps; i++) {
+        uint32_t gi = i;
+        if (a.mode == 0) {
+            const uint32_t rot = at[i];
+            if (rot == 0) continue;  // diff == 0 => external product == 0 exactly (CTA-uniform)
+            phase_digits<K>(tid, dig, [&](uint32_t p, uint32_t j) { return rot_coeff(acc + p * K::N, j, rot, K::LOGN) - acc[p * K::N + j]; });
+        } else {
+            gi = __ldg(a.ggsw_index + ct);
+            const uint32_t *x0 = a.in0 + (size_t)ct * K::P * K::N, *x1 = a.in1 + (size_t)ct * K::P * K::N;
+            if (a.mode == 1) phase_digits<K>(tid, dig, [&](uint32_t p, uint32_t j) { return __ldg(x0 + p * K::N + j); });
+            else phase_digits<K>(tid, dig, [&](uint32_t p, uint32_t j) { return __ldg(x1 + p * K::N + j) - __ldg(x0 + p * K::N + j); });
+        }
+        __syncthreads();
+        const uint32_t *g = a.bsk_ntt + (size_t)gi * GGSW_WORDS + (size_t)pr * (K::ROWS * K::P * K::N);
+        if (pr == 0) team_cmux<K, 0>(R, t, jbB, a.tw[0], dig, buf0, buf1, res_pr, g);
+        else team_cmux<K, 1>(R, t, jbB, a.tw[1], dig, buf0, buf1, res_pr, g);
+        __syncthreads();  // both teams are done reading dig before res (same bytes) is written
+        if (pr == 0) team_inverse<K, 0>(R, t, jbB, a.tw[0], buf0, buf1, res_pr);
+        else team_inverse<K, 1>(R, t, jbB, a.tw[1], buf0, buf1, res_pr);
+        __syncthreads();
+        phase_crt<K>(tid, res, acc);
+        __syncthreads();
+    }
+    uint32_t *out = a.glwe_out + (size_t)ct * K::P * K::N;
+    for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += K::THREADS) out[idx] = acc[idx];
+}
+
+// ------------------------------------------------------------------------------------------ K0
+// grid = number of polynomials (n*ROWS*P); block = 2T (one team per prime); in natural [n][ROWS][P][N],
+// out [n][2][ROWS][P][N].
+template <class K>
+__global__ void __launch_bounds__(K::THREADS) bsk_transform_kernel(const uint32_t *__restrict__ raw, uint32_t *__restrict__ out,
+                                                                   TwTables tw0, TwTables tw1) {
+    using C = typename K::Ntt;
+    __shared__ __align__(16) uint32_t buf[2 * 2 * C::NPAD];
+    const uint32_t tid = threadIdx.x, pr = tid / K::T, t = tid % K::T;
+    const size_t poly = blockIdx.x;  // = (i*ROWS + r)*P + c
+    const size_t i = poly / (K::ROWS * K::P), rc = poly % (K::ROWS * K::P);
+    const uint32_t *g = raw + poly * K::N;
+    uint32_t *o = out + ((i * 2 + pr) * (K::ROWS * K::P) + rc) * K::N;
+    uint32_t *buf0 = buf + (pr * 2) * C::NPAD, *buf1 = buf0 + C::NPAD;
+    const uint32_t jbB = jbase_B<C>(t);
+    TeamRegs<K> R;
+    if (pr == 0) {
+        team_init<K>(R, tw0, t);
+        phase_T1<K, 0>(R, t, g, buf0);
+        team_bar(0, K::T);
+        phase_F2<K, 0>(R, jbB, tw0, buf0, buf1);
+        team_bar(0, K::T);
+        phase_T3<K, 0>(R, t, buf1, o);
+    } else {
+        team_init<K>(R, tw1, t);
+        phase_T1<K, 1>(R, t, g, buf0);
+        team_bar(1, K::T);
+        phase_F2<K, 1>(R, jbB, tw1, buf0, buf1);
+        team_bar(1, K::T);
+        phase_T3<K, 1>(R, t, buf1, o);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K3+K4
+// Sample extraction (bootstrapping.rs:122-156, index 0) fused with the KS decomposition
+// (key_switching.rs:71-78): glwe [B][P][N] -> digits int8 [B][kN*L] (+ body b' per ciphertext).
+template <int LOGB, int L>
+__global__ void ks_digits_kernel(const uint32_t *__restrict__ glwe, int8_t *__restrict__ digits, uint32_t *__restrict__ body,
+                                 uint32_t k, uint32_t logn, uint32_t batch, int from_lwe) {
+    const uint32_t N = 1u << logn, kN = k * N;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)batch * kN) return;
+    const uint32_t b = (uint32_t)(gid / kN), idx = (uint32_t)(gid % kN);
+    uint32_t v;
+    if (from_lwe) {  // input already is an extracted LWE [B][kN+1]
+        v = glwe[(size_t)b * (kN + 1) + idx];
+        if (idx == 0) body[b] = glwe[(size_t)b * (kN + 1) + kN];
+    } else {
+        const uint32_t p = idx >> logn, tt = idx & (N - 1u);
+        const uint32_t *poly = glwe + ((size_t)b * (k + 1) + p) * N;
+        v = tt == 0 ? poly[0] : 0u - poly[N - tt];
+        if (idx == 0) body[b] = glwe[((size_t)b * (k + 1) + k) * N];
+    }
+    int32_t d[L];
+    decompose_signed<LOGB, L>(v, d);
+    int8_t *o = digits + (size_t)b * kN * L + (size_t)idx * L;
+#pragma unroll
+    for (int lev = 0; lev < L; lev++) o[lev] = (int8_t)d[lev];
+}
+
+// out[b][c] = -(sum_r D[b][r] * KSK[r][c]) (+ body[b] at c == n), wrapping u32.
+// CTA tile: 64 ciphertexts x 128 columns, 256 threads, 8x4 register micro-tile, BK = 32.
+constexpr int KS_BM = 64, KS_BN = 128, KS_BK = 32, KS_THREADS = 256;
+__global__ void __launch_bounds__(KS_THREADS) ks_gemm_kernel(const int8_t *__restrict__ digits, const uint32_t *__restrict__ ksk,
+                                                             const uint32_t *__restrict__ body, uint32_t *__restrict__ out,
+                                                             uint32_t KD, uint32_t n, uint32_t batch) {
+    __shared__ __align__(16) int32_t sD[KS_BK][KS_BM];
+    __shared__ __align__(16) uint32_t sK[KS_BK][KS_BN];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t c0 = blockIdx.x * KS_BN, b0 = blockIdx.y * KS_BM;
+    const uint32_t tx = tid % 32, ty = tid / 32;  // tx -> 4 columns, ty -> 8 rows
+    const uint32_t ncols = n + 1;
+    uint32_t accv[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) accv[i][j] = 0;
+    for (uint32_t k0 = 0; k0 < KD; k0 += KS_BK) {
+        // digits tile: 64 rows x 32 k -> sD[k][row]
+        for (uint32_t e = tid; e < KS_BM * KS_BK; e += KS_THREADS) {
+            const uint32_t row = e / KS_BK, kk = e % KS_BK;
+            const uint32_t b = b0 + row;
+            sD[kk][row] = (b < batch && k0 + kk < KD) ? (int32_t)digits[(size_t)b * KD + k0 + kk] : 0;
+        }
+        for (uint32_t e = tid; e < KS_BK * KS_BN; e += KS_THREADS) {
+            const uint32_t kk = e / KS_BN, cc = e % KS_BN;
+            const uint32_t c = c0 + cc;
+            sK[kk][cc] = (c < ncols && k0 + kk < KD) ? __ldg(ksk + (size_t)(k0 + kk) * ncols + c) : 0u;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < KS_BK; kk++) {
+            int32_t av[8];
+            uint32_t bv[4];
+            *reinterpret_cast<int4 *>(&av[0]) = *reinterpret_cast<const int4 *>(&sD[kk][ty * 8]);
+            *reinterpret_cast<int4 *>(&av[4]) = *reinterpret_cast<const int4 *>(&sD[kk][ty * 8 + 4]);
+            *reinterpret_cast<uint4 *>(&bv[0]) = *reinterpret_cast<const uint4 *>(&sK[kk][tx * 4]);
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) accv[i][j] += (uint32_t)av[i] * bv[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t b = b0 + ty * 8 + i;
+        if (b >= batch) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t c = c0 + tx * 4 + j;
+            if (c >= ncols) continue;
+            uint32_t v = 0u - accv[i][j];             // key_switching.rs:96 negate
+            if (c == n) v += body[b];                 // key_switching.rs:98-100
+            out[(size_t)b * ncols + c] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K5
+// boolean.rs:18  ct_in = 2*ct1 + ct0   (lwe.rs:9-23)
+__global__ void gate_linear_kernel(const uint32_t *__restrict__ ct0, const uint32_t *__restrict__ ct1, uint32_t *__restrict__ out, size_t len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) out[i] = ct1[i] * 2u + ct0[i];
+}
+// NAND/NOR/XNOR = trivial(1) - gate:  out[j] = -x[j];  out[n] += encode(1)   
+__global__ void gate_negate_kernel(uint32_t *__restrict__ x, const uint8_t *__restrict__ gates, int all, uint32_t n, uint32_t batch, uint32_t one) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)batch * (n + 1)) return;
+    const uint32_t b = (uint32_t)(i / (n + 1)), c = (uint32_t)(i % (n + 1));
+    if (all || gates[b] >= 3) {
+        uint32_t v = 0u - x[i];
+        if (c == n) v += one;
+        x[i] = v;
+    }
+}
+__global__ void switch_modulus_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t len, int logn) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) out[i] = mod_switch(in[i], logn);
+}
+template <int LOGB, int L>
+__global__ void decompose_kernel(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, size_t len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    int32_t d[L];
+    decompose_signed<LOGB, L>(in[i], d);
+#pragma unroll
+    for (int lev = 0; lev < L; lev++) out[i * L + lev] = (uint32_t)d[lev];
+}
+// glwe.rs:20-34: every polynomial of GLWE b times X^{rot[b]}, rot already reduced to [0, 2N)
+__global__ void mul_monomial_kernel(const uint32_t *__restrict__ in, const uint32_t *__restrict__ rot, uint32_t *__restrict__ out,
+                                    uint32_t polys_per_ct, int logn, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const uint32_t N = 1u << logn;
+    const size_t poly = i >> logn;
+    const uint32_t j = (uint32_t)(i & (N - 1u));
+    out[i] = rot_coeff(in + poly * N, j, rot[poly / polys_per_ct], logn);
+}
+__global__ void sample_extract_kernel(const uint32_t *__restrict__ glwe, uint32_t *__restrict__ out, uint32_t k, int logn, uint32_t batch) {
+    const uint32_t N = 1u << logn, kN = k * N;
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)batch * (kN + 1)) return;
+    const uint32_t b = (uint32_t)(gid / (kN + 1)), idx = (uint32_t)(gid % (kN + 1));
+    const uint32_t *g = glwe + (size_t)b * (k + 1) * N;
+    uint32_t v;
+    if (idx == kN) v = g[(size_t)k * N];
+    else {
+        const uint32_t p = idx >> logn, tt = idx & (N - 1u);
+        v = tt == 0 ? g[(size_t)p * N] : 0u - g[(size_t)p * N + N - tt];
+    }
+    out[gid] = v;
+}
+
+// ------------------------------------------------------------------------------------------ peaks
+// Integer-pipe peak microbenchmarks: 8 independent dependency chains per thread, 8-way unrolled.
+template <int KIND>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t a, uint32_t b, int iters) {
+    uint32_t x[8];
+    unsigned long long y[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x[i] = threadIdx.x + i; y[i] = x[i]; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (KIND == 0) x[i] = x[i] * a + b;                                  // IMAD
+                else if (KIND == 1) x[i] = __umulhi(x[i], a) + b;                    // IMAD.HI
+                else asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y[i]) : "r"(a), "r"(b + i));  // IMAD.WIDE
+            }
+        }
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i] + (uint32_t)y[i] + (uint32_t)(y[i] >> 32);
+    if (s == 0x12345678u) sink[0] = s;
+}
+
+}  // namespace tfhe

@@ -35,11 +35,13 @@ struct PbsCfg {
     static_assert((double)ROWS * N * (1 << LOGB) * 2147483648.0 < (double)kHalfQ0Q1, "CRT range");
     static_assert((double)ROWS * (2 * LOGN + 2) * (double)kQ1 * (double)kQ1 < 18446744073709551616.0, "u64 MAC range");
     // shared memory carve-up (bytes)
+    // dig[ROWS][N] (digits) and res[2][P][N] (inverse-NTT residues) share bytes: a CTA barrier
+    // separates the last digit read from the first residue write.
     static constexpr int SM_ACC = 0;
     static constexpr int SM_DIG = SM_ACC + P * N * 4;
-    static constexpr int SM_BUF = SM_DIG + ((ROWS * N * DIG_BYTES + 15) & ~15);
-    static constexpr int SM_RES = SM_BUF + 2 * 2 * Ntt::NPAD * 4;
-    static constexpr int SM_AT = SM_RES + 2 * P * N * 4;  // mod-switched mask (u16), n+1 entries follow
+    static constexpr int DIG_BYTES_TOTAL = ROWS * N * DIG_BYTES, RES_BYTES_TOTAL = 2 * P * N * 4;
+    static constexpr int SM_BUF = SM_DIG + (((DIG_BYTES_TOTAL > RES_BYTES_TOTAL ? DIG_BYTES_TOTAL : RES_BYTES_TOTAL) + 15) & ~15);
+    static constexpr int SM_AT = SM_BUF + 2 * 2 * Ntt::NPAD * 4;  // mod-switched mask (u16), n+1 entries follow
 };
 
 // position of natural coefficient j inside a digit row: thread t of layout A holds j = (e<<LOGT)|t
