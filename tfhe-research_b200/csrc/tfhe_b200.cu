@@ -110,9 +110,18 @@ using K0 = PbsCfg<9, 3, 2, 6, 4>;
 using K1 = PbsCfg<10, 4, 1, 3, 8>;
 using K2 = PbsCfg<11, 4, 1, 3, 8>;
 template <class K> struct MinBlocks;
-template <> struct MinBlocks<K0> { static constexpr int v = 5; };
-template <> struct MinBlocks<K1> { static constexpr int v = 4; };
-template <> struct MinBlocks<K2> { static constexpr int v = 2; };
+#ifndef TFHE_MINB_P0
+#define TFHE_MINB_P0 5
+#endif
+#ifndef TFHE_MINB_P1
+#define TFHE_MINB_P1 4
+#endif
+#ifndef TFHE_MINB_P2
+#define TFHE_MINB_P2 2
+#endif
+template <> struct MinBlocks<K0> { static constexpr int v = TFHE_MINB_P0; };
+template <> struct MinBlocks<K1> { static constexpr int v = TFHE_MINB_P1; };
+template <> struct MinBlocks<K2> { static constexpr int v = TFHE_MINB_P2; };
 
 template <class K>
 int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
