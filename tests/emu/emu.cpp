@@ -20,11 +20,14 @@ template <class K>
 struct Emu {
     using C = typename K::Ntt;
     HostTw tw;
+    PrimeTab prime[2];
     std::vector<TeamRegs<K>> regs;          // [2 primes][T]
     std::vector<uint32_t> acc, res, buf;    // shared memory images
     std::vector<uint8_t> dig;
     Emu() : regs(2 * K::T), acc(K::P * K::N), res(2 * K::P * K::N), buf(2 * 2 * C::NPAD), dig(K::ROWS * K::N * K::DIG_BYTES) {
         build_tw_tables(C::LOGN, C::LOGE, tw);
+        fill_prime_tab(0, C::LOGN, C::LOGE, prime[0]);
+        fill_prime_tab(1, C::LOGN, C::LOGE, prime[1]);
         for (int pr = 0; pr < 2; pr++)
             for (uint32_t t = 0; t < (uint32_t)K::T; t++) team_init<K>(regs[pr * K::T + t], tables(pr), t);
     }
@@ -41,10 +44,10 @@ struct Emu {
     template <int PR>
     void transform_poly(const uint32_t *g, uint32_t *out) {
         TwTables t = tables(PR);
-        for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_T1<K, PR>(regs[PR * K::T + th], th, g, bufp(PR, 0));
-        for (uint32_t th = 0; th < (uint32_t)K::T; th++)
-            phase_F2<K, PR>(regs[PR * K::T + th], jbase_B<C>(th), t, bufp(PR, 0), bufp(PR, 1));
-        for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_T3<K, PR>(regs[PR * K::T + th], th, bufp(PR, 1), out);
+        const PrimeTab &pt = prime[PR];
+        for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_T1<K>(regs[PR * K::T + th], th, jbase_B<C>(th), pt, t, g, bufp(PR, 0));
+        for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F2<K>(regs[PR * K::T + th], jbase_B<C>(th), pt, bufp(PR, 0), bufp(PR, 1));
+        for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_T3<K>(regs[PR * K::T + th], th, pt, bufp(PR, 1), out);
     }
     // raw GGSW [ROWS][P][N] -> [2][ROWS][P][N] (NTT domain, slot order)
     void transform_ggsw(const uint32_t *raw, uint32_t *ntt) {
@@ -59,18 +62,22 @@ struct Emu {
     void team_phase(const uint32_t *ggsw_ntt) {
         TwTables t = tables(PR);
         TeamRegs<K> *R = &regs[PR * K::T];
+        const PrimeTab &pt = prime[PR];
         for (uint32_t th = 0; th < (uint32_t)K::T; th++) team_zero_acc<K>(R[th]);
         for (int r = 0; r < K::ROWS; r++) {
             const uint32_t *g_row = ggsw_ntt + (size_t)(PR * K::ROWS + r) * K::P * K::N;
-            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F1<K, PR>(R[th], th, dig.data(), r, bufp(PR, 0));
-            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F2<K, PR>(R[th], jbase_B<C>(th), t, bufp(PR, 0), bufp(PR, 1));
-            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F3<K, PR>(R[th], th, bufp(PR, 1), g_row);
+            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F1<K>(R[th], th, jbase_B<C>(th), pt, t, dig.data(), r, bufp(PR, 0));
+            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F2<K>(R[th], jbase_B<C>(th), pt, bufp(PR, 0), bufp(PR, 1));
+            for (uint32_t th = 0; th < (uint32_t)K::T; th++) {
+                phase_F3a<K>(R[th], th, pt, bufp(PR, 1));
+                phase_F3b<K, true>(R[th], th, g_row);
+            }
         }
         for (int c = 0; c < K::P; c++) {
-            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_I1<K, PR>(R[th], th, c, t, bufp(PR, 0));
-            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_I2<K, PR>(R[th], jbase_B<C>(th), t, bufp(PR, 0), bufp(PR, 1));
+            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_I1<K>(R[th], th, jbase_B<C>(th), c, pt, t, bufp(PR, 0));
+            for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_I2<K>(R[th], jbase_B<C>(th), pt, bufp(PR, 0), bufp(PR, 1));
             for (uint32_t th = 0; th < (uint32_t)K::T; th++)
-                phase_I3<K, PR>(R[th], th, bufp(PR, 1), res.data() + (size_t)(PR * K::P + c) * K::N);
+                phase_I3<K>(R[th], th, pt, bufp(PR, 1), res.data() + (size_t)(PR * K::P + c) * K::N);
         }
     }
     // acc <- ExtProd(ggsw, diff) + acc, diff given by functor (reads a snapshot of acc)

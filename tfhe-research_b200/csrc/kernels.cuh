@@ -1,8 +1,9 @@
 // kernels.cuh -- sm_100a kernels of the PBS path.  No tensor cores: this is modular integer
-// arithmetic (IMAD / IMAD.HI / IMAD.WIDE on the FMA pipe, IADD3/LOP3/VIMNMX on the ALU pipe).
+// arithmetic (IMAD / IMAD.WIDE on the FMA pipe, IADD3/LOP3/VIADDMNMX on the ALU pipe).
 //
 //   K2 pbs_kernel           blind rotation = n fused CMUX steps per ciphertext, accumulator resident
-//                           in shared memory (bootstrapping.rs:58-105, ggsw.rs:132-178); also runs a
+//                           in shared memory (bootstrapping.rs:58-105, ggsw.rs:132-178); GGSW rows are
+//                           streamed global -> shared with cp.async.bulk (TMA) + mbarrier; also runs a
 //                           single external product / CMUX for the sub-operation entry points
 //   K0 bsk_transform_kernel raw BSK -> 2-prime NTT domain, pre-scaled by N^-1 (one-off at upload)
 //   K3+K4 ks_digits_kernel / ks_gemm_kernel   sample extract + KS decomposition, then the wrapping
@@ -18,6 +19,7 @@ namespace tfhe {
 
 // ------------------------------------------------------------------------------------------ K2
 struct PbsArgs {
+    PrimeTab prime[2];         // per-prime constants + pass-A twiddles (constant bank, uniform LDC)
     const uint32_t *bsk_ntt;   // [n][2][ROWS][P][N] slot order, residues < q, pre-scaled by N^-1
     TwTables tw[2];
     // mode 0 (blind rotate)
@@ -28,44 +30,88 @@ struct PbsArgs {
     const uint32_t *in0, *in1; // [B][P][N]
     const uint32_t *ggsw_index;  // [B]
     uint32_t *glwe_out;        // [B][P][N]
-    uint32_t *err_flag;        // set to 1 when a test-vector entry >= 2^log_p (glwe.rs:144)
+    uint32_t *err_flag;        // bit 0: a test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out
     uint32_t n, batch, mode, log_p, enc_shift;
 };
 
 __device__ __forceinline__ void team_bar(int pr, int nthreads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(pr + 1), "r"(nthreads) : "memory");
+    // literal barrier ids so that ptxas reserves 3 named barriers per CTA instead of all 16
+    if (pr == 0) asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared (SASS: UBLKCP), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded wait (a hung kernel would cost a GPU strike): ~seconds of polling, then flag + trap
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *err_flag) {
+    uint32_t done = 0;
+    for (uint32_t spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (!done && spin > (1u << 26)) {
+            atomicOr(err_flag, 2u);
+            __trap();
+        }
+    }
 }
 
-template <class K, int PR>
-__device__ __forceinline__ void team_cmux(TeamRegs<K> &R, uint32_t t, uint32_t jbB, const TwTables &tw, const uint8_t *dig,
-                                          uint32_t *buf0, uint32_t *buf1, uint32_t *res_pr, const uint32_t *g) {
+template <class K>
+__device__ __forceinline__ void team_cmux(TeamRegs<K> &R, uint32_t pr, uint32_t t, uint32_t jbB, const PrimeTab &pt, const TwTables &tw,
+                                          const uint8_t *dig, uint32_t *buf0, uint32_t *buf1, const uint32_t *g, uint32_t *gbuf,
+                                          uint64_t *bar, uint32_t &parity, uint32_t *err_flag) {
     team_zero_acc<K>(R);
 #pragma unroll 1
     for (int r = 0; r < K::ROWS; r++) {
-        phase_F1<K, PR>(R, t, dig, r, buf0);
-        team_bar(PR, K::T);
-        phase_F2<K, PR>(R, jbB, tw, buf0, buf1);
-        team_bar(PR, K::T);
-        phase_F3<K, PR>(R, t, buf1, g + (size_t)r * K::P * K::N);
+        phase_F1<K>(R, t, jbB, pt, tw, dig, r, buf0);
+        team_bar(pr, K::T);  // also: every thread of the team is done reading gbuf (row r-1)
+        if constexpr (K::STAGE_G) {
+            if (t == 0) {
+                mbar_expect_tx(bar, K::G_ROW_BYTES);
+                bulk_g2s(gbuf, g + (size_t)r * K::P * K::N, K::G_ROW_BYTES, bar);
+            }
+        }
+        phase_F2<K>(R, jbB, pt, buf0, buf1);
+        team_bar(pr, K::T);
+        phase_F3a<K>(R, t, pt, buf1);
+        if constexpr (K::STAGE_G) {
+            mbar_wait(bar, parity, err_flag);
+            parity ^= 1u;
+            phase_F3b<K, true>(R, t, gbuf);
+        } else {
+            phase_F3b<K, false>(R, t, g + (size_t)r * K::P * K::N);
+        }
     }
 }
-template <class K, int PR>
-__device__ __forceinline__ void team_inverse(TeamRegs<K> &R, uint32_t t, uint32_t jbB, const TwTables &tw, uint32_t *buf0,
-                                             uint32_t *buf1, uint32_t *res_pr) {
-    static_for<0, K::P>([&](auto ci) {
-        constexpr int c = decltype(ci)::value;
-        phase_I1<K, PR>(R, t, c, tw, buf0);
-        team_bar(PR, K::T);
-        phase_I2<K, PR>(R, jbB, tw, buf0, buf1);
-        team_bar(PR, K::T);
-        phase_I3<K, PR>(R, t, buf1, res_pr + c * K::N);
-    });
+template <class K>
+__device__ __forceinline__ void team_inverse(TeamRegs<K> &R, uint32_t pr, uint32_t t, uint32_t jbB, const PrimeTab &pt, const TwTables &tw,
+                                             uint32_t *buf0, uint32_t *buf1, uint32_t *res_pr) {
+#pragma unroll 1
+    for (int c = 0; c < K::P; c++) {
+        phase_I1<K>(R, t, jbB, c, pt, tw, buf0);
+        team_bar(pr, K::T);
+        phase_I2<K>(R, jbB, pt, buf0, buf1);
+        team_bar(pr, K::T);
+        phase_I3<K>(R, t, pt, buf1, res_pr + c * K::N);
+    }
 }
 
 template <class K, int MINB>
-__global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const PbsArgs a) {
+__global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const __grid_constant__ PbsArgs a) {
     using C = typename K::Ntt;
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem + K::SM_ACC);
     uint8_t *dig = smem + K::SM_DIG;
     uint32_t *res = reinterpret_cast<uint32_t *>(smem + K::SM_DIG);  // aliases dig (barrier-separated)
@@ -78,10 +124,19 @@ __global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const PbsArgs a) 
     const uint32_t jbB = jbase_B<C>(t);
     uint32_t *buf0 = buf + (pr * 2 + 0) * C::NPAD, *buf1 = buf + (pr * 2 + 1) * C::NPAD;
     uint32_t *res_pr = res + pr * K::P * K::N;
+    uint32_t *gbuf = reinterpret_cast<uint32_t *>(smem + K::SM_G + pr * K::G_ROW_BYTES);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + K::SM_BAR) + pr;
+    uint32_t parity = 0;
     constexpr size_t GGSW_WORDS = (size_t)2 * K::ROWS * K::P * K::N;
+    const PrimeTab &pt = a.prime[pr];
+    const TwTables &tw = a.tw[pr];
 
+    if constexpr (K::STAGE_G) {
+        if (t == 0) mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     TeamRegs<K> R;
-    team_init<K>(R, a.tw[pr], t);
+    team_init<K>(R, tw, t);
 
     uint32_t n_steps;
     if (a.mode == 0) {
@@ -127,11 +182,9 @@ __global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const PbsArgs a) 
         }
         __syncthreads();
         const uint32_t *g = a.bsk_ntt + (size_t)gi * GGSW_WORDS + (size_t)pr * (K::ROWS * K::P * K::N);
-        if (pr == 0) team_cmux<K, 0>(R, t, jbB, a.tw[0], dig, buf0, buf1, res_pr, g);
-        else team_cmux<K, 1>(R, t, jbB, a.tw[1], dig, buf0, buf1, res_pr, g);
+        team_cmux<K>(R, pr, t, jbB, pt, tw, dig, buf0, buf1, g, gbuf, bar, parity, a.err_flag);
         __syncthreads();  // both teams are done reading dig before res (same bytes) is written
-        if (pr == 0) team_inverse<K, 0>(R, t, jbB, a.tw[0], buf0, buf1, res_pr);
-        else team_inverse<K, 1>(R, t, jbB, a.tw[1], buf0, buf1, res_pr);
+        team_inverse<K>(R, pr, t, jbB, pt, tw, buf0, buf1, res_pr);
         __syncthreads();
         phase_crt<K>(tid, res, acc);
         __syncthreads();
@@ -143,34 +196,32 @@ __global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const PbsArgs a) 
 // ------------------------------------------------------------------------------------------ K0
 // grid = number of polynomials (n*ROWS*P); block = 2T (one team per prime); in natural [n][ROWS][P][N],
 // out [n][2][ROWS][P][N].
+struct TransformArgs {
+    PrimeTab prime[2];
+    TwTables tw[2];
+    const uint32_t *raw;
+    uint32_t *out;
+};
 template <class K>
-__global__ void __launch_bounds__(K::THREADS) bsk_transform_kernel(const uint32_t *__restrict__ raw, uint32_t *__restrict__ out,
-                                                                   TwTables tw0, TwTables tw1) {
+__global__ void __launch_bounds__(K::THREADS) bsk_transform_kernel(const __grid_constant__ TransformArgs a) {
     using C = typename K::Ntt;
     __shared__ __align__(16) uint32_t buf[2 * 2 * C::NPAD];
     const uint32_t tid = threadIdx.x, pr = tid / K::T, t = tid % K::T;
     const size_t poly = blockIdx.x;  // = (i*ROWS + r)*P + c
     const size_t i = poly / (K::ROWS * K::P), rc = poly % (K::ROWS * K::P);
-    const uint32_t *g = raw + poly * K::N;
-    uint32_t *o = out + ((i * 2 + pr) * (K::ROWS * K::P) + rc) * K::N;
+    const uint32_t *g = a.raw + poly * K::N;
+    uint32_t *o = a.out + ((i * 2 + pr) * (K::ROWS * K::P) + rc) * K::N;
     uint32_t *buf0 = buf + (pr * 2) * C::NPAD, *buf1 = buf0 + C::NPAD;
     const uint32_t jbB = jbase_B<C>(t);
+    const PrimeTab &pt = a.prime[pr];
+    const TwTables &tw = a.tw[pr];
     TeamRegs<K> R;
-    if (pr == 0) {
-        team_init<K>(R, tw0, t);
-        phase_T1<K, 0>(R, t, g, buf0);
-        team_bar(0, K::T);
-        phase_F2<K, 0>(R, jbB, tw0, buf0, buf1);
-        team_bar(0, K::T);
-        phase_T3<K, 0>(R, t, buf1, o);
-    } else {
-        team_init<K>(R, tw1, t);
-        phase_T1<K, 1>(R, t, g, buf0);
-        team_bar(1, K::T);
-        phase_F2<K, 1>(R, jbB, tw1, buf0, buf1);
-        team_bar(1, K::T);
-        phase_T3<K, 1>(R, t, buf1, o);
-    }
+    team_init<K>(R, tw, t);
+    phase_T1<K>(R, t, jbB, pt, tw, g, buf0);
+    team_bar(pr, K::T);
+    phase_F2<K>(R, jbB, pt, buf0, buf1);
+    team_bar(pr, K::T);
+    phase_T3<K>(R, t, pt, buf1, o);
 }
 
 // ------------------------------------------------------------------------------------------ K3+K4
@@ -329,7 +380,7 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t 
             for (int i = 0; i < 8; i++) {
                 if (KIND == 0) x[i] = x[i] * a + b;                                  // IMAD
                 else if (KIND == 1) x[i] = __umulhi(x[i], a) + b;                    // IMAD.HI
-                else asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y[i]) : "r"(a), "r"(b + i));  // IMAD.WIDE
+                else y[i] = (unsigned long long)(uint32_t)y[i] * a + y[i];         // IMAD.WIDE (loop-variant multiplicand)
             }
         }
     }

@@ -4,7 +4,8 @@
 // (external_product) -> glwe.rs:69-108 (decompose) + utils.rs:155-173 (poly_dot_product).
 //
 // One CTA owns one GLWE accumulator (shared memory) and runs two TEAMS of T threads, one per RNS
-// prime.  A CMUX step is a fixed sequence of phases separated by barriers:
+// prime; both teams execute the SAME instructions (the prime and its twiddles are runtime values).
+// A CMUX step is a fixed sequence of phases separated by barriers:
 //   D   (all threads)  diff = rot(acc, a) - acc, signed digits of every coefficient -> dig[]
 //   F_r (each team)    forward NTT of digit polynomial r (3 register passes, 2 exchanges) and
 //                      multiply-accumulate against GGSW row r into 64-bit register accumulators
@@ -17,7 +18,7 @@
 
 namespace tfhe {
 
-template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_>
+template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, bool STAGE_G_ = true>
 struct PbsCfg {
     using Ntt = NttCfg<LOGN_, LOGE_>;
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_;
@@ -29,26 +30,40 @@ struct PbsCfg {
     static constexpr int DIG_OFF = 1 << (LOGB - 1);
     static constexpr int DIG_BYTES = (LOGB <= 7) ? 1 : 2;  // stored digit = d + B/2 in [0, 3B/2]
     static constexpr int DIG_WORDS = E * DIG_BYTES / 4;    // 32-bit words per thread per digit row
+    static constexpr int DIG_SH = DIG_WORDS == 8 ? 2 : DIG_WORDS == 4 ? 3 : 4;  // log2(32 / DIG_WORDS)
     static_assert(LOGB * L <= 32 && 32 % LOGB == 0, "decomposer must divide log_q (SURVEY 9-B H2)");
-    static_assert(DIG_WORDS >= 1, "digit row too small");
+    static_assert(DIG_WORDS == 2 || DIG_WORDS == 4 || DIG_WORDS == 8, "digit row geometry");
     // exactness: |sum| <= ROWS*N*B*2^31 must stay below Q0*Q1/2; lazy u64 accumulators must not wrap
     static_assert((double)ROWS * N * (1 << LOGB) * 2147483648.0 < (double)kHalfQ0Q1, "CRT range");
     static_assert((double)ROWS * (2 * LOGN + 2) * (double)kQ1 * (double)kQ1 < 18446744073709551616.0, "u64 MAC range");
-    // shared memory carve-up (bytes)
-    // dig[ROWS][N] (digits) and res[2][P][N] (inverse-NTT residues) share bytes: a CTA barrier
-    // separates the last digit read from the first residue write.
+    // GGSW rows are streamed global -> shared with cp.async.bulk (TMA) when STAGE_G, else read with LDG
+    static constexpr bool STAGE_G = STAGE_G_;
+    static constexpr int G_ROW_BYTES = P * N * 4;  // one GGSW row of one prime
+    // shared memory carve-up (bytes).  dig[ROWS][N] (digits) and res[2][P][N] (inverse-NTT residues)
+    // share bytes: a CTA barrier separates the last digit read from the first residue write.
     static constexpr int SM_ACC = 0;
     static constexpr int SM_DIG = SM_ACC + P * N * 4;
     static constexpr int DIG_BYTES_TOTAL = ROWS * N * DIG_BYTES, RES_BYTES_TOTAL = 2 * P * N * 4;
-    static constexpr int SM_BUF = SM_DIG + (((DIG_BYTES_TOTAL > RES_BYTES_TOTAL ? DIG_BYTES_TOTAL : RES_BYTES_TOTAL) + 15) & ~15);
-    static constexpr int SM_AT = SM_BUF + 2 * 2 * Ntt::NPAD * 4;  // mod-switched mask (u16), n+1 entries follow
+    static constexpr int SM_BUF = SM_DIG + (((DIG_BYTES_TOTAL > RES_BYTES_TOTAL ? DIG_BYTES_TOTAL : RES_BYTES_TOTAL) + 127) & ~127);
+    static constexpr int SM_G = SM_BUF + ((2 * 2 * Ntt::NPAD * 4 + 127) & ~127);      // [2 primes][G_ROW_BYTES]
+    static constexpr int SM_BAR = SM_G + (STAGE_G ? 2 * G_ROW_BYTES : 0);              // 2 mbarriers
+    static constexpr int SM_AT = SM_BAR + 16;  // mod-switched mask (u16), n+1 entries follow
 };
 
-// position of natural coefficient j inside a digit row: thread t of layout A holds j = (e<<LOGT)|t
-// for e = 0..E-1, and wants those E digits contiguous.
-template <class C>
-TFHE_HD constexpr uint32_t dig_pos(uint32_t j) {
-    return ((j & (C::T - 1u)) << C::LOGE) | (j >> C::LOGT);
+// Byte offset of the digit of natural coefficient j inside digit row `row`.  Thread t of layout A
+// holds j = (e<<LOGT)|t for e = 0..E-1 and wants those E digits in its own DIG_WORDS words; the word
+// index is XOR-swizzled with bits of t so that both the writers (consecutive t, fixed e) and the
+// readers (consecutive t, fixed word) hit 32 distinct banks.
+template <class K>
+TFHE_HD constexpr uint32_t dig_word(uint32_t t, uint32_t w) {
+    return t * K::DIG_WORDS + (w ^ ((t >> K::DIG_SH) & (K::DIG_WORDS - 1u)));
+}
+template <class K>
+TFHE_HD constexpr uint32_t dig_byte_off(uint32_t row, uint32_t j) {
+    using C = typename K::Ntt;
+    const uint32_t t = j & (C::T - 1u), e = j >> C::LOGT;
+    const uint32_t byte_in_row = e * K::DIG_BYTES;
+    return row * (K::N * K::DIG_BYTES) + dig_word<K>(t, byte_in_row >> 2) * 4u + (byte_in_row & 3u);
 }
 
 TFHE_HD void ld_global4(uint32_t *dst, const uint32_t *src) {
@@ -71,18 +86,16 @@ TFHE_HD uint2 ld_global_tw(const uint2 *p) {
 // diff_fn(p, j) returns coefficient j of polynomial p of the GLWE to decompose.
 template <class K, class DiffFn>
 TFHE_HD void phase_digits(uint32_t tid, uint8_t *dig_bytes, DiffFn diff_fn) {
-    using C = typename K::Ntt;
     for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += K::THREADS) {
         const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
         int32_t d[K::L];
         decompose_signed<K::LOGB, K::L>(diff_fn(p, j), d);
-        const uint32_t pos = dig_pos<C>(j);
 #pragma unroll
         for (int lev = 0; lev < K::L; lev++) {
             const uint32_t v = (uint32_t)(d[lev] + K::DIG_OFF);
-            const uint32_t off = (p * K::L + lev) * K::N + pos;
+            const uint32_t off = dig_byte_off<K>(p * K::L + lev, j);
             if constexpr (K::DIG_BYTES == 1) dig_bytes[off] = (uint8_t)v;
-            else reinterpret_cast<uint16_t *>(dig_bytes)[off] = (uint16_t)v;
+            else *reinterpret_cast<uint16_t *>(dig_bytes + off) = (uint16_t)v;
         }
     }
 }
@@ -93,9 +106,10 @@ struct TeamRegs {
     uint32_t x[K::E];
     uint64_t acc[K::P][K::E];
     uint2 twC[K::Ntt::NC_TW];  // forward pass-C twiddles, resident for the whole kernel
+    uint2 twB[K::Ntt::NB_TW];  // pass-B twiddles, prefetched at the start of each transform
 };
 
-// twiddle tables in global memory, one set per prime (built on the host, see host_tables.cpp):
+// twiddle tables in global memory, one set per prime (built on the host, see host_tables.hpp):
 //   fwdB/invB: [2^LOGE (hA)][NB_TW] (w, ws)      fwdC/invC: [T (t)][NC_TW] (w, ws)
 struct TwTables {
     const uint2 *fwdB, *fwdC, *invB, *invC;
@@ -114,20 +128,25 @@ TFHE_HD void team_zero_acc(TeamRegs<K> &r) {
 #pragma unroll
         for (int e = 0; e < K::E; e++) r.acc[c][e] = 0;
 }
+template <class K>
+TFHE_HD void prefetch_twB(TeamRegs<K> &r, const uint2 *tabB, uint32_t jbB) {
+    using C = typename K::Ntt;
+    const uint32_t hA = jbB >> (C::LOGN - C::LOGE);
+#pragma unroll
+    for (int i = 0; i < C::NB_TW; i++) r.twB[i] = ld_global_tw(tabB + hA * C::NB_TW + i);
+}
 
 // F1: load the E digits of row `row` (layout A), lift to [q-B/2, q+B], pass A, store to buf0.
-template <class K, int PR>
-TFHE_HD void phase_F1(TeamRegs<K> &r, uint32_t t, const uint8_t *dig_bytes, uint32_t row, uint32_t *buf0) {
+template <class K>
+TFHE_HD void phase_F1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, const PrimeTab &pt, const TwTables &tw, const uint8_t *dig_bytes,
+                      uint32_t row, uint32_t *buf0) {
     using C = typename K::Ntt;
-    constexpr uint32_t q = prime_c(PR);
+    prefetch_twB<K>(r, tw.fwdB, jbB);
+    const uint32_t q = pt.q;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(dig_bytes + (size_t)row * K::N * K::DIG_BYTES);
     uint32_t w[K::DIG_WORDS];
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(dig_bytes + ((size_t)row * K::N + t * K::E) * K::DIG_BYTES);
-    if constexpr (K::DIG_WORDS >= 4) {
 #pragma unroll
-        for (int i = 0; i < K::DIG_WORDS; i += 4) ld_vec<4>(w + i, src + i);
-    } else {
-        ld_vec<K::DIG_WORDS>(w, src);
-    }
+    for (int i = 0; i < K::DIG_WORDS; i++) w[i] = src[dig_word<K>(t, i)];
 #pragma unroll
     for (int e = 0; e < K::E; e++) {
         uint32_t d;
@@ -135,67 +154,72 @@ TFHE_HD void phase_F1(TeamRegs<K> &r, uint32_t t, const uint8_t *dig_bytes, uint
         else d = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
         r.x[e] = d + (q - K::DIG_OFF);
     }
-    fwd_pass_A<C, PR>(r.x);
+    fwd_pass_A<C>(r.x, pt.fwdA, q);
     store_A<C>(r.x, buf0, t);
 }
 // F2: layout B, pass B, store to buf1.
-template <class K, int PR>
-TFHE_HD void phase_F2(TeamRegs<K> &r, uint32_t jbB, const TwTables &tw, const uint32_t *buf0, uint32_t *buf1) {
+template <class K>
+TFHE_HD void phase_F2(TeamRegs<K> &r, uint32_t jbB, const PrimeTab &pt, const uint32_t *buf0, uint32_t *buf1) {
     using C = typename K::Ntt;
     load_B<C>(r.x, buf0, jbB);
-    uint2 twB[C::NB_TW];
-    const uint32_t hA = jbB >> (C::LOGN - C::LOGE);
-#pragma unroll
-    for (int i = 0; i < C::NB_TW; i++) twB[i] = ld_global_tw(tw.fwdB + hA * C::NB_TW + i);
-    fwd_pass_B<C, PR>(r.x, twB);
+    fwd_pass_B<C>(r.x, r.twB, pt.q);
     store_B<C>(r.x, buf1, jbB);
 }
-// F3: layout C, pass C, multiply-accumulate against GGSW row (g_row = [P][N] words in bsk_slot order).
-template <class K, int PR>
-TFHE_HD void phase_F3(TeamRegs<K> &r, uint32_t t, const uint32_t *buf1, const uint32_t *g_row) {
+// F3a: layout C, pass C.   F3b: multiply-accumulate against GGSW row g_row = [P][N] words (bsk_slot order;
+// shared memory when staged by TMA, else global).
+template <class K>
+TFHE_HD void phase_F3a(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const uint32_t *buf1) {
     using C = typename K::Ntt;
     load_C<C>(r.x, buf1, t);
-    fwd_pass_C<C, PR>(r.x, r.twC);
+    fwd_pass_C<C>(r.x, r.twC, pt.q);
+}
+template <class K, bool SHARED_G>
+TFHE_HD void phase_F3b(TeamRegs<K> &r, uint32_t t, const uint32_t *g_row) {
+    using C = typename K::Ntt;
 #pragma unroll
     for (int c = 0; c < K::P; c++) {
 #pragma unroll
         for (int ch = 0; ch < K::E / 4; ch++) {
             uint32_t g[4];
-            ld_global4(g, g_row + c * K::N + ((ch * C::T + t) << 2));
+            const uint32_t *src = g_row + c * K::N + ((ch * C::T + t) << 2);
+            if constexpr (SHARED_G) ld_vec<4>(g, src);
+            else ld_global4(g, src);
 #pragma unroll
             for (int w = 0; w < 4; w++) r.acc[c][4 * ch + w] += (uint64_t)r.x[4 * ch + w] * g[w];
         }
     }
 }
 // I1: reduce accumulator column c to [0,2q), inverse pass C, store (layout C) to buf0.
-template <class K, int PR>
-TFHE_HD void phase_I1(TeamRegs<K> &r, uint32_t t, int c, const TwTables &tw, uint32_t *buf0) {
+template <class K>
+TFHE_HD void phase_I1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, int c, const PrimeTab &pt, const TwTables &tw, uint32_t *buf0) {
     using C = typename K::Ntt;
-#pragma unroll
-    for (int e = 0; e < K::E; e++) r.x[e] = reduce_acc64<PR>(r.acc[c][e]);
+    prefetch_twB<K>(r, tw.invB, jbB);
     uint2 twc[C::NC_TW];
 #pragma unroll
     for (int i = 0; i < C::NC_TW; i++) twc[i] = ld_global_tw(tw.invC + t * C::NC_TW + i);
-    inv_pass_C<C, PR>(r.x, twc);
+    static_for<0, K::P>([&](auto ci) {
+        constexpr int cc = decltype(ci)::value;
+        if (c == cc) {
+#pragma unroll
+            for (int e = 0; e < K::E; e++) r.x[e] = reduce_acc64_rt(r.acc[cc][e], pt);
+        }
+    });
+    inv_pass_C<C>(r.x, twc, pt.q);
     store_C<C>(r.x, buf0, t);
 }
-template <class K, int PR>
-TFHE_HD void phase_I2(TeamRegs<K> &r, uint32_t jbB, const TwTables &tw, const uint32_t *buf0, uint32_t *buf1) {
+template <class K>
+TFHE_HD void phase_I2(TeamRegs<K> &r, uint32_t jbB, const PrimeTab &pt, const uint32_t *buf0, uint32_t *buf1) {
     using C = typename K::Ntt;
     load_B<C>(r.x, buf0, jbB);
-    uint2 twB[C::NB_TW];
-    const uint32_t hA = jbB >> (C::LOGN - C::LOGE);
-#pragma unroll
-    for (int i = 0; i < C::NB_TW; i++) twB[i] = ld_global_tw(tw.invB + hA * C::NB_TW + i);
-    inv_pass_B<C, PR>(r.x, twB);
+    inv_pass_B<C>(r.x, r.twB, pt.q);
     store_B<C>(r.x, buf1, jbB);
 }
 // I3: layout A, inverse pass A, store residues in natural order (unpadded) to res_c[N].
-template <class K, int PR>
-TFHE_HD void phase_I3(TeamRegs<K> &r, uint32_t t, const uint32_t *buf1, uint32_t *res_c) {
+template <class K>
+TFHE_HD void phase_I3(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const uint32_t *buf1, uint32_t *res_c) {
     using C = typename K::Ntt;
     load_A<C>(r.x, buf1, t);
-    inv_pass_A<C, PR>(r.x);
+    inv_pass_A<C>(r.x, pt.invA, pt.q);
 #pragma unroll
     for (int e = 0; e < K::E; e++) res_c[(e << C::LOGT) | t] = r.x[e];
 }
@@ -217,26 +241,24 @@ TFHE_HD uint32_t centred_residue(uint32_t g, uint32_t q) {
     return neg ? (m ? q - m : 0u) : m;
 }
 // T1: load polynomial g[N] (natural order), lift, pass A, store to buf0.   (T2 == phase_F2)
-template <class K, int PR>
-TFHE_HD void phase_T1(TeamRegs<K> &r, uint32_t t, const uint32_t *g, uint32_t *buf0) {
+template <class K>
+TFHE_HD void phase_T1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, const PrimeTab &pt, const TwTables &tw, const uint32_t *g, uint32_t *buf0) {
     using C = typename K::Ntt;
+    prefetch_twB<K>(r, tw.fwdB, jbB);
 #pragma unroll
-    for (int e = 0; e < K::E; e++) r.x[e] = centred_residue(g[(e << C::LOGT) | t], prime_c(PR));
-    fwd_pass_A<C, PR>(r.x);
+    for (int e = 0; e < K::E; e++) r.x[e] = centred_residue(g[(e << C::LOGT) | t], pt.q);
+    fwd_pass_A<C>(r.x, pt.fwdA, pt.q);
     store_A<C>(r.x, buf0, t);
 }
 // T3: pass C, scale by N^-1 (so the inverse NTT needs no final scaling), reduce to [0,q), store in
 // bsk_slot order.
-template <class K, int PR>
-TFHE_HD void phase_T3(TeamRegs<K> &r, uint32_t t, const uint32_t *buf1, uint32_t *out) {
+template <class K>
+TFHE_HD void phase_T3(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const uint32_t *buf1, uint32_t *out) {
     using C = typename K::Ntt;
-    constexpr uint32_t q = prime_c(PR);
-    constexpr uint32_t ninv = invmod_c((uint32_t)K::N % q, q);
-    constexpr uint32_t ninv_s = shoup_c(ninv, q);
     load_C<C>(r.x, buf1, t);
-    fwd_pass_C<C, PR>(r.x, r.twC);
+    fwd_pass_C<C>(r.x, r.twC, pt.q);
 #pragma unroll
-    for (int e = 0; e < K::E; e++) out[bsk_slot<C>(t, e)] = csub(shoup_mul(r.x[e], ninv, ninv_s, q), q);
+    for (int e = 0; e < K::E; e++) out[bsk_slot<C>(t, e)] = csub(shoup_mul(r.x[e], pt.ninv, pt.ninv_s, pt.q), pt.q);
 }
 
 }  // namespace tfhe

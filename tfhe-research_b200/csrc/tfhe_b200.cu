@@ -41,6 +41,7 @@ struct tfhe_ctx {
     std::string err;
     uint32_t *d_tw[2][4] = {};
     TwTables tw[2];
+    PrimeTab prime[2];
     DevBuf in0, in1, in2, out, glwe, digits, body, luts, lutidx, misc;
     uint32_t *d_err = nullptr;
     uint64_t launches = 0;
@@ -106,15 +107,21 @@ int finish_out(tfhe_ctx *ctx, void *dst, size_t bytes, const void *dev) {
 }
 
 // ---- kernel configurations (must match api_internal.hpp) ----
-using K0 = PbsCfg<9, 3, 2, 6, 4>;
-using K1 = PbsCfg<10, 4, 1, 3, 8>;
-using K2 = PbsCfg<11, 4, 1, 3, 8>;
+#ifndef TFHE_STAGE_P0
+#define TFHE_STAGE_P0 1
+#endif
+#ifndef TFHE_STAGE_P1
+#define TFHE_STAGE_P1 1
+#endif
+using K0 = PbsCfg<9, 3, 2, 6, 4, TFHE_STAGE_P0 != 0>;
+using K1 = PbsCfg<10, 4, 1, 3, 8, TFHE_STAGE_P1 != 0>;
+using K2 = PbsCfg<11, 4, 1, 3, 8, /*STAGE_G=*/false>;  // 32 KB of row staging would halve its occupancy
 template <class K> struct MinBlocks;
 #ifndef TFHE_MINB_P0
 #define TFHE_MINB_P0 5
 #endif
 #ifndef TFHE_MINB_P1
-#define TFHE_MINB_P1 4
+#define TFHE_MINB_P1 3
 #endif
 #ifndef TFHE_MINB_P2
 #define TFHE_MINB_P2 2
@@ -144,7 +151,11 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a) {
 template <class K>
 int launch_transform_t(tfhe_ctx *ctx, const uint32_t *raw, uint32_t *out, size_t n) {
     const size_t polys = n * K::ROWS * K::P;
-    bsk_transform_kernel<K><<<(unsigned)polys, K::THREADS, 0, ctx->stream>>>(raw, out, ctx->tw[0], ctx->tw[1]);
+    TransformArgs ta;
+    ta.prime[0] = ctx->prime[0]; ta.prime[1] = ctx->prime[1];
+    ta.tw[0] = ctx->tw[0]; ta.tw[1] = ctx->tw[1];
+    ta.raw = raw; ta.out = out;
+    bsk_transform_kernel<K><<<(unsigned)polys, K::THREADS, 0, ctx->stream>>>(ta);
     CU(cudaGetLastError());
     ctx->launches++;
     return TFHE_OK;
@@ -194,6 +205,7 @@ int run_bootstrap(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *d_in, const 
     PbsArgs a = {};
     a.bsk_ntt = bk->d_bsk_ntt;
     a.tw[0] = ctx->tw[0]; a.tw[1] = ctx->tw[1];
+    a.prime[0] = ctx->prime[0]; a.prime[1] = ctx->prime[1];
     a.lwe_in = d_in; a.luts = d_luts; a.lut_idx = d_lut_idx;
     a.glwe_out = (uint32_t *)ctx->glwe.p;
     a.err_flag = ctx->d_err;
@@ -218,6 +230,7 @@ int finish_timed(tfhe_ctx *ctx) {
     CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4])); ctx->last_ms[2] = t;
     uint32_t flag = 0;
     CU(cudaMemcpy(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost));
+    if (flag & 2u) return fail(ctx, TFHE_E_CUDA, "TMA bulk copy wait timed out in pbs_kernel");
     if (flag) return fail(ctx, TFHE_E_ASSERT, "test vector entry >= 2^log_p (reference assert! glwe.rs:144)");
     return TFHE_OK;
 }
@@ -253,6 +266,8 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     const int loge = (p->glwe_poly_degree == 9) ? 3 : 4;
     HostTw tw;
     build_tw_tables((int)p->glwe_poly_degree, loge, tw);
+    fill_prime_tab(0, (int)p->glwe_poly_degree, loge, ctx->prime[0]);
+    fill_prime_tab(1, (int)p->glwe_poly_degree, loge, ctx->prime[1]);
     for (int pr = 0; pr < 2; pr++) {
         const std::vector<uint32_t> *src[4] = {&tw.fwdB[pr], &tw.fwdC[pr], &tw.invB[pr], &tw.invC[pr]};
         for (int i = 0; i < 4; i++) {
@@ -492,6 +507,7 @@ static int ext_or_cmux(tfhe_ctx *ctx, const tfhe_bk *bk, int mode, const uint32_
     PbsArgs a = {};
     a.bsk_ntt = bk->d_bsk_ntt;
     a.tw[0] = ctx->tw[0]; a.tw[1] = ctx->tw[1];
+    a.prime[0] = ctx->prime[0]; a.prime[1] = ctx->prime[1];
     a.in0 = (const uint32_t *)d0; a.in1 = (const uint32_t *)(mode == 2 ? d1 : d0);
     a.ggsw_index = (const uint32_t *)ctx->lutidx.p;
     a.glwe_out = (uint32_t *)d_out;
@@ -526,6 +542,7 @@ int tfhe_blind_rotate(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, 
     PbsArgs a = {};
     a.bsk_ntt = bk->d_bsk_ntt;
     a.tw[0] = ctx->tw[0]; a.tw[1] = ctx->tw[1];
+    a.prime[0] = ctx->prime[0]; a.prime[1] = ctx->prime[1];
     a.lwe_in = (const uint32_t *)d_in; a.luts = (const uint32_t *)d_luts; a.lut_idx = (const uint32_t *)d_idx;
     a.glwe_out = (uint32_t *)d_out;
     a.err_flag = ctx->d_err;

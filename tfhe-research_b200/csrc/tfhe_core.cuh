@@ -29,7 +29,7 @@
 #endif
 
 #ifndef TFHE_MULHI_WIDE
-#define TFHE_MULHI_WIDE 1
+#define TFHE_MULHI_WIDE 0
 #endif
 
 #if !defined(__CUDACC__)
@@ -92,10 +92,12 @@ struct Prime {
 // ---------------------------------------------------------------- scalar helpers
 TFHE_HD uint32_t mulhi_u32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__) && TFHE_MULHI_WIDE
-    // measured on B200: IMAD.HI issues at half the IMAD rate (8.9 vs 18.5 T lane-ops/s) while IMAD.WIDE
-    // runs at full rate (17.7 T/s), so take the high word of a wide multiply instead of mul.hi
+    // A/B switch: high word via IMAD.WIDE instead of IMAD.HI.  Measured on B200 both issue at HALF the plain
+    // IMAD rate (ncu: fma-heavy pipe cycles; IMAD.HI 8.9 vs IMAD 18.5 T lane-ops/s) and perform the same,
+    // so the default stays mul.hi (no 64-bit register pair).
     uint32_t lo, hi;
     asm("{\n\t.reg .b64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+    (void)lo;
     return hi;
 #elif defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -322,109 +324,86 @@ TFHE_HD void load_C(uint32_t *x, const uint32_t *buf, uint32_t t) {
 }
 
 // ---- register passes ----
-// Forward pass A: stages 0..LOGE-1 on the hA bits; twiddles are compile-time immediates.
-template <class C, int PR>
-TFHE_HD void fwd_pass_A(uint32_t *x) {
-    constexpr uint32_t q = prime_c(PR);
-    static_for<0, C::LOGE>([&](auto si) {
-        constexpr int s = decltype(si)::value;
-        constexpr int half = C::E >> (s + 1);
-        static_for<0, C::E>([&](auto ei) {
-            constexpr int e = decltype(ei)::value;
-            if constexpr ((e & half) == 0) {
-                constexpr uint32_t b = (uint32_t)e >> (C::LOGE - s);
-                constexpr uint32_t w = fwd_tw_c(PR, C::LOGN, s, b);
-                constexpr uint32_t ws = shoup_c(w, q);
-                ct_bfly(x[e], x[e + half], w, ws, q);
-            }
-        });
-    });
-}
-// Forward pass B: stages LOGE..LOGE+QB-1 on the mid bits.  tw[2^u-1+m] = w(LOGE+u, (hA<<u)|m) as (w, ws).
-template <class C, int PR>
-TFHE_HD void fwd_pass_B(uint32_t *x, const uint2 *tw) {
-    constexpr uint32_t q = prime_c(PR);
-    static_for<0, C::QB>([&](auto ui) {
+// All passes take the prime q and their twiddles as RUNTIME values so that both RNS primes execute
+// the same instructions (one copy of the unrolled code in the instruction cache; the v1 kernel with
+// compile-time primes was bound by instruction fetch, profiles/r01_v1_*).  tw[2^u-1+m] = (w, ws).
+//
+// Pass over register bits [LO, LO+Q): stage u pairs bit LO+Q-1-u, twiddle index = top u bits of the field.
+template <int E, int LO, int Q>
+TFHE_HD void fwd_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q) {
+    static_for<0, Q>([&](auto ui) {
         constexpr int u = decltype(ui)::value;
-        constexpr int bit = 1 << (C::XB + C::QB - 1 - u);
-        static_for<0, C::E>([&](auto ei) {
+        constexpr int bit = 1 << (LO + Q - 1 - u);
+        static_for<0, E>([&](auto ei) {
             constexpr int e = decltype(ei)::value;
             if constexpr ((e & bit) == 0) {
-                constexpr int mid = e >> C::XB;
-                constexpr int m = mid >> (C::QB - u);
+                constexpr int field = (e >> LO) & ((1 << Q) - 1);
+                constexpr int m = field >> (Q - u);
                 const uint2 w = tw[(1 << u) - 1 + m];
                 ct_bfly(x[e], x[e + bit], w.x, w.y, q);
             }
         });
     });
 }
-// Forward pass C: stages LOGE+QB..LOGN-1 on the lo bits.  tw[2^u-1+m] = w(LOGE+QB+u, (t<<u)|m).
-template <class C, int PR>
-TFHE_HD void fwd_pass_C(uint32_t *x, const uint2 *tw) {
-    constexpr uint32_t q = prime_c(PR);
-    static_for<0, C::LOGE>([&](auto ui) {
-        constexpr int u = decltype(ui)::value;
-        constexpr int half = C::E >> (u + 1);
-        static_for<0, C::E>([&](auto ei) {
-            constexpr int e = decltype(ei)::value;
-            if constexpr ((e & half) == 0) {
-                constexpr int m = e >> (C::LOGE - u);
-                const uint2 w = tw[(1 << u) - 1 + m];
-                ct_bfly(x[e], x[e + half], w.x, w.y, q);
-            }
-        });
-    });
-}
-// Inverse passes (Gentleman-Sande), exact mirrors; tw holds the INVERSE twiddles, same indexing.
-template <class C, int PR>
-TFHE_HD void inv_pass_C(uint32_t *x, const uint2 *tw) {
-    constexpr uint32_t q = prime_c(PR);
-    static_for<0, C::LOGE>([&](auto ui) {
-        constexpr int u = C::LOGE - 1 - decltype(ui)::value;
-        constexpr int half = C::E >> (u + 1);
-        static_for<0, C::E>([&](auto ei) {
-            constexpr int e = decltype(ei)::value;
-            if constexpr ((e & half) == 0) {
-                constexpr int m = e >> (C::LOGE - u);
-                const uint2 w = tw[(1 << u) - 1 + m];
-                gs_bfly(x[e], x[e + half], w.x, w.y, q);
-            }
-        });
-    });
-}
-template <class C, int PR>
-TFHE_HD void inv_pass_B(uint32_t *x, const uint2 *tw) {
-    constexpr uint32_t q = prime_c(PR);
-    static_for<0, C::QB>([&](auto ui) {
-        constexpr int u = C::QB - 1 - decltype(ui)::value;
-        constexpr int bit = 1 << (C::XB + C::QB - 1 - u);
-        static_for<0, C::E>([&](auto ei) {
+template <int E, int LO, int Q>
+TFHE_HD void inv_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q) {
+    static_for<0, Q>([&](auto ui) {
+        constexpr int u = Q - 1 - decltype(ui)::value;
+        constexpr int bit = 1 << (LO + Q - 1 - u);
+        static_for<0, E>([&](auto ei) {
             constexpr int e = decltype(ei)::value;
             if constexpr ((e & bit) == 0) {
-                constexpr int mid = e >> C::XB;
-                constexpr int m = mid >> (C::QB - u);
+                constexpr int field = (e >> LO) & ((1 << Q) - 1);
+                constexpr int m = field >> (Q - u);
                 const uint2 w = tw[(1 << u) - 1 + m];
                 gs_bfly(x[e], x[e + bit], w.x, w.y, q);
             }
         });
     });
 }
-template <class C, int PR>
-TFHE_HD void inv_pass_A(uint32_t *x) {
-    constexpr uint32_t q = prime_c(PR);
-    static_for<0, C::LOGE>([&](auto si) {
-        constexpr int s = C::LOGE - 1 - decltype(si)::value;
-        constexpr int half = C::E >> (s + 1);
-        static_for<0, C::E>([&](auto ei) {
-            constexpr int e = decltype(ei)::value;
-            if constexpr ((e & half) == 0) {
-                constexpr uint32_t b = (uint32_t)e >> (C::LOGE - s);
-                constexpr uint32_t w = inv_tw_c(PR, C::LOGN, s, b);
-                constexpr uint32_t ws = shoup_c(w, q);
-                gs_bfly(x[e], x[e + half], w, ws, q);
-            }
-        });
-    });
+// pass A: stages 0..LOGE-1 on the hA bits (all E register bits); twA[2^s-1+b] = w(s, b), the same for
+//         every thread (kept in the kernel-parameter constant bank).
+// pass B: stages LOGE..LOGE+QB-1 on the mid bits (register bits [XB, XB+QB)); twB = w(LOGE+u, (hA<<u)|m).
+// pass C: stages LOGE+QB..LOGN-1 on the lo bits; twC = w(LOGE+QB+u, (t<<u)|m).
+template <class C> TFHE_HD void fwd_pass_A(uint32_t *x, const uint2 *tw, uint32_t q) { fwd_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
+template <class C> TFHE_HD void fwd_pass_B(uint32_t *x, const uint2 *tw, uint32_t q) { fwd_pass_bits<C::E, C::XB, C::QB>(x, tw, q); }
+template <class C> TFHE_HD void fwd_pass_C(uint32_t *x, const uint2 *tw, uint32_t q) { fwd_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
+template <class C> TFHE_HD void inv_pass_A(uint32_t *x, const uint2 *tw, uint32_t q) { inv_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
+template <class C> TFHE_HD void inv_pass_B(uint32_t *x, const uint2 *tw, uint32_t q) { inv_pass_bits<C::E, C::XB, C::QB>(x, tw, q); }
+template <class C> TFHE_HD void inv_pass_C(uint32_t *x, const uint2 *tw, uint32_t q) { inv_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
+
+// Per-prime constants handed to the kernels by value (kernel-parameter constant bank; a warp only
+// ever reads its own prime's entry, so every access is a uniform LDC).
+constexpr int kMaxPassA = 15;  // E-1 for E = 16
+struct PrimeTab {
+    uint32_t q, c32, c32_s, one_s;  // prime, 2^32 mod q, shoup(c32), floor(2^32/q)
+    uint32_t ninv, ninv_s, pad0, pad1;  // N^-1 mod q (key transform only)
+    uint2 fwdA[kMaxPassA + 1];
+    uint2 invA[kMaxPassA + 1];
+};
+inline void fill_prime_tab(int pr, int logn, int loge, PrimeTab &t) {
+    const uint32_t q = prime_c(pr);
+    t.q = q;
+    t.c32 = (uint32_t)((1ull << 32) % q);
+    t.c32_s = shoup_c(t.c32, q);
+    t.one_s = shoup_c(1u, q);
+    t.ninv = invmod_c((1u << logn) % q, q);
+    t.ninv_s = shoup_c(t.ninv, q);
+    t.pad0 = t.pad1 = 0;
+    for (int i = 0; i <= kMaxPassA; i++) t.fwdA[i] = t.invA[i] = uint2{0, 0};
+    for (int s = 0; s < loge; s++)
+        for (uint32_t b = 0; b < (1u << s); b++) {
+            const uint32_t w = fwd_tw_c(pr, logn, s, b), wi = invmod_c(w, q);
+            t.fwdA[(1 << s) - 1 + b] = uint2{w, shoup_c(w, q)};
+            t.invA[(1 << s) - 1 + b] = uint2{wi, shoup_c(wi, q)};
+        }
+}
+
+// 64-bit lazy accumulator -> [0, 2q), runtime prime
+TFHE_HD uint32_t reduce_acc64_rt(uint64_t a, const PrimeTab &p) {
+    uint32_t hi = (uint32_t)(a >> 32), lo = (uint32_t)a;
+    uint32_t r = shoup_mul(hi, p.c32, p.c32_s, p.q) + shoup_mul(lo, 1u, p.one_s, p.q);  // < 4q
+    return umin_u32(r, r - 2u * p.q);
 }
 
 // Position (in the transformed, bit-reversed domain) -> slot in the stored BSK row: thread t of
