@@ -47,7 +47,7 @@ struct Emu {
         const PrimeTab &pt = prime[PR];
         for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_T1<K>(regs[PR * K::T + th], th, jbase_B<C>(th), pt, t, g, bufp(PR, 0));
         for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F2<K>(regs[PR * K::T + th], jbase_B<C>(th), pt, bufp(PR, 0), bufp(PR, 1));
-        for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_T3<K>(regs[PR * K::T + th], th, pt, bufp(PR, 1), out);
+        for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_T3<K>(regs[PR * K::T + th], th, pt, t, bufp(PR, 1), out);
     }
     // raw GGSW [ROWS][P][N] -> [2][ROWS][P][N] (NTT domain, slot order)
     void transform_ggsw(const uint32_t *raw, uint32_t *ntt) {
@@ -69,7 +69,7 @@ struct Emu {
             for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F1<K>(R[th], th, jbase_B<C>(th), pt, t, dig.data(), r, bufp(PR, 0));
             for (uint32_t th = 0; th < (uint32_t)K::T; th++) phase_F2<K>(R[th], jbase_B<C>(th), pt, bufp(PR, 0), bufp(PR, 1));
             for (uint32_t th = 0; th < (uint32_t)K::T; th++) {
-                phase_F3a<K>(R[th], th, pt, bufp(PR, 1));
+                phase_F3a<K>(R[th], th, pt, t, bufp(PR, 1));
                 phase_F3b<K, true>(R[th], th, g_row);
             }
         }

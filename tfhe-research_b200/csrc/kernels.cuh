@@ -85,7 +85,7 @@ __device__ __forceinline__ void team_cmux(TeamRegs<K> &R, uint32_t pr, uint32_t 
         }
         phase_F2<K>(R, jbB, pt, buf0, buf1);
         team_bar(pr, K::T);
-        phase_F3a<K>(R, t, pt, buf1);
+        phase_F3a<K>(R, t, pt, tw, buf1);
         if constexpr (K::STAGE_G) {
             mbar_wait(bar, parity, err_flag);
             parity ^= 1u;
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const __grid_cons
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem + K::SM_ACC);
     uint8_t *dig = smem + K::SM_DIG;
-    uint32_t *res = reinterpret_cast<uint32_t *>(smem + K::SM_DIG);  // aliases dig (barrier-separated)
+    uint32_t *res = reinterpret_cast<uint32_t *>(smem + K::SM_RES);  // aliases the G rows (or dig), see PbsCfg
     uint32_t *buf = reinterpret_cast<uint32_t *>(smem + K::SM_BUF);
     uint16_t *at = reinterpret_cast<uint16_t *>(smem + K::SM_AT);
 
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const __grid_cons
         __syncthreads();
         const uint32_t *g = a.bsk_ntt + (size_t)gi * GGSW_WORDS + (size_t)pr * (K::ROWS * K::P * K::N);
         team_cmux<K>(R, pr, t, jbB, pt, tw, dig, buf0, buf1, g, gbuf, bar, parity, a.err_flag);
-        __syncthreads();  // both teams are done reading dig before res (same bytes) is written
+        if constexpr (!K::STAGE_G) __syncthreads();  // both teams are done reading dig before res (same bytes) is written
         team_inverse<K>(R, pr, t, jbB, pt, tw, buf0, buf1, res_pr);
         __syncthreads();
         phase_crt<K>(tid, res, acc);
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(K::THREADS) bsk_transform_kernel(const __grid_
     team_bar(pr, K::T);
     phase_F2<K>(R, jbB, pt, buf0, buf1);
     team_bar(pr, K::T);
-    phase_T3<K>(R, t, pt, buf1, o);
+    phase_T3<K>(R, t, pt, tw, buf1, o);
 }
 
 // ------------------------------------------------------------------------------------------ K3+K4

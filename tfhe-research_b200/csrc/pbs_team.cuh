@@ -18,7 +18,7 @@
 
 namespace tfhe {
 
-template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, bool STAGE_G_ = true>
+template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, bool STAGE_G_ = true, bool TWC_GLOBAL_ = false>
 struct PbsCfg {
     using Ntt = NttCfg<LOGN_, LOGE_>;
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_;
@@ -38,14 +38,20 @@ struct PbsCfg {
     static_assert((double)ROWS * (2 * LOGN + 2) * (double)kQ1 * (double)kQ1 < 18446744073709551616.0, "u64 MAC range");
     // GGSW rows are streamed global -> shared with cp.async.bulk (TMA) when STAGE_G, else read with LDG
     static constexpr bool STAGE_G = STAGE_G_;
+    // forward pass-C twiddles: resident in registers for the whole kernel, or re-loaded from global/L1 for
+    // every transform (saves 2*(E-1) registers; pays off when the kernel would otherwise spill)
+    static constexpr bool TWC_GLOBAL = TWC_GLOBAL_;
     static constexpr int G_ROW_BYTES = P * N * 4;  // one GGSW row of one prime
-    // shared memory carve-up (bytes).  dig[ROWS][N] (digits) and res[2][P][N] (inverse-NTT residues)
-    // share bytes: a CTA barrier separates the last digit read from the first residue write.
+    // shared memory carve-up (bytes).  res[2][P][N] (inverse-NTT residues) shares bytes with the staged GGSW
+    // rows when STAGE_G (a team only writes its own half, after its own last MAC; team barriers order the
+    // two), else with dig[ROWS][N] (a CTA barrier separates the last digit read from the first residue write).
     static constexpr int SM_ACC = 0;
     static constexpr int SM_DIG = SM_ACC + P * N * 4;
     static constexpr int DIG_BYTES_TOTAL = ROWS * N * DIG_BYTES, RES_BYTES_TOTAL = 2 * P * N * 4;
-    static constexpr int SM_BUF = SM_DIG + (((DIG_BYTES_TOTAL > RES_BYTES_TOTAL ? DIG_BYTES_TOTAL : RES_BYTES_TOTAL) + 127) & ~127);
+    static constexpr int DIG_REGION = STAGE_G ? DIG_BYTES_TOTAL : (DIG_BYTES_TOTAL > RES_BYTES_TOTAL ? DIG_BYTES_TOTAL : RES_BYTES_TOTAL);
+    static constexpr int SM_BUF = SM_DIG + ((DIG_REGION + 127) & ~127);
     static constexpr int SM_G = SM_BUF + ((2 * 2 * Ntt::NPAD * 4 + 127) & ~127);      // [2 primes][G_ROW_BYTES]
+    static constexpr int SM_RES = STAGE_G ? SM_G : SM_DIG;
     static constexpr int SM_BAR = SM_G + (STAGE_G ? 2 * G_ROW_BYTES : 0);              // 2 mbarriers
     static constexpr int SM_AT = SM_BAR + 16;  // mod-switched mask (u16), n+1 entries follow
 };
@@ -105,7 +111,7 @@ template <class K>
 struct TeamRegs {
     uint32_t x[K::E];
     uint64_t acc[K::P][K::E];
-    uint2 twC[K::Ntt::NC_TW];  // forward pass-C twiddles, resident for the whole kernel
+    uint2 twC[K::TWC_GLOBAL ? 1 : K::Ntt::NC_TW];  // forward pass-C twiddles when register resident
     uint2 twB[K::Ntt::NB_TW];  // pass-B twiddles, prefetched at the start of each transform
 };
 
@@ -118,8 +124,10 @@ struct TwTables {
 template <class K>
 TFHE_HD void team_init(TeamRegs<K> &r, const TwTables &tw, uint32_t t) {
     using C = typename K::Ntt;
+    if constexpr (!K::TWC_GLOBAL) {
 #pragma unroll
-    for (int i = 0; i < C::NC_TW; i++) r.twC[i] = ld_global_tw(tw.fwdC + t * C::NC_TW + i);
+        for (int i = 0; i < C::NC_TW; i++) r.twC[i] = ld_global_tw(tw.fwdC + t * C::NC_TW + i);
+    }
 }
 template <class K>
 TFHE_HD void team_zero_acc(TeamRegs<K> &r) {
@@ -154,7 +162,7 @@ TFHE_HD void phase_F1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, const PrimeTab &
         else d = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
         r.x[e] = d + (q - K::DIG_OFF);
     }
-    fwd_pass_A<C>(r.x, pt.fwdA, q);
+    fwd_pass_A<C>(r.x, pt.fwdA, q, pt.zero);
     store_A<C>(r.x, buf0, t);
 }
 // F2: layout B, pass B, store to buf1.
@@ -162,16 +170,24 @@ template <class K>
 TFHE_HD void phase_F2(TeamRegs<K> &r, uint32_t jbB, const PrimeTab &pt, const uint32_t *buf0, uint32_t *buf1) {
     using C = typename K::Ntt;
     load_B<C>(r.x, buf0, jbB);
-    fwd_pass_B<C>(r.x, r.twB, pt.q);
+    fwd_pass_B<C>(r.x, r.twB, pt.q, pt.zero);
     store_B<C>(r.x, buf1, jbB);
 }
 // F3a: layout C, pass C.   F3b: multiply-accumulate against GGSW row g_row = [P][N] words (bsk_slot order;
 // shared memory when staged by TMA, else global).
 template <class K>
-TFHE_HD void phase_F3a(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const uint32_t *buf1) {
+TFHE_HD void phase_F3a(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const TwTables &tw, const uint32_t *buf1) {
     using C = typename K::Ntt;
-    load_C<C>(r.x, buf1, t);
-    fwd_pass_C<C>(r.x, r.twC, pt.q);
+    if constexpr (K::TWC_GLOBAL) {
+        uint2 twc[C::NC_TW];
+#pragma unroll
+        for (int i = 0; i < C::NC_TW; i++) twc[i] = ld_global_tw(tw.fwdC + t * C::NC_TW + i);
+        load_C<C>(r.x, buf1, t);
+        fwd_pass_C<C>(r.x, twc, pt.q, pt.zero);
+    } else {
+        load_C<C>(r.x, buf1, t);
+        fwd_pass_C<C>(r.x, r.twC, pt.q, pt.zero);
+    }
 }
 template <class K, bool SHARED_G>
 TFHE_HD void phase_F3b(TeamRegs<K> &r, uint32_t t, const uint32_t *g_row) {
@@ -204,14 +220,14 @@ TFHE_HD void phase_I1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, int c, const Pri
             for (int e = 0; e < K::E; e++) r.x[e] = reduce_acc64_rt(r.acc[cc][e], pt);
         }
     });
-    inv_pass_C<C>(r.x, twc, pt.q);
+    inv_pass_C<C>(r.x, twc, pt.q, pt.zero);
     store_C<C>(r.x, buf0, t);
 }
 template <class K>
 TFHE_HD void phase_I2(TeamRegs<K> &r, uint32_t jbB, const PrimeTab &pt, const uint32_t *buf0, uint32_t *buf1) {
     using C = typename K::Ntt;
     load_B<C>(r.x, buf0, jbB);
-    inv_pass_B<C>(r.x, r.twB, pt.q);
+    inv_pass_B<C>(r.x, r.twB, pt.q, pt.zero);
     store_B<C>(r.x, buf1, jbB);
 }
 // I3: layout A, inverse pass A, store residues in natural order (unpadded) to res_c[N].
@@ -219,7 +235,7 @@ template <class K>
 TFHE_HD void phase_I3(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const uint32_t *buf1, uint32_t *res_c) {
     using C = typename K::Ntt;
     load_A<C>(r.x, buf1, t);
-    inv_pass_A<C>(r.x, pt.invA, pt.q);
+    inv_pass_A<C>(r.x, pt.invA, pt.q, pt.zero);
 #pragma unroll
     for (int e = 0; e < K::E; e++) res_c[(e << C::LOGT) | t] = r.x[e];
 }
@@ -247,16 +263,15 @@ TFHE_HD void phase_T1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, const PrimeTab &
     prefetch_twB<K>(r, tw.fwdB, jbB);
 #pragma unroll
     for (int e = 0; e < K::E; e++) r.x[e] = centred_residue(g[(e << C::LOGT) | t], pt.q);
-    fwd_pass_A<C>(r.x, pt.fwdA, pt.q);
+    fwd_pass_A<C>(r.x, pt.fwdA, pt.q, pt.zero);
     store_A<C>(r.x, buf0, t);
 }
 // T3: pass C, scale by N^-1 (so the inverse NTT needs no final scaling), reduce to [0,q), store in
 // bsk_slot order.
 template <class K>
-TFHE_HD void phase_T3(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const uint32_t *buf1, uint32_t *out) {
+TFHE_HD void phase_T3(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const TwTables &tw, const uint32_t *buf1, uint32_t *out) {
+    phase_F3a<K>(r, t, pt, tw, buf1);
     using C = typename K::Ntt;
-    load_C<C>(r.x, buf1, t);
-    fwd_pass_C<C>(r.x, r.twC, pt.q);
 #pragma unroll
     for (int e = 0; e < K::E; e++) out[bsk_slot<C>(t, e)] = csub(shoup_mul(r.x[e], pt.ninv, pt.ninv_s, pt.q), pt.q);
 }

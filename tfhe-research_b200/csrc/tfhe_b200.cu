@@ -115,10 +115,11 @@ int finish_out(tfhe_ctx *ctx, void *dst, size_t bytes, const void *dev) {
 #endif
 using K0 = PbsCfg<9, 3, 2, 6, 4, TFHE_STAGE_P0 != 0>;
 using K1 = PbsCfg<10, 4, 1, 3, 8, TFHE_STAGE_P1 != 0>;
-using K2 = PbsCfg<11, 4, 1, 3, 8, /*STAGE_G=*/false>;  // 32 KB of row staging would halve its occupancy
+using K2 = PbsCfg<11, 4, 1, 3, 8, /*STAGE_G=*/false, /*TWC_GLOBAL=*/true>;  // 32 KB of row staging would halve its occupancy;
+                                                                        // at 128 registers register-resident twiddles spill
 template <class K> struct MinBlocks;
 #ifndef TFHE_MINB_P0
-#define TFHE_MINB_P0 5
+#define TFHE_MINB_P0 4
 #endif
 #ifndef TFHE_MINB_P1
 #define TFHE_MINB_P1 3

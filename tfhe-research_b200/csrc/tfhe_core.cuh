@@ -31,6 +31,9 @@
 #ifndef TFHE_MULHI_WIDE
 #define TFHE_MULHI_WIDE 0
 #endif
+#ifndef TFHE_ADD3
+#define TFHE_ADD3 1
+#endif
 
 #if !defined(__CUDACC__)
 struct uint2 { uint32_t x, y; };  // host-only stand-in (tests/emu)
@@ -115,17 +118,29 @@ TFHE_HD uint32_t shoup_mul(uint32_t x, uint32_t w, uint32_t ws, uint32_t q) {
 // [0,2q) -> [0,q)
 TFHE_HD uint32_t csub(uint32_t x, uint32_t q) { return umin_u32(x, x - q); }
 
+// 32-bit add that ptxas must emit on the ALU pipe: a third addend `z` that is zero at run time but opaque at
+// compile time (a kernel-parameter word) makes it a genuine 3-input IADD3; a plain 2-input add is often
+// emitted as IMAD.IADD, which put ~15% more work on the binding FMA-heavy pipe (profiles/r01_v2_*).
+TFHE_HD uint32_t add_alu(uint32_t a, uint32_t b, uint32_t z) {
+#if TFHE_ADD3
+    return a + b + z;
+#else
+    (void)z;
+    return a + b;
+#endif
+}
+
 // Cooley-Tukey butterfly, no correction: inputs < B*q  ->  outputs < (B+2)*q.
-TFHE_HD void ct_bfly(uint32_t &X, uint32_t &Y, uint32_t w, uint32_t ws, uint32_t q) {
+TFHE_HD void ct_bfly(uint32_t &X, uint32_t &Y, uint32_t w, uint32_t ws, uint32_t q, uint32_t z = 0) {
     uint32_t T = shoup_mul(Y, w, ws, q);
     TFHE_CHECK((uint64_t)X + T < (1ull << 32) && (uint64_t)X + 2ull * q < (1ull << 32));
     Y = X - T + 2u * q;
-    X = X + T;
+    X = add_alu(X, T, z);
 }
 // Gentleman-Sande butterfly, inputs and outputs in [0, 2q).
-TFHE_HD void gs_bfly(uint32_t &X, uint32_t &Y, uint32_t w, uint32_t ws, uint32_t q) {
+TFHE_HD void gs_bfly(uint32_t &X, uint32_t &Y, uint32_t w, uint32_t ws, uint32_t q, uint32_t z = 0) {
     TFHE_CHECK(X < 2u * q && Y < 2u * q);
-    uint32_t S = X + Y;
+    uint32_t S = add_alu(X, Y, z);
     uint32_t D = X - Y + 2u * q;
     X = umin_u32(S, S - 2u * q);
     Y = shoup_mul(D, w, ws, q);
@@ -330,7 +345,7 @@ TFHE_HD void load_C(uint32_t *x, const uint32_t *buf, uint32_t t) {
 //
 // Pass over register bits [LO, LO+Q): stage u pairs bit LO+Q-1-u, twiddle index = top u bits of the field.
 template <int E, int LO, int Q>
-TFHE_HD void fwd_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q) {
+TFHE_HD void fwd_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) {
     static_for<0, Q>([&](auto ui) {
         constexpr int u = decltype(ui)::value;
         constexpr int bit = 1 << (LO + Q - 1 - u);
@@ -340,13 +355,13 @@ TFHE_HD void fwd_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q) {
                 constexpr int field = (e >> LO) & ((1 << Q) - 1);
                 constexpr int m = field >> (Q - u);
                 const uint2 w = tw[(1 << u) - 1 + m];
-                ct_bfly(x[e], x[e + bit], w.x, w.y, q);
+                ct_bfly(x[e], x[e + bit], w.x, w.y, q, z);
             }
         });
     });
 }
 template <int E, int LO, int Q>
-TFHE_HD void inv_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q) {
+TFHE_HD void inv_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) {
     static_for<0, Q>([&](auto ui) {
         constexpr int u = Q - 1 - decltype(ui)::value;
         constexpr int bit = 1 << (LO + Q - 1 - u);
@@ -356,7 +371,7 @@ TFHE_HD void inv_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q) {
                 constexpr int field = (e >> LO) & ((1 << Q) - 1);
                 constexpr int m = field >> (Q - u);
                 const uint2 w = tw[(1 << u) - 1 + m];
-                gs_bfly(x[e], x[e + bit], w.x, w.y, q);
+                gs_bfly(x[e], x[e + bit], w.x, w.y, q, z);
             }
         });
     });
@@ -365,19 +380,19 @@ TFHE_HD void inv_pass_bits(uint32_t *x, const uint2 *tw, uint32_t q) {
 //         every thread (kept in the kernel-parameter constant bank).
 // pass B: stages LOGE..LOGE+QB-1 on the mid bits (register bits [XB, XB+QB)); twB = w(LOGE+u, (hA<<u)|m).
 // pass C: stages LOGE+QB..LOGN-1 on the lo bits; twC = w(LOGE+QB+u, (t<<u)|m).
-template <class C> TFHE_HD void fwd_pass_A(uint32_t *x, const uint2 *tw, uint32_t q) { fwd_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
-template <class C> TFHE_HD void fwd_pass_B(uint32_t *x, const uint2 *tw, uint32_t q) { fwd_pass_bits<C::E, C::XB, C::QB>(x, tw, q); }
-template <class C> TFHE_HD void fwd_pass_C(uint32_t *x, const uint2 *tw, uint32_t q) { fwd_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
-template <class C> TFHE_HD void inv_pass_A(uint32_t *x, const uint2 *tw, uint32_t q) { inv_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
-template <class C> TFHE_HD void inv_pass_B(uint32_t *x, const uint2 *tw, uint32_t q) { inv_pass_bits<C::E, C::XB, C::QB>(x, tw, q); }
-template <class C> TFHE_HD void inv_pass_C(uint32_t *x, const uint2 *tw, uint32_t q) { inv_pass_bits<C::E, 0, C::LOGE>(x, tw, q); }
+template <class C> TFHE_HD void fwd_pass_A(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) { fwd_pass_bits<C::E, 0, C::LOGE>(x, tw, q, z); }
+template <class C> TFHE_HD void fwd_pass_B(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) { fwd_pass_bits<C::E, C::XB, C::QB>(x, tw, q, z); }
+template <class C> TFHE_HD void fwd_pass_C(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) { fwd_pass_bits<C::E, 0, C::LOGE>(x, tw, q, z); }
+template <class C> TFHE_HD void inv_pass_A(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) { inv_pass_bits<C::E, 0, C::LOGE>(x, tw, q, z); }
+template <class C> TFHE_HD void inv_pass_B(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) { inv_pass_bits<C::E, C::XB, C::QB>(x, tw, q, z); }
+template <class C> TFHE_HD void inv_pass_C(uint32_t *x, const uint2 *tw, uint32_t q, uint32_t z) { inv_pass_bits<C::E, 0, C::LOGE>(x, tw, q, z); }
 
 // Per-prime constants handed to the kernels by value (kernel-parameter constant bank; a warp only
 // ever reads its own prime's entry, so every access is a uniform LDC).
 constexpr int kMaxPassA = 15;  // E-1 for E = 16
 struct PrimeTab {
     uint32_t q, c32, c32_s, one_s;  // prime, 2^32 mod q, shoup(c32), floor(2^32/q)
-    uint32_t ninv, ninv_s, pad0, pad1;  // N^-1 mod q (key transform only)
+    uint32_t ninv, ninv_s, zero, pad1;  // N^-1 mod q (key transform only); zero: run-time 0 for add_alu
     uint2 fwdA[kMaxPassA + 1];
     uint2 invA[kMaxPassA + 1];
 };
@@ -389,7 +404,7 @@ inline void fill_prime_tab(int pr, int logn, int loge, PrimeTab &t) {
     t.one_s = shoup_c(1u, q);
     t.ninv = invmod_c((1u << logn) % q, q);
     t.ninv_s = shoup_c(t.ninv, q);
-    t.pad0 = t.pad1 = 0;
+    t.zero = t.pad1 = 0;
     for (int i = 0; i <= kMaxPassA; i++) t.fwdA[i] = t.invA[i] = uint2{0, 0};
     for (int s = 0; s < loge; s++)
         for (uint32_t b = 0; b < (1u << s); b++) {
