@@ -32,6 +32,7 @@ struct PbsArgs {
     uint32_t *glwe_out;        // [B][P][N]
     uint32_t *err_flag;        // bit 0: a test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out
     uint32_t n, batch, mode, log_p, enc_shift;
+    uint32_t skew_ns, skew_div, skew_mod;  // start-up stagger of co-resident CTAs (see pbs_kernel)
 };
 
 __device__ __forceinline__ void team_bar(int pr, int nthreads) {
@@ -137,6 +138,13 @@ __global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const __grid_cons
     }
     TeamRegs<K> R;
     team_init<K>(R, tw, t);
+
+    // Co-resident CTAs run identical phase sequences; started together they stay phase-locked and hit the
+    // FMA pipe in the same bursts.  An initial stagger of a fraction of a CMUX step de-phases them.
+    if (a.skew_ns) {
+        const uint32_t slot = (blockIdx.x / a.skew_div) % a.skew_mod;
+        for (uint32_t s = 0; s < slot; s++) __nanosleep(a.skew_ns);
+    }
 
     uint32_t n_steps;
     if (a.mode == 0) {
@@ -367,20 +375,48 @@ __global__ void sample_extract_kernel(const uint32_t *__restrict__ glwe, uint32_
 
 // ------------------------------------------------------------------------------------------ peaks
 // Integer-pipe peak microbenchmarks: 8 independent dependency chains per thread, 8-way unrolled.
+//   KIND 0 IMAD, 1 IMAD.HI, 2 IMAD.WIDE (64 lane-ops per inner iteration each);
+//   KIND 3 lazy Shoup/Harvey butterflies in registers exactly as the NTT passes issue them
+//          (IMAD.HI + 2 IMAD + 2 IADD3 each): 32 butterflies per inner iteration -- the achievable
+//          butterfly rate is the practical ceiling of the blind-rotation kernel.
 template <int KIND>
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t a, uint32_t b, int iters) {
     uint32_t x[8];
     unsigned long long y[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { x[i] = threadIdx.x + i; y[i] = x[i]; }
-    for (int it = 0; it < iters; it++) {
+    if (KIND >= 3) {
+        // KIND 3: one (w, ws) pair shared by all butterflies, q in a register.
+        // KIND 4: a different (w, ws) register pair per butterfly (as in the NTT passes), q in a register.
+        // KIND 5: like 4 with q as a compile-time immediate.
+        const uint32_t qr = (KIND == 5) ? kQ0 : (kQ0 + (b & 0u));
+        const uint32_t w = a % kQ0, ws = (uint32_t)(((unsigned long long)w << 32) / kQ0), z = b & 0u;
+        uint32_t wv[4], wsv[4];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int i = 0; i < 4; i++) { wv[i] = w + 17u * i * (KIND >= 4) + threadIdx.x * (KIND >= 4); wsv[i] = ws + 13u * i * (KIND >= 4); }
+        for (int it = 0; it < iters; it++) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (KIND == 0) x[i] = x[i] * a + b;                                  // IMAD
-                else if (KIND == 1) x[i] = __umulhi(x[i], a) + b;                    // IMAD.HI
-                else y[i] = (unsigned long long)(uint32_t)y[i] * a + y[i];         // IMAD.WIDE (loop-variant multiplicand)
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (KIND == 5) ct_bfly(x[i], x[i + 4], wv[i] + u, wsv[i], kQ0, z);
+                    else ct_bfly(x[i], x[i + 4], wv[i] + u, wsv[i], qr, z);
+                }
+                const uint32_t q = kQ0;
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = umin_u32(x[i], x[i] - 8u * q);  // keep the lazy range bounded (ALU only)
+            }
+        }
+    } else {
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (KIND == 0) x[i] = x[i] * a + b;                                  // IMAD
+                    else if (KIND == 1) x[i] = __umulhi(x[i], a) + b;                    // IMAD.HI
+                    else y[i] = (unsigned long long)(uint32_t)y[i] * a + y[i];         // IMAD.WIDE (loop-variant multiplicand)
+                }
             }
         }
     }

@@ -16,7 +16,15 @@
 #pragma once
 #include "tfhe_core.cuh"
 
+// unroll factor of the per-coefficient loops of the digit (D) and CRT (R) phases: independent iterations,
+// so unrolling lets the shared-memory loads of several coefficients overlap
+#ifndef TFHE_DR_UNROLL
+#define TFHE_DR_UNROLL 16
+#endif
+
 namespace tfhe {
+
+constexpr int kDrUnroll = TFHE_DR_UNROLL;
 
 template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, bool STAGE_G_ = true, bool TWC_GLOBAL_ = false>
 struct PbsCfg {
@@ -92,6 +100,7 @@ TFHE_HD uint2 ld_global_tw(const uint2 *p) {
 // diff_fn(p, j) returns coefficient j of polynomial p of the GLWE to decompose.
 template <class K, class DiffFn>
 TFHE_HD void phase_digits(uint32_t tid, uint8_t *dig_bytes, DiffFn diff_fn) {
+#pragma unroll(kDrUnroll)
     for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += K::THREADS) {
         const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
         int32_t d[K::L];
@@ -244,6 +253,7 @@ TFHE_HD void phase_I3(TeamRegs<K> &r, uint32_t t, const PrimeTab &pt, const uint
 // res = [2 primes][P][N]; out[c][j] = base[c][j] + lift(res)  (ggsw.rs:175 `res += glwe_ciphertext0`)
 template <class K>
 TFHE_HD void phase_crt(uint32_t tid, const uint32_t *res, uint32_t *acc) {
+#pragma unroll(kDrUnroll)
     for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += K::THREADS)
         acc[idx] += crt_to_u32(res[idx], res[K::P * K::N + idx]);
 }

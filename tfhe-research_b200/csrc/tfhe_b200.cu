@@ -2,6 +2,7 @@
 // the batched PBS entry points.  No CPU fallback: every entry point here needs a CUDA device.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -45,6 +46,7 @@ struct tfhe_ctx {
     DevBuf in0, in1, in2, out, glwe, digits, body, luts, lutidx, misc;
     uint32_t *d_err = nullptr;
     uint64_t launches = 0;
+    int sm_count = 148;
     cudaEvent_t ev[5] = {};
     double last_ms[3] = {0, 0, 0};
     size_t N() const { return (size_t)1 << p.glwe_poly_degree; }
@@ -114,7 +116,10 @@ int finish_out(tfhe_ctx *ctx, void *dst, size_t bytes, const void *dev) {
 #define TFHE_STAGE_P1 1
 #endif
 using K0 = PbsCfg<9, 3, 2, 6, 4, TFHE_STAGE_P0 != 0>;
-using K1 = PbsCfg<10, 4, 1, 3, 8, TFHE_STAGE_P1 != 0>;
+#ifndef TFHE_TWCG_P1
+#define TFHE_TWCG_P1 0
+#endif
+using K1 = PbsCfg<10, 4, 1, 3, 8, TFHE_STAGE_P1 != 0, TFHE_TWCG_P1 != 0>;
 using K2 = PbsCfg<11, 4, 1, 3, 8, /*STAGE_G=*/false, /*TWC_GLOBAL=*/true>;  // 32 KB of row staging would halve its occupancy;
                                                                         // at 128 registers register-resident twiddles spill
 template <class K> struct MinBlocks;
@@ -213,6 +218,12 @@ int run_bootstrap(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *d_in, const 
     a.n = (uint32_t)ctx->n(); a.batch = (uint32_t)batch; a.mode = 0;
     a.log_p = ctx->p.log_p;
     a.enc_shift = ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits);
+    if (const char *e = getenv("TFHE_B200_SKEW_NS")) {
+        a.skew_ns = (uint32_t)atoi(e);
+        a.skew_div = (uint32_t)ctx->sm_count;
+        a.skew_mod = 3;
+        if (const char *m = getenv("TFHE_B200_SKEW_MOD")) a.skew_mod = (uint32_t)atoi(m);
+    }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     int rc = launch_pbs(ctx, a);
     if (rc) return rc;
@@ -263,6 +274,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     for (auto &e : ctx->ev)
         if (cudaEventCreate(&e) != cudaSuccess) return bail("cudaEventCreate");
     if (cudaMalloc(&ctx->d_err, 4) != cudaSuccess) return bail("cudaMalloc");
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     // per-thread twiddle tables
     const int loge = (p->glwe_poly_degree == 9) ? 3 : 4;
     HostTw tw;
@@ -610,7 +622,7 @@ int tfhe_gate_linear(tfhe_ctx *ctx, const uint32_t *ct0, const uint32_t *ct1, si
     return TFHE_OK;
 }
 
-int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[3]) {
+int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[6]) {
     if (!ctx || !out) return TFHE_E_PARAM;
     CU(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
@@ -621,18 +633,21 @@ int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[3]) {
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
-    for (int kind = 0; kind < 3; kind++) {
+    for (int kind = 0; kind < 6; kind++) {
         double best = 0;
         for (int rep = 0; rep < 4; rep++) {
             CU(cudaEventRecord(e0, ctx->stream));
             if (kind == 0) int_peak_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, iters);
             else if (kind == 1) int_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, iters);
-            else int_peak_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, iters);
+            else if (kind == 2) int_peak_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, iters);
+            else if (kind == 3) int_peak_kernel<3><<<blocks, 256, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, iters);
+            else if (kind == 4) int_peak_kernel<4><<<blocks, 256, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, iters);
+            else int_peak_kernel<5><<<blocks, 256, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, iters);
             CU(cudaEventRecord(e1, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
             float ms = 0;
             CU(cudaEventElapsedTime(&ms, e0, e1));
-            const double ops = (double)blocks * 256.0 * iters * 64.0;
+            const double ops = (double)blocks * 256.0 * iters * (kind >= 3 ? 32.0 : 64.0);
             const double rate = ops / (ms * 1e-3);
             if (rep > 0 && rate > best) best = rate;  // first repetition is warm-up
             ctx->launches++;
