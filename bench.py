@@ -236,11 +236,25 @@ def main():
     bsk_bytes = 2 * p.bsk_words * 4
     waves = -(-B // (148 * 4))
     hbm_alg = bsk_bytes * waves + B * (p.n + 1) * 4 + B * p.glwe_words * 4
+    # practical ceiling of this instruction mix: butterflies only, at the measured register-resident
+    # Shoup-butterfly rate (IMAD.HI and IMAD.WIDE issue at HALF the plain IMAD rate on B200)
+    P_, l_ = p.k + 1, p.pbs_levels
+    bfly_per_launch = B * p.n * 2 * (p.N // 2) * p.glwe_poly_degree * (P_ * l_ + P_)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("preset") == args.preset and tj.get("batch") == B:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     roofline = {"bound": "int32-imad", "achieved": achieved / 1e12, "peak": peaks["imad"] / 1e12, "unit": "T IMAD-class lane-ops/s",
-                "frac": achieved / peaks["imad"], "traffic": None, "kernel": "pbs_kernel (blind rotation)", "kernel_ms": t_br,
-                "peak_source": "measured live: tfhe_measure_int_peak (dependent-free IMAD loop); imad_hi / imad_wide alongside",
+                "frac": achieved / peaks["imad"], "traffic": traffic, "kernel": "pbs_kernel (blind rotation)", "kernel_ms": t_br,
+                "peak_source": "measured live: tfhe_measure_int_peak (dependent-free IMAD loop); imad_hi / imad_wide / Shoup-butterfly rates alongside",
                 "peaks": {k: v / 1e12 for k, v in peaks.items()},
                 "algorithmic_ops_per_launch": ops_per_launch,
+                "butterflies_per_launch": bfly_per_launch,
+                "frac_of_butterfly_ceiling": (bfly_per_launch / (t_br * 1e-3)) / peaks["shoup_butterfly"],
+                "note": "IMAD.HI/IMAD.WIDE are half-rate, so a Shoup butterfly (1 HI + 2 IMAD) holds the FMA-heavy pipe for 8 cycles per warp, "
+                        "not the 6 the 3-ops-per-butterfly accounting assumes; ncu FMA-heavy pipe utilisation is in profiles/",
                 "hbm": {"algorithmic_bytes_per_launch": hbm_alg, "achieved_gbs": hbm_alg / (t_br * 1e-3) / 1e9, "peak_gbs": 6548.5,
                         "frac": hbm_alg / (t_br * 1e-3) / 1e9 / 6548.5, "note": "not the binding roofline (integer pipe binds by >100x)"}}
     line = {"metric": "PBS/sec", "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
