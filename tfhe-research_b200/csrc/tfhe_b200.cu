@@ -115,7 +115,10 @@ int finish_out(tfhe_ctx *ctx, void *dst, size_t bytes, const void *dev) {
 #ifndef TFHE_STAGE_P1
 #define TFHE_STAGE_P1 1
 #endif
-using K0 = PbsCfg<9, 3, 2, 6, 4, TFHE_STAGE_P0 != 0>;
+#ifndef TFHE_TWCG_P0
+#define TFHE_TWCG_P0 1
+#endif
+using K0 = PbsCfg<9, 3, 2, 6, 4, TFHE_STAGE_P0 != 0, TFHE_TWCG_P0 != 0>;
 #ifndef TFHE_TWCG_P1
 #define TFHE_TWCG_P1 0
 #endif
