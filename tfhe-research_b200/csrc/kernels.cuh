@@ -80,6 +80,9 @@ __device__ __forceinline__ void team_cmux(TeamRegs<K> &R, uint32_t pr, uint32_t 
         team_bar(pr, K::T);  // also: every thread of the team is done reading gbuf (row r-1)
         if constexpr (K::STAGE_G) {
             if (t == 0) {
+                // the staging buffer was last touched through the generic proxy (LDS of row r-1, or the residue
+                // stores/loads that alias it): order those before the async-proxy write of the bulk copy
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_expect_tx(bar, K::G_ROW_BYTES);
                 bulk_g2s(gbuf, g + (size_t)r * K::P * K::N, K::G_ROW_BYTES, bar);
             }
