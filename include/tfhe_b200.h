@@ -121,6 +121,11 @@ int tfhe_decompose(tfhe_ctx *ctx, int which, const uint32_t *values, size_t len,
 /* glwe.rs:20-34: out[b] = glwe[b] * X^{index[b]} (index as in Monomial, may be negative) */
 int tfhe_glwe_mul_monomial(tfhe_ctx *ctx, const uint32_t *glwe /* [B][k+1][N] */, const int64_t *index /* [B], host */,
                            size_t batch, uint32_t *out);
+/* utils.rs:155-160 poly_mul (the Toeplitz product) for a batch of pairs: out[b] = a[b] (*) g[b] in
+ * Z_{2^32}[X]/(X^N+1).  a[b] holds SMALL SIGNED coefficients, |a| <= 1024 (the digit range of the path; larger
+ * values would leave the exact range of the 2-prime transform and are rejected with TFHE_E_PARAM), g[b] any u32. */
+int tfhe_negacyclic_mul(tfhe_ctx *ctx, const int32_t *a /* [B][N], host or device */, const uint32_t *g /* [B][N] */,
+                        size_t batch, uint32_t *out /* [B][N] */);
 /* ggsw.rs:132-161: out[b] = external_product(BSK[ggsw_index[b]], glwe[b]) */
 int tfhe_external_product(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *ggsw_index /* [B], host */,
                           const uint32_t *glwe, size_t batch, uint32_t *out);

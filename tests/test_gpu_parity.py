@@ -188,3 +188,28 @@ def test_reference_defaults_full_n_one_gate():
     out = e.ctx.gate(e.bk, T.NAND, ct0, ct1)
     assert np.array_equal(out[0], orc.gate(e.o, 3, ct0[0], ct1[0], e.bsk, e.ksk))
     assert e.dec(out[0]) == 0
+
+
+@pytest.mark.parametrize("preset,n", CASES)
+def test_negacyclic_mul_utils_rs_155(preset, n):
+    """poly_mul (Toeplitz product, utils.rs:113-160) of signed digit-range polynomials with arbitrary u32 polynomials."""
+    e = env(preset, n)
+    L = orc.lib()
+    N = e.p.N
+    rng = np.random.default_rng(9)
+    B = 6
+    a = rng.integers(-1024, 1025, (B, N)).astype(np.int32)
+    a[0, :4] = [1024, -1024, 0, 1]
+    a[1] = 0
+    a[1, 1] = 1                                     # times X: a pure negacyclic shift
+    g = r32(rng, B, N)
+    g[2] = 0xFFFFFFFF
+    got = e.ctx.negacyclic_mul(a, g)
+    for b in range(B):
+        exp = orc.z(N)
+        L.orc_poly_mul(a[b].astype(np.uint32), g[b], N, exp)
+        assert np.array_equal(got[b], exp), b
+    assert np.array_equal(got[1], np.concatenate([(-g[1, -1:].astype(np.int64) & 0xFFFFFFFF).astype(np.uint32), g[1, :-1]]))
+    with pytest.raises(T.TfheError) as ei:
+        e.ctx.negacyclic_mul(np.full((1, N), 5000, dtype=np.int32), g[:1])
+    assert ei.value.code == T.TFHE_E_PARAM

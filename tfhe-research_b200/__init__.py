@@ -111,6 +111,7 @@ def lib():
         "tfhe_gate_batch": [VP, VP, C.c_int, VP, VP, SZ, VP], "tfhe_gates_batch": [VP, VP, VP, VP, VP, SZ, VP],
         "tfhe_switch_modulus": [VP, VP, SZ, VP], "tfhe_decompose": [VP, C.c_int, VP, SZ, VP],
         "tfhe_glwe_mul_monomial": [VP, VP, VP, SZ, VP],
+        "tfhe_negacyclic_mul": [VP, VP, VP, SZ, VP],
         "tfhe_external_product": [VP, VP, VP, VP, SZ, VP], "tfhe_cmux": [VP, VP, VP, VP, VP, SZ, VP],
         "tfhe_blind_rotate": [VP, VP, VP, VP, SZ, VP, SZ, VP],
         "tfhe_sample_extract": [VP, VP, SZ, VP], "tfhe_key_switch": [VP, VP, VP, SZ, VP],
@@ -135,7 +136,7 @@ EXPORTS = [
     "tfhe_lwe_decrypt", "tfhe_keygen", "tfhe_ctx_create", "tfhe_ctx_destroy", "tfhe_last_error", "tfhe_ctx_set_stream",
     "tfhe_ctx_launch_count", "tfhe_bk_upload", "tfhe_bk_free", "tfhe_bootstrap_batch", "tfhe_gate_batch",
     "tfhe_gates_batch", "tfhe_switch_modulus", "tfhe_decompose", "tfhe_glwe_mul_monomial", "tfhe_external_product",
-    "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
+    "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
     "tfhe_measure_int_peak", "tfhe_last_timing",
 ]
 
@@ -350,6 +351,14 @@ class Context:
         index = np.ascontiguousarray(index, dtype=np.int64)
         out = _like(glwe, glwe.shape)
         self._ck(lib().tfhe_glwe_mul_monomial(self._h, _ptr(glwe), index.ctypes.data, len(index), _ptr(out)))
+        return out
+
+    def negacyclic_mul(self, a_small, g):
+        """utils.rs:155-160 poly_mul: a_small int32 [B, N] with |a| <= 1024, g uint32 [B, N]."""
+        a_small = np.ascontiguousarray(a_small, dtype=np.int32)
+        g = _u32(g)
+        out = np.empty(g.shape, dtype=np.uint32)
+        self._ck(lib().tfhe_negacyclic_mul(self._h, a_small.ctypes.data, _ptr(g), g.shape[0], out.ctypes.data))
         return out
 
     def external_product(self, bk, ggsw_index, glwe):

@@ -321,6 +321,68 @@ __global__ void __launch_bounds__(KS_THREADS) ks_gemm_kernel(const int8_t *__res
     }
 }
 
+// ------------------------------------------------------------------------------------------ sub-op: poly_mul
+// utils.rs:155-160 poly_mul (Toeplitz product) for a batch of pairs: out[b] = a[b] (*) g[b] in Z_{2^32}[X]/(X^N+1),
+// a = small signed coefficients (|a| <= amax checked on the host so that N*amax*2^31 < Q0*Q1/2), g = arbitrary u32.
+// Same team code as the blind rotation: NTT(a) * NTT(centred g) * N^-1 per prime, inverse NTT, CRT.
+struct PolyMulArgs {
+    PrimeTab prime[2];
+    TwTables tw[2];
+    const int32_t *a;   // [B][N]
+    const uint32_t *g;  // [B][N]
+    uint32_t *out;      // [B][N]
+};
+template <class K>
+__global__ void __launch_bounds__(K::THREADS) polymul_kernel(const __grid_constant__ PolyMulArgs a) {
+    using C = typename K::Ntt;
+    __shared__ __align__(16) uint32_t buf[2 * 2 * C::NPAD];
+    const uint32_t tid = threadIdx.x, pr = tid / K::T, t = tid % K::T;
+    const uint32_t jbB = jbase_B<C>(t);
+    const PrimeTab &pt = a.prime[pr];
+    const TwTables &tw = a.tw[pr];
+    uint32_t *buf0 = buf + (pr * 2) * C::NPAD, *buf1 = buf0 + C::NPAD;
+    uint32_t *res_pr = buf0;  // the team's first exchange buffer is free once the last pass has read buf1
+    const int32_t *pa = a.a + (size_t)blockIdx.x * K::N;
+    const uint32_t *pg = a.g + (size_t)blockIdx.x * K::N;
+    TeamRegs<K> R;
+    team_init<K>(R, tw, t);
+    uint32_t ahat[K::E];
+    // forward NTT of a (signed small -> [0, q))
+    prefetch_twB<K>(R, tw.fwdB, jbB);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const int32_t v = pa[(e << C::LOGT) | t];
+        R.x[e] = v < 0 ? pt.q - (uint32_t)(-v) : (uint32_t)v;
+    }
+    fwd_pass_A<C>(R.x, pt.fwdA, pt.q, pt.zero);
+    store_A<C>(R.x, buf0, t);
+    team_bar(pr, K::T);
+    phase_F2<K>(R, jbB, pt, buf0, buf1);
+    team_bar(pr, K::T);
+    phase_F3a<K>(R, t, pt, tw, buf1);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) ahat[e] = csub(shoup_mul(R.x[e], 1u, pt.one_s, pt.q), pt.q);  // reduce to [0, q)
+    // forward NTT of g, pointwise product, scale by N^-1
+    phase_T1<K>(R, t, jbB, pt, tw, pg, buf0);
+    team_bar(pr, K::T);
+    phase_F2<K>(R, jbB, pt, buf0, buf1);
+    team_bar(pr, K::T);
+    phase_F3a<K>(R, t, pt, tw, buf1);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t ghat = csub(shoup_mul(R.x[e], pt.ninv, pt.ninv_s, pt.q), pt.q);
+        R.acc[0][e] = (uint64_t)ahat[e] * ghat;
+    }
+    phase_I1<K>(R, t, jbB, 0, pt, tw, buf0);
+    team_bar(pr, K::T);
+    phase_I2<K>(R, jbB, pt, buf0, buf1);
+    team_bar(pr, K::T);
+    phase_I3<K>(R, t, pt, buf1, res_pr);
+    __syncthreads();
+    uint32_t *o = a.out + (size_t)blockIdx.x * K::N;
+    for (uint32_t j = tid; j < (uint32_t)K::N; j += K::THREADS) o[j] = crt_to_u32(buf[j], buf[2 * C::NPAD + j]);
+}
+
 // ------------------------------------------------------------------------------------------ K5
 // boolean.rs:18  ct_in = 2*ct1 + ct0   (lwe.rs:9-23)
 __global__ void gate_linear_kernel(const uint32_t *__restrict__ ct0, const uint32_t *__restrict__ ct1, uint32_t *__restrict__ out, size_t len) {

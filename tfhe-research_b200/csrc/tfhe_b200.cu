@@ -250,6 +250,18 @@ int finish_timed(tfhe_ctx *ctx) {
     return TFHE_OK;
 }
 
+template <class K>
+int launch_polymul_t(tfhe_ctx *ctx, const int32_t *a, const uint32_t *g, uint32_t *out, size_t batch) {
+    PolyMulArgs pa;
+    pa.prime[0] = ctx->prime[0]; pa.prime[1] = ctx->prime[1];
+    pa.tw[0] = ctx->tw[0]; pa.tw[1] = ctx->tw[1];
+    pa.a = a; pa.g = g; pa.out = out;
+    polymul_kernel<K><<<(unsigned)batch, K::THREADS, 0, ctx->stream>>>(pa);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return TFHE_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -604,6 +616,32 @@ int tfhe_key_switch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, si
     if ((rc = stage_out(ctx, lwe_out, out_bytes, ctx->out, &d_out))) return rc;
     if ((rc = run_key_switch(ctx, bk, (const uint32_t *)d_in, 1, batch, (uint32_t *)d_out))) return rc;
     if ((rc = finish_out(ctx, lwe_out, out_bytes, d_out))) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TFHE_OK;
+}
+
+int tfhe_negacyclic_mul(tfhe_ctx *ctx, const int32_t *a, const uint32_t *g, size_t batch, uint32_t *out) {
+    if (!ctx || !a || !g || !out) return TFHE_E_PARAM;
+    if (batch == 0) return TFHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = batch * ctx->N() * 4;
+    // range check of the small operand (on a host copy: this is a parity-test entry point, not a hot path)
+    std::vector<int32_t> ha(batch * ctx->N());
+    CU(cudaMemcpy(ha.data(), a, bytes, cudaMemcpyDefault));
+    for (int32_t v : ha)
+        if (v > 1024 || v < -1024) return fail(ctx, TFHE_E_PARAM, "tfhe_negacyclic_mul: |a| > 1024 is outside the exact range");
+    const void *d_a, *d_g; void *d_out; int rc;
+    if ((rc = stage_in(ctx, a, bytes, ctx->in0, &d_a))) return rc;
+    if ((rc = stage_in(ctx, g, bytes, ctx->in1, &d_g))) return rc;
+    if ((rc = stage_out(ctx, out, bytes, ctx->out, &d_out))) return rc;
+    switch (ctx->pbs_id) {
+    case 0: rc = launch_polymul_t<K0>(ctx, (const int32_t *)d_a, (const uint32_t *)d_g, (uint32_t *)d_out, batch); break;
+    case 1: rc = launch_polymul_t<K1>(ctx, (const int32_t *)d_a, (const uint32_t *)d_g, (uint32_t *)d_out, batch); break;
+    case 2: rc = launch_polymul_t<K2>(ctx, (const int32_t *)d_a, (const uint32_t *)d_g, (uint32_t *)d_out, batch); break;
+    default: rc = fail(ctx, TFHE_E_PARAM, "no kernel instantiation");
+    }
+    if (rc) return rc;
+    if ((rc = finish_out(ctx, out, bytes, d_out))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     return TFHE_OK;
 }
