@@ -146,8 +146,10 @@ int tfhe_gate_linear(tfhe_ctx *ctx, const uint32_t *ct0, const uint32_t *ct1, si
 /* Measures the integer-pipe peaks of this device with dependent-free unrolled loops:
  * out[0] = 32-bit IMAD lane-ops/s, out[1] = IMAD.HI (mul.hi.u32), out[2] = IMAD.WIDE (mad.wide.u32),
  * out[3..5] = lazy Shoup NTT butterflies/s (IMAD.HI + 2 IMAD + 2 IADD3 each) issued from registers:
- * [3] one shared twiddle, [4] per-butterfly twiddle registers (as in the NTT passes), [5] like [4], q immediate. */
-int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[6]);
+ * [3] one shared twiddle, [4] per-butterfly twiddle registers (as in the NTT passes), [5] like [4], q immediate;
+ * out[6..7] = FMA-bound butterfly stream (16 values, 8 twiddle pairs in registers, no corrections) with 128-thread
+ * CTAs at 3 and at 8 CTAs per SM -- the blind-rotation kernel's own residency and a saturating one. */
+int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[8]);
 /* Device time (ms, CUDA events on the ctx stream) of the last tfhe_bootstrap_batch / tfhe_gate(s)_batch:
  * out[0] blind rotation kernel, out[1] key-switch kernels, out[2] whole call incl. copies. */
 int tfhe_last_timing(const tfhe_ctx *ctx, double out[3]);

@@ -116,7 +116,7 @@ def lib():
         "tfhe_blind_rotate": [VP, VP, VP, VP, SZ, VP, SZ, VP],
         "tfhe_sample_extract": [VP, VP, SZ, VP], "tfhe_key_switch": [VP, VP, VP, SZ, VP],
         "tfhe_gate_linear": [VP, VP, VP, SZ, VP],
-        "tfhe_measure_int_peak": [VP, C.POINTER(C.c_double * 6)], "tfhe_last_timing": [VP, C.POINTER(C.c_double * 3)],
+        "tfhe_measure_int_peak": [VP, C.POINTER(C.c_double * 8)], "tfhe_last_timing": [VP, C.POINTER(C.c_double * 3)],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -409,10 +409,11 @@ class Context:
         return out
 
     def measure_int_peak(self):
-        out = (C.c_double * 6)()
+        out = (C.c_double * 8)()
         self._ck(lib().tfhe_measure_int_peak(self._h, C.byref(out)))
         return {"imad": out[0], "imad_hi": out[1], "imad_wide": out[2], "shoup_butterfly_shared_tw": out[3],
-                "shoup_butterfly": out[4], "shoup_butterfly_imm_q": out[5]}
+                "shoup_butterfly": out[4], "shoup_butterfly_imm_q": out[5],
+                "butterfly_stream_3cta": out[6], "butterfly_stream_8cta": out[7]}
 
     def last_timing(self):
         out = (C.c_double * 3)()

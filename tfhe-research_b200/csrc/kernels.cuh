@@ -13,6 +13,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef TFHE_MERGE_ROWS
+#define TFHE_MERGE_ROWS 0
+#endif
+
 #include "pbs_team.cuh"
 
 namespace tfhe {
@@ -74,6 +78,37 @@ __device__ __forceinline__ void team_cmux(TeamRegs<K> &R, uint32_t pr, uint32_t 
                                           const uint8_t *dig, uint32_t *buf0, uint32_t *buf1, const uint32_t *g, uint32_t *gbuf,
                                           uint64_t *bar, uint32_t &parity, uint32_t *err_flag) {
     team_zero_acc<K>(R);
+#if TFHE_MERGE_ROWS
+    // Software pipelining across rows: the last pass + multiply-accumulate of row r share one barrier interval
+    // with the digit load + first pass of row r+1, so the scheduler has two independent instruction streams.
+    phase_F1<K>(R, t, jbB, pt, tw, dig, 0, buf0);
+    team_bar(pr, K::T);
+#pragma unroll 1
+    for (int r = 0; r < K::ROWS; r++) {
+        if constexpr (K::STAGE_G) {
+            if (t == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, K::G_ROW_BYTES);
+                bulk_g2s(gbuf, g + (size_t)r * K::P * K::N, K::G_ROW_BYTES, bar);
+            }
+        }
+        phase_F2<K>(R, jbB, pt, buf0, buf1);
+        team_bar(pr, K::T);
+        phase_F3a<K>(R, t, pt, tw, buf1);
+        if (r + 1 < K::ROWS) {
+            uint32_t y[K::E];
+            phase_F1x<K>(y, t, pt, dig, r + 1, buf0);   // buf0 was last read before the previous barrier
+        }
+        if constexpr (K::STAGE_G) {
+            mbar_wait(bar, parity, err_flag);
+            parity ^= 1u;
+            phase_F3b<K, true>(R, t, gbuf);
+        } else {
+            phase_F3b<K, false>(R, t, g + (size_t)r * K::P * K::N);
+        }
+        team_bar(pr, K::T);  // buf0 (row r+1) complete; gbuf and buf1 free again
+    }
+#else
 #pragma unroll 1
     for (int r = 0; r < K::ROWS; r++) {
         phase_F1<K>(R, t, jbB, pt, tw, dig, r, buf0);
@@ -98,6 +133,7 @@ __device__ __forceinline__ void team_cmux(TeamRegs<K> &R, uint32_t pr, uint32_t 
             phase_F3b<K, false>(R, t, g + (size_t)r * K::P * K::N);
         }
     }
+#endif
 }
 template <class K>
 __device__ __forceinline__ void team_inverse(TeamRegs<K> &R, uint32_t pr, uint32_t t, uint32_t jbB, const PrimeTab &pt, const TwTables &tw,
@@ -489,6 +525,32 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, uint32_t 
 #pragma unroll
     for (int i = 0; i < 8; i++) s += x[i] + (uint32_t)y[i] + (uint32_t)(y[i] >> 32);
     if (s == 0x12345678u) sink[0] = s;
+}
+
+// FMA-bound butterfly stream with realistic register variety: 16 values, 8 butterflies per stage with 8 distinct
+// (w, ws) register pairs, 4 stages per round like one register pass; no range corrections (values may wrap --
+// only the instruction stream matters).  64 butterflies... 32 per inner iteration (4 stages x 8).
+__global__ void __launch_bounds__(128, 3) bfly_stream_kernel(uint32_t *sink, uint32_t a, uint32_t b, int iters) {
+    uint32_t x[16];
+    uint2 tw[8];
+    const uint32_t q = kQ0 + (b & 0u), z = b & 0u;
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = threadIdx.x * 7u + i;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tw[i] = uint2{a % kQ0 + 17u * i + threadIdx.x, a + 13u * i};
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const int half = 8 >> s;
+#pragma unroll
+            for (int e = 0; e < 16; e++)
+                if ((e & half) == 0) ct_bfly(x[e], x[e + half], tw[(e + s) & 7].x, tw[(e + s) & 7].y, q, z);
+        }
+    }
+    uint32_t sacc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) sacc += x[i];
+    if (sacc == 0x12345678u) sink[0] = sacc;
 }
 
 }  // namespace tfhe

@@ -155,10 +155,17 @@ TFHE_HD void prefetch_twB(TeamRegs<K> &r, const uint2 *tabB, uint32_t jbB) {
 
 // F1: load the E digits of row `row` (layout A), lift to [q-B/2, q+B], pass A, store to buf0.
 template <class K>
+TFHE_HD void phase_F1x(uint32_t *x, uint32_t t, const PrimeTab &pt, const uint8_t *dig_bytes, uint32_t row, uint32_t *buf0);
+template <class K>
 TFHE_HD void phase_F1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, const PrimeTab &pt, const TwTables &tw, const uint8_t *dig_bytes,
                       uint32_t row, uint32_t *buf0) {
-    using C = typename K::Ntt;
     prefetch_twB<K>(r, tw.fwdB, jbB);
+    phase_F1x<K>(r.x, t, pt, dig_bytes, row, buf0);
+}
+// same on an explicit register array (used when row r+1's first pass is overlapped with row r's last pass)
+template <class K>
+TFHE_HD void phase_F1x(uint32_t *x, uint32_t t, const PrimeTab &pt, const uint8_t *dig_bytes, uint32_t row, uint32_t *buf0) {
+    using C = typename K::Ntt;
     const uint32_t q = pt.q;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(dig_bytes + (size_t)row * K::N * K::DIG_BYTES);
     uint32_t w[K::DIG_WORDS];
@@ -169,10 +176,10 @@ TFHE_HD void phase_F1(TeamRegs<K> &r, uint32_t t, uint32_t jbB, const PrimeTab &
         uint32_t d;
         if constexpr (K::DIG_BYTES == 1) d = (w[e >> 2] >> (8 * (e & 3))) & 0xFFu;
         else d = (w[e >> 1] >> (16 * (e & 1))) & 0xFFFFu;
-        r.x[e] = d + (q - K::DIG_OFF);
+        x[e] = d + (q - K::DIG_OFF);
     }
-    fwd_pass_A<C>(r.x, pt.fwdA, q, pt.zero);
-    store_A<C>(r.x, buf0, t);
+    fwd_pass_A<C>(x, pt.fwdA, q, pt.zero);
+    store_A<C>(x, buf0, t);
 }
 // F2: layout B, pass B, store to buf1.
 template <class K>

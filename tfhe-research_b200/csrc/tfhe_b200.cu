@@ -663,7 +663,7 @@ int tfhe_gate_linear(tfhe_ctx *ctx, const uint32_t *ct0, const uint32_t *ct1, si
     return TFHE_OK;
 }
 
-int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[6]) {
+int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[8]) {
     if (!ctx || !out) return TFHE_E_PARAM;
     CU(cudaSetDevice(ctx->device));
     cudaDeviceProp prop;
@@ -694,6 +694,23 @@ int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[6]) {
             ctx->launches++;
         }
         out[kind] = best;
+    }
+    // FMA-bound butterfly stream at the blind-rotation kernel's residency (128-thread CTAs, 3 and 8 per SM)
+    for (int cfg = 0; cfg < 2; cfg++) {
+        const int per_sm = cfg == 0 ? 3 : 8, nblocks = prop.multiProcessorCount * per_sm, it2 = 8192;
+        double best = 0;
+        for (int rep = 0; rep < 3; rep++) {
+            CU(cudaEventRecord(e0, ctx->stream));
+            bfly_stream_kernel<<<nblocks, 128, 0, ctx->stream>>>(sink, 0x9E3779B1u, 12345u, it2);
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            const double rate = (double)nblocks * 128.0 * it2 * 32.0 / (ms * 1e-3);
+            if (rep > 0 && rate > best) best = rate;
+            ctx->launches++;
+        }
+        out[6 + cfg] = best;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
