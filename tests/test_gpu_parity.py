@@ -132,6 +132,9 @@ def test_blind_rotate_extract_keyswitch_bootstrap(preset, n):
         assert np.array_equal(out[b], orc.bootstrap(e.o, cts[b], e.bsk, e.ksk, tvs[idx[b]])), b
     for b in range(0, B - 2, 2):                     # identity LUT ciphertexts decrypt to their message
         assert e.dec(out[b]) == b % pm
+    for nb in (1, 3, 8):                             # small batches take the split-row (atomic) key-switch path
+        assert np.array_equal(e.ctx.key_switch(e.bk, ext[:nb]), ks[:nb]), nb
+        assert np.array_equal(e.ctx.bootstrap(e.bk, cts[:nb], tvs, idx[:nb]), out[:nb]), nb
 
 
 @pytest.mark.parametrize("preset,n", [("P0", 4), ("P1", 3)])

@@ -357,6 +357,62 @@ __global__ void __launch_bounds__(KS_THREADS) ks_gemm_kernel(const int8_t *__res
     }
 }
 
+// Small-batch key switch (latency path): the KSK (tens of MB) is the only traffic that matters, so the rows are
+// split over many CTAs and partial sums are combined with u32 atomics (addition mod 2^32 is associative, so the
+// result is bit-identical to the sequential reference sum).  out must be pre-initialised by ks_init_kernel.
+__global__ void ks_init_kernel(const uint32_t *__restrict__ body, uint32_t *__restrict__ out, uint32_t n, uint32_t batch) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)batch * (n + 1)) return;
+    out[i] = (i % (n + 1) == n) ? body[i / (n + 1)] : 0u;      // key_switching.rs:98-100
+}
+constexpr int KSV_THREADS = 256, KSV_MAXB = 8;
+__global__ void __launch_bounds__(KSV_THREADS) ks_gemv_kernel(const int8_t *__restrict__ digits, const uint32_t *__restrict__ ksk,
+                                                              uint32_t *__restrict__ out, uint32_t KD, uint32_t n, uint32_t batch,
+                                                              uint32_t rows_per_cta) {
+    __shared__ int32_t sD[KSV_MAXB][64];
+    const uint32_t ncols = n + 1;
+    const uint32_t r0 = blockIdx.x * rows_per_cta, r1 = min(KD, r0 + rows_per_cta);
+    for (uint32_t cbase = 0; cbase < ncols; cbase += KSV_THREADS * 4) {
+        uint32_t accv[KSV_MAXB][4];
+#pragma unroll
+        for (int b = 0; b < KSV_MAXB; b++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) accv[b][j] = 0;
+        for (uint32_t rb = r0; rb < r1; rb += 64) {
+            __syncthreads();
+            for (uint32_t e = threadIdx.x; e < KSV_MAXB * 64; e += KSV_THREADS) {
+                const uint32_t b = e / 64, rr = rb + e % 64;
+                sD[b][e % 64] = (b < batch && rr < r1) ? (int32_t)digits[(size_t)b * KD + rr] : 0;
+            }
+            __syncthreads();
+            const uint32_t rn = min(64u, r1 - rb);
+            for (uint32_t rr = 0; rr < rn; rr++) {
+                const uint32_t *row = ksk + (size_t)(rb + rr) * ncols;
+                uint32_t kv[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t c = cbase + j * KSV_THREADS + threadIdx.x;
+                    kv[j] = c < ncols ? __ldg(row + c) : 0u;
+                }
+#pragma unroll
+                for (int b = 0; b < KSV_MAXB; b++) {
+                    const uint32_t d = (uint32_t)sD[b][rr];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) accv[b][j] += d * kv[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < KSV_MAXB; b++)
+            if ((uint32_t)b < batch)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t c = cbase + j * KSV_THREADS + threadIdx.x;
+                    if (c < ncols && accv[b][j]) atomicAdd(out + (size_t)b * ncols + c, 0u - accv[b][j]);  // key_switching.rs:96 negate
+                }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ sub-op: poly_mul
 // utils.rs:155-160 poly_mul (Toeplitz product) for a batch of pairs: out[b] = a[b] (*) g[b] in Z_{2^32}[X]/(X^N+1),
 // a = small signed coefficients (|a| <= amax checked on the host so that N*amax*2^31 < Q0*Q1/2), g = arbitrary u32.

@@ -193,6 +193,19 @@ int run_key_switch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *src, int fr
     else
         ks_digits_kernel<2, 8><<<blocks, 256, 0, ctx->stream>>>(src, dg, bd, (uint32_t)ctx->k(), ctx->p.glwe_poly_degree, (uint32_t)batch, from_lwe);
     CU(cudaGetLastError());
+    if (batch <= (size_t)KSV_MAXB) {
+        // latency path: rows of the KSK split over ~2 CTAs per SM, partial sums combined with u32 atomics
+        const size_t len = batch * (ctx->n() + 1);
+        ks_init_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>(bd, d_out, (uint32_t)ctx->n(), (uint32_t)batch);
+        CU(cudaGetLastError());
+        const uint32_t ctas = (uint32_t)ctx->sm_count * 2;
+        const uint32_t rows_per_cta = (uint32_t)((KD + ctas - 1) / ctas);
+        ks_gemv_kernel<<<(unsigned)((KD + rows_per_cta - 1) / rows_per_cta), KSV_THREADS, 0, ctx->stream>>>(
+            dg, bk->d_ksk, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch, rows_per_cta);
+        CU(cudaGetLastError());
+        ctx->launches += 3;
+        return TFHE_OK;
+    }
     dim3 grid((unsigned)((ctx->n() + 1 + KS_BN - 1) / KS_BN), (unsigned)((batch + KS_BM - 1) / KS_BM));
     ks_gemm_kernel<<<grid, KS_THREADS, 0, ctx->stream>>>(dg, bk->d_ksk, bd, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch);
     CU(cudaGetLastError());
