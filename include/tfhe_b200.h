@@ -95,10 +95,28 @@ int tfhe_ctx_set_stream(tfhe_ctx *ctx, void *cuda_stream);
 /* Kernels launched by this ctx since creation (the bench's gpu_launches claim). */
 uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx);
 
-/* Copies BSK+KSK (host or device pointers) to the ctx's device and transforms the BSK into the 2-prime
- * NTT domain (kernel K0).  The caller keeps ownership of the inputs. */
+/* Arithmetic path of the external product (both reproduce ggsw.rs:132-161 bit for bit):
+ *   TFHE_PATH_NTT  2-prime RNS number-theoretic transform + CRT (integer IMAD pipe), every parameter set;
+ *   TFHE_PATH_FFT  double-precision folded FFT with a limb-split key, provably exact, FP64 pipe;
+ *                  instantiated for the parameter sets listed by tfhe_ctx_set_pbs_path's TFHE_E_PARAM.
+ * The path is fixed per bootstrapping key: select it BEFORE tfhe_bk_upload (default: env TFHE_B200_PBS_PATH=ntt|fft,
+ * else the faster instantiated path for the parameter set). */
+#define TFHE_PATH_NTT 0
+#define TFHE_PATH_FFT 1
+int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path);
+int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx);
+/* FFT path only: the largest distance to the nearest integer of any value rounded by the blind rotation since the
+ * ctx was created or this function was last called (resets it).  The a-priori bound is 2^-9; exactness needs < 1/2. */
+int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out);
+
+/* Copies BSK+KSK (host or device pointers) to the ctx's device and transforms the BSK into the domain of the ctx's
+ * arithmetic path (2-prime NTT: kernel K0; or limb-split FFT).  The caller keeps ownership of the inputs. */
 int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe_bk **out);
 void tfhe_bk_free(tfhe_bk *bk);
+/* Inspection (parity tests of the one-off key transform): size in bytes of the transformed BSK held on the device,
+ * and a copy of it to host memory.  NTT path: u32[n][2][(k+1)l][k+1][N]; FFT path: f64 pairs[n][(k+1)l][2][k+1][N/2]. */
+size_t tfhe_bk_transformed_bytes(const tfhe_bk *bk);
+int tfhe_bk_read_transformed(const tfhe_bk *bk, void *out, size_t bytes);
 
 /* ------------------------------------------------------------------ the hot path */
 /* bootstrapping.rs:58-120 `bootstrap`, batched.  luts = T unencoded test vectors [T][N] (values < 2^log_p,

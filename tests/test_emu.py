@@ -104,3 +104,84 @@ def test_emulated_cmux_step_bit_exact(emu, cfg):
     got = acc.copy().reshape(-1)
     emu.emu_step(cfg, 0, ntt, got, 0)
     assert got.tolist() == acc.reshape(-1).tolist()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# FP64-FFT path (fft_team.cuh): same checks, through tests/emu/emu_fft.cpp
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def emu_fft():
+    src = os.path.join(HERE, "emu", "emu_fft.cpp")
+    so = os.path.join(HERE, "emu", "libemu_fft.so")
+    deps = [src] + [os.path.join(HERE, "..", "tfhe-research_b200", "csrc", f) for f in ("tfhe_core.cuh", "fft_team.cuh", "host_tables_fft.hpp")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", "-march=x86-64-v3", "-ffp-contract=off", "-fPIC", "-shared", "-o", so, src], check=True)
+    L = C.CDLL(so)
+    L.emu_fft_transform_ggsw.argtypes = [C.c_int, u32p, f64p]
+    L.emu_fft_step.argtypes = [C.c_int, C.c_int, f64p, u32p, C.c_uint32, C.POINTER(C.c_double)]
+    return L
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2])
+def test_emulated_fft_cmux_step_bit_exact(emu_fft, cfg):
+    p = orc.params(**CFGS[cfg])
+    N, k, l = p.N, p.k, p.pbs_levels
+    rng = np.random.default_rng(200 + cfg)
+    r32 = lambda *s: rng.integers(0, 1 << 32, s, dtype=np.uint64).astype(np.uint32)
+    ggsw = r32((k + 1) * l, k + 1, N)
+    # extreme key words: the centred limbs reach -2^15 and +2^15
+    ggsw[0, 0, :6] = [0x7FFFFFFF, 0x80000000, 0x00008000, 0xFFFF8000, 0x7FFF7FFF, 0x80008000]
+    key = np.zeros((k + 1) * l * 2 * (k + 1) * (N // 2) * 2, dtype=np.float64)
+    assert emu_fft.emu_fft_transform_ggsw(cfg, ggsw.reshape(-1), key) == 0
+    O = orc.lib()
+    worst = 0.0
+    mf = C.c_double(0.0)
+    glwe = r32(k + 1, N)
+    glwe[0, :8] = [0xFFFFFFFF, 0x7FFFFF80, 0x0000F800, 0xF8F8F8F8, 0, 0x80000000, 0x0FF80000, 0x00FFFFFF]
+    exp = orc.z((k + 1) * N)
+    O.orc_external_product(C.byref(p), ggsw.reshape(-1), glwe.reshape(-1), exp)
+    got = glwe.copy().reshape(-1)
+    assert emu_fft.emu_fft_step(cfg, 1, key, got, 0, C.byref(mf)) == 0
+    assert got.tolist() == exp.tolist()
+    worst = max(worst, mf.value)
+    for a in (1, N - 1, N, N + 5, 2 * N - 1, 777 % (2 * N)):
+        acc = r32(k + 1, N)
+        c1 = orc.z((k + 1) * N)
+        O.orc_glwe_mul_monomial(C.byref(p), acc.reshape(-1), a, c1)
+        exp = orc.z((k + 1) * N)
+        O.orc_cmux(C.byref(p), ggsw.reshape(-1), acc.reshape(-1), c1, exp)
+        got = acc.copy().reshape(-1)
+        assert emu_fft.emu_fft_step(cfg, 0, key, got, a, C.byref(mf)) == 0
+        assert got.tolist() == exp.tolist(), a
+        worst = max(worst, mf.value)
+    acc = r32(k + 1, N)
+    got = acc.copy().reshape(-1)
+    emu_fft.emu_fft_step(cfg, 0, key, got, 0, C.byref(mf))
+    assert got.tolist() == acc.reshape(-1).tolist()
+    # distance of every pre-rounding value to the nearest integer: the a-priori bound is 2^-9, observed ~2^-16
+    assert worst < 2.0 ** -10, worst
+
+
+def test_emulated_fft_worst_case_inputs(emu_fft):
+    """Adversarial magnitudes: every digit at its extreme (+B via the H3 quirk, -B/2) and every key limb at +-2^15."""
+    cfg = 1
+    p = orc.params(**CFGS[cfg])
+    N, k, l = p.N, p.k, p.pbs_levels
+    rng = np.random.default_rng(7)
+    O = orc.lib()
+    mf = C.c_double(0.0)
+    for trial in range(3):
+        sign = rng.integers(0, 2, ((k + 1) * l, k + 1, N)).astype(np.uint32)
+        ggsw = np.where(sign == 1, np.uint32(0x7FFF7FFF), np.uint32(0x80008000)).astype(np.uint32)
+        # 0xFF..F8 windows + carry give +B digits; 0x80 windows give -B/2
+        glwe = np.where(rng.integers(0, 2, (k + 1, N)) == 1, np.uint32(0xFFFFFF80), np.uint32(0x80808080)).astype(np.uint32)
+        key = np.zeros((k + 1) * l * 2 * (k + 1) * (N // 2) * 2, dtype=np.float64)
+        assert emu_fft.emu_fft_transform_ggsw(cfg, ggsw.reshape(-1), key) == 0
+        exp = orc.z((k + 1) * N)
+        O.orc_external_product(C.byref(p), ggsw.reshape(-1), glwe.reshape(-1), exp)
+        got = glwe.copy().reshape(-1)
+        assert emu_fft.emu_fft_step(cfg, 1, key, got, 0, C.byref(mf)) == 0
+        assert got.tolist() == exp.tolist()
+        assert mf.value < 2.0 ** -10, mf.value

@@ -20,10 +20,11 @@ FIELDS = [f for f, _ in T.TfheParams._fields_]
 
 class Env:
     def __init__(self, preset):
+        preset, _, path = preset.partition(":")   # "P1" = 2-prime NTT path, "P1:fft" = exact FP64-FFT path
         self.p = T.TfheParams.preset(preset)
         self.o = orc.params(**{f: getattr(self.p, f) for f in FIELDS})
         self.lwe_sk, self.glwe_sk, self.bsk, self.ksk = T.bootstrapping_key_gen(self.p, 0xB200)
-        self.ctx = T.Context(self.p, 0)
+        self.ctx = T.Context(self.p, 0, path=T.PATH_FFT if path == "fft" else T.PATH_NTT)
         self.bk = self.ctx.upload_key(self.bsk, self.ksk)
 
     def enc(self, m, idx):
@@ -48,9 +49,10 @@ def make_batch(e, B, n_unique=128):
     return np.tile(uniq, ((B + n_unique - 1) // n_unique, 1))[:B].copy(), n_unique
 
 
-def test_p1_batch_4096_identity():
+@pytest.mark.parametrize("which", ["P1", "P1:fft"])
+def test_p1_batch_4096_identity(which):
     """BASELINE config #2: batch of 4096 PBS, N=1024, n=630, identity test vector."""
-    e = env("P1")
+    e = env(which)
     pm = 1 << e.p.log_p
     cts, nu = make_batch(e, 4096)
     tv = T.construct_identity_test_vector(e.p)
@@ -64,11 +66,17 @@ def test_p1_batch_4096_identity():
     # oracle spot check at full n (reference algorithm, ~1 s each)
     for i in (0, 77):
         assert np.array_equal(out[i], orc.bootstrap(e.o, cts[i], e.bsk, e.ksk, tv))
+    if which.endswith(":fft"):
+        # a-posteriori exactness certificate: no value was further than 2^-6 from an integer before rounding
+        # (a-priori bound 2^-9); and the two arithmetic paths agree bit for bit on the whole batch
+        assert e.ctx.fft_rounding_margin() < 2.0 ** -6
+        assert np.array_equal(out, env("P1").ctx.bootstrap(env("P1").bk, cts, tv))
 
 
-def test_p1_trivial_ciphertexts_closed_form():
+@pytest.mark.parametrize("which", ["P1", "P1:fft"])
+def test_p1_trivial_ciphertexts_closed_form(which):
     """a = 0 => every a~_i = 0 => all CMUX steps are skipped and acc = X^{-b~} * v(X) exactly."""
-    e = env("P1")
+    e = env(which)
     p = e.p
     N, n = p.N, p.n
     tv = T.construct_identity_test_vector(p)

@@ -21,11 +21,14 @@ def oparams(p):
 
 
 class Env:
+    """preset may carry the arithmetic path: "P1" (2-prime NTT) or "P1:fft" (exact FP64 FFT, limb-split key)."""
+
     def __init__(self, preset, n, seed=0xB200):
+        preset, _, path = preset.partition(":")
         self.p = T.TfheParams.preset(preset, lwe_dimension=n)
         self.o = oparams(self.p)
         self.lwe_sk, self.glwe_sk, self.bsk, self.ksk = T.bootstrapping_key_gen(self.p, seed)
-        self.ctx = T.Context(self.p, 0)
+        self.ctx = T.Context(self.p, 0, path=T.PATH_FFT if path == "fft" else T.PATH_NTT)
         self.bk = self.ctx.upload_key(self.bsk, self.ksk)
 
     def enc(self, m, idx, seed=1):
@@ -45,7 +48,7 @@ def env(preset, n):
     return _envs[key]
 
 
-CASES = [("P0", 4), ("P1", 3), ("P2", 2)]
+CASES = [("P0", 4), ("P1", 3), ("P2", 2), ("P1:fft", 3), ("P1:fft", 21)]
 
 
 def r32(rng, *shape):
@@ -137,7 +140,7 @@ def test_blind_rotate_extract_keyswitch_bootstrap(preset, n):
         assert np.array_equal(e.ctx.bootstrap(e.bk, cts[:nb], tvs, idx[:nb]), out[:nb]), nb
 
 
-@pytest.mark.parametrize("preset,n", [("P0", 4), ("P1", 3)])
+@pytest.mark.parametrize("preset,n", [("P0", 4), ("P1", 3), ("P1:fft", 3)])
 def test_gates_boolean_rs(preset, n):
     e = env(preset, n)
     fs = [lambda a, b: a & b, lambda a, b: a | b, lambda a, b: a ^ b,

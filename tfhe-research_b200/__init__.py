@@ -24,10 +24,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"]
 _SOURCES = ["tfhe_b200.cu", "host_api.cpp"]
 _DEPS = _SOURCES + ["kernels.cuh", "pbs_team.cuh", "tfhe_core.cuh", "host_tables.hpp", "api_internal.hpp",
+                    "kernels_fft.cuh", "fft_team.cuh", "host_tables_fft.hpp",
                     os.path.join("..", "..", "include", "tfhe_b200.h")]
 
 TFHE_OK, TFHE_E_PARAM, TFHE_E_CUDA, TFHE_E_OOM, TFHE_E_ASSERT, TFHE_E_NCCL = 0, -1, -2, -3, -4, -5
 AND, OR, XOR, NAND, NOR, XNOR = range(6)
+PATH_NTT, PATH_FFT = 0, 1   # arithmetic path of the external product (include/tfhe_b200.h TFHE_PATH_*)
 
 
 class TfheError(RuntimeError):
@@ -106,7 +108,9 @@ def lib():
         "tfhe_lwe_decrypt": [VP, SZ, VP, C.POINTER(C.c_uint32)],
         "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP],
         "tfhe_ctx_create": [PP, C.c_int, C.POINTER(VP)], "tfhe_ctx_set_stream": [VP, VP],
-        "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)],
+        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP],
+        "tfhe_fft_rounding_margin": [VP, C.POINTER(C.c_double)],
+        "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)], "tfhe_bk_read_transformed": [VP, VP, SZ],
         "tfhe_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP],
         "tfhe_gate_batch": [VP, VP, C.c_int, VP, VP, SZ, VP], "tfhe_gates_batch": [VP, VP, VP, VP, VP, SZ, VP],
         "tfhe_switch_modulus": [VP, VP, SZ, VP], "tfhe_decompose": [VP, C.c_int, VP, SZ, VP],
@@ -126,6 +130,7 @@ def lib():
     L.tfhe_bk_free.argtypes = [VP]; L.tfhe_bk_free.restype = None
     L.tfhe_last_error.argtypes = [VP]; L.tfhe_last_error.restype = C.c_char_p
     L.tfhe_ctx_launch_count.argtypes = [VP]; L.tfhe_ctx_launch_count.restype = C.c_uint64
+    L.tfhe_bk_transformed_bytes.argtypes = [VP]; L.tfhe_bk_transformed_bytes.restype = C.c_size_t
     _LIB = L
     return L
 
@@ -137,7 +142,8 @@ EXPORTS = [
     "tfhe_ctx_launch_count", "tfhe_bk_upload", "tfhe_bk_free", "tfhe_bootstrap_batch", "tfhe_gate_batch",
     "tfhe_gates_batch", "tfhe_switch_modulus", "tfhe_decompose", "tfhe_glwe_mul_monomial", "tfhe_external_product",
     "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
-    "tfhe_measure_int_peak", "tfhe_last_timing",
+    "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin",
+    "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed",
 ]
 
 
@@ -257,6 +263,13 @@ class BootstrappingKey:
             lib().tfhe_bk_free(self._h)
             self._h = None
 
+    def transformed(self) -> np.ndarray:
+        """Host copy of the transformed BSK (u32 residues on the NTT path, float64 re/im pairs on the FFT path)."""
+        nbytes = lib().tfhe_bk_transformed_bytes(self._h)
+        out = np.empty(nbytes // 8, dtype=np.float64) if self.ctx.pbs_path == PATH_FFT else np.empty(nbytes // 4, dtype=np.uint32)
+        self.ctx._ck(lib().tfhe_bk_read_transformed(self._h, out.ctypes.data, nbytes))
+        return out
+
     def __del__(self):
         try:
             self.free()
@@ -267,7 +280,7 @@ class BootstrappingKey:
 class Context:
     """One CUDA device.  Inputs may be numpy arrays (host, copied in/out) or CUDA torch tensors (in place)."""
 
-    def __init__(self, params: TfheParams, device: int = 0):
+    def __init__(self, params: TfheParams, device: int = 0, path=None):
         self.params = params
         h = C.c_void_p()
         rc = lib().tfhe_ctx_create(C.byref(params), device, C.byref(h))
@@ -275,6 +288,22 @@ class Context:
             raise TfheError(rc, "no usable CUDA device: the PBS path has no CPU fallback")
         _check(rc, "tfhe_ctx_create")
         self._h = h
+        if path is not None:
+            self.set_pbs_path(path)
+
+    def set_pbs_path(self, path: int):
+        """PATH_NTT (2-prime integer NTT) or PATH_FFT (exact FP64 FFT, limb-split key); call before upload_key."""
+        self._ck(lib().tfhe_ctx_set_pbs_path(self._h, int(path)))
+
+    @property
+    def pbs_path(self) -> int:
+        return int(lib().tfhe_ctx_get_pbs_path(self._h))
+
+    def fft_rounding_margin(self) -> float:
+        """Largest distance to an integer of any value rounded by the FFT path since the last call (must be << 0.5)."""
+        out = C.c_double()
+        self._ck(lib().tfhe_fft_rounding_margin(self._h, C.byref(out)))
+        return out.value
 
     def _ck(self, rc):
         if rc != 0:

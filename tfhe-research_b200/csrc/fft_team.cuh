@@ -1,0 +1,376 @@
+// fft_team.cuh -- exact negacyclic products mod 2^32 through a double-precision FFT with a limb-split key
+// (second arithmetic path of the blind rotation; the first is the 2-prime NTT of pbs_team.cuh).
+//
+// Why: on B200 the FP64 pipe (DFMA/DADD/DMUL, 64 lanes/clk/SM = 18.5 T op/s measured, profiles/r01_fp64_peak.json)
+// is a separate pipe from the FMA-heavy pipe that IMAD / IMAD.HI / IMAD.WIDE share, and the 2-prime NTT is bound by
+// that integer pipe.  A folded complex FFT of size M = N/2 needs 6 DP ops per butterfly for two real coefficients
+// where the NTT needs 2 primes x (IMAD.HI + 2 IMAD) = 16 pipe cycles.
+//
+// Reference semantics reproduced (bit for bit): ggsw.rs:132-161 external_product, utils.rs:113-173 poly_dot_product
+//   out[c] = sum_r dec[r] (*) G[r][c]  in Z_{2^32}[X]/(X^N+1).
+// Exactness argument:
+//   * digits d are small signed integers, |d| <= B = 2^LOGB (decomposer.rs:42-80 incl. the +B quirk);
+//   * every key word g is lifted to its centred representative s in [-2^31, 2^31) and split into two centred limbs
+//     s = lo + 2^16 hi, lo in [-2^15, 2^15), hi in [-2^15, 2^15];  out = sum d(*)lo + 2^16 sum d(*)hi  (mod 2^32);
+//   * each limb convolution is an integer of magnitude <= ROWS*N*B*2^15 <= 2^36.6 (P2); the floating-point result
+//     differs from it by at most  c * 2^-53 * sum_r ||d_r||_2 ||limb_r||_2  with c ~ 2^7.2 (Percival-type bound for
+//     a length-2^10 transform incl. the pointwise products and twiddle errors) <= 2^-9, so rounding to nearest
+//     recovers the exact integer;  static_assert below keeps a 2^9 safety factor, and the kernel can record the
+//     largest distance to an integer it ever saw (CHECK), which the full-size GPU tests assert to be < 2^-6.
+//
+// Transform: the fold z_j = a_j + i a_{j+M} maps R[X]/(X^N+1) to C[X]/(X^M - i); the forward transform evaluates at
+// the M roots of X^M = i (zeta^(4k+1), zeta = exp(2 pi i / 4M)) with a Cooley-Tukey flow (natural in, bit-reversed
+// out, merged twiddles: no separate twist), the inverse is the mirrored Gentleman-Sande flow with conjugate
+// twiddles; the 1/M scaling is folded into the stored key (a power of two: exact).
+//
+// Everything here is __host__ __device__ so tests/emu can step the identical code on the CPU.
+#pragma once
+#include <math.h>
+
+#include "tfhe_core.cuh"
+
+namespace tfhe {
+namespace fft {
+
+struct alignas(16) cplx {
+    double re, im;
+};
+
+// ---- pinned FP64 operations (no compiler contraction: the CPU emulation reproduces the GPU doubles) ----
+TFHE_HD double fma_d(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return ::fma(a, b, c);
+#endif
+}
+TFHE_HD double mul_d(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+TFHE_HD double add_d(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+// small signed integer -> double without the conversion unit: bits of (2^52 + 2^31 + d), minus the bias
+TFHE_HD double i2d(int32_t d) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(__hiloint2double(0x43300000, (int)((uint32_t)d ^ 0x80000000u)), -4503601774854144.0);
+#else
+    return (double)d;
+#endif
+}
+// round to nearest integer, returned mod 2^32 (|x| < 2^51); *frac receives |x - rint(x)| when CHECK
+template <bool CHECK>
+TFHE_HD uint32_t round_u32(double x, double &maxfrac) {
+#if defined(__CUDA_ARCH__)
+    const double t = __dadd_rn(x, 6755399441055744.0);  // 1.5 * 2^52: low mantissa word = rint(x) mod 2^32
+    if (CHECK) maxfrac = fmax(maxfrac, fabs(__dadd_rn(x, -__dadd_rn(t, -6755399441055744.0))));
+    return (uint32_t)__double2loint(t);
+#else
+    const double r = nearbyint(x);
+    if (CHECK) maxfrac = fmax(maxfrac, fabs(x - r));
+    return (uint32_t)(int64_t)r;
+#endif
+}
+
+// Cooley-Tukey butterfly  X' = X + wY,  Y' = X - wY = 2X - X'   (6 DFMA)
+TFHE_HD void ct_bfly(cplx &X, cplx &Y, const cplx w) {
+    const double xr = fma_d(-Y.im, w.im, fma_d(Y.re, w.re, X.re));
+    const double xi = fma_d(Y.im, w.re, fma_d(Y.re, w.im, X.im));
+    Y.re = fma_d(2.0, X.re, -xr);
+    Y.im = fma_d(2.0, X.im, -xi);
+    X.re = xr;
+    X.im = xi;
+}
+// Gentleman-Sande butterfly of the inverse  X' = X + Y,  Y' = (X - Y) conj(w)   (4 DADD + 2 DMUL + 2 DFMA)
+TFHE_HD void gs_bfly(cplx &X, cplx &Y, const cplx w) {
+    const double dr = add_d(X.re, -Y.re), di = add_d(X.im, -Y.im);
+    X.re = add_d(X.re, Y.re);
+    X.im = add_d(X.im, Y.im);
+    Y.re = fma_d(di, w.im, mul_d(dr, w.re));
+    Y.im = fma_d(di, w.re, -mul_d(dr, w.im));
+}
+
+// ---------------------------------------------------------------- team geometry (mirrors NttCfg)
+// M = 2^LOGM complex points per polynomial, a TEAM of T = M/E threads, E = 2^LOGE points per thread.
+// Index bits of j (MSB first):  hA[LOGE] | mid[QB] | lo[LOGE].
+//   layout A: regs <-> hA                      thread t <-> (mid|lo)          j = (e << LOGT) | t
+//   layout B: regs <-> mid | top XB bits of lo thread   <-> hA + low QB bits of lo
+//   layout C: regs <-> lo                      thread t <-> (hA|mid)          j = (t << LOGE) | e
+// Exchange buffers hold 16-byte elements at phys(j) = j + (j >> LOGE): additive over disjoint bit sets (register
+// offsets are immediates) and conflict-free for 128-bit accesses in all three layouts (8 consecutive lanes hit
+// 8 distinct 16-byte bank groups).
+template <int LOGM_, int LOGE_>
+struct FftCfg {
+    static constexpr int LOGM = LOGM_, LOGE = LOGE_;
+    static constexpr int M = 1 << LOGM, E = 1 << LOGE, LOGT = LOGM - LOGE, T = 1 << LOGT;
+    static constexpr int QB = LOGM - 2 * LOGE, XB = LOGE - QB;
+    static constexpr int NA_TW = E - 1, NB_TW = (1 << QB) - 1, NC_TW = E - 1;
+    static constexpr int MPAD = M + (M >> LOGE);
+    static_assert(QB >= 1 && QB <= LOGE, "unsupported (LOGM, LOGE)");
+    static_assert(LOGT >= 5, "team must be at least one warp");
+};
+template <class C>
+TFHE_HD constexpr uint32_t cphys(uint32_t j) { return j + (j >> C::LOGE); }
+template <class C>
+TFHE_HD constexpr uint32_t jbase_B(uint32_t t) {
+    return (t & ((1u << C::QB) - 1u)) | ((t >> C::QB) << (C::LOGE + C::QB));
+}
+
+template <class C> TFHE_HD void store_A(const cplx *x, cplx *buf, uint32_t t) {
+    cplx *b = buf + cphys<C>(t);
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; b[cphys<C>(e << C::LOGT)] = x[e]; });
+}
+template <class C> TFHE_HD void load_A(cplx *x, const cplx *buf, uint32_t t) {
+    const cplx *b = buf + cphys<C>(t);
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = b[cphys<C>(e << C::LOGT)]; });
+}
+template <class C> TFHE_HD void store_B(const cplx *x, cplx *buf, uint32_t jbB) {
+    cplx *b = buf + cphys<C>(jbB);
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; b[cphys<C>(e << C::QB)] = x[e]; });
+}
+template <class C> TFHE_HD void load_B(cplx *x, const cplx *buf, uint32_t jbB) {
+    const cplx *b = buf + cphys<C>(jbB);
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = b[cphys<C>(e << C::QB)]; });
+}
+template <class C> TFHE_HD void store_C(const cplx *x, cplx *buf, uint32_t t) {
+    cplx *b = buf + cphys<C>(t << C::LOGE);
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; b[cphys<C>(e)] = x[e]; });
+}
+template <class C> TFHE_HD void load_C(cplx *x, const cplx *buf, uint32_t t) {
+    const cplx *b = buf + cphys<C>(t << C::LOGE);
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = b[cphys<C>(e)]; });
+}
+
+// register passes: stage u pairs register bit LOGE-1-u; twiddle index 2^u - 1 + (top u bits of e)
+template <int LOGE, int NST>
+TFHE_HD void fwd_pass(cplx *x, const cplx *tw) {
+    static_for<0, NST>([&](auto ui) {
+        constexpr int u = decltype(ui)::value;
+        constexpr int bit = 1 << (LOGE - 1 - u);
+        static_for<0, (1 << LOGE)>([&](auto ei) {
+            constexpr int e = decltype(ei)::value;
+            if constexpr ((e & bit) == 0) ct_bfly(x[e], x[e + bit], tw[(1 << u) - 1 + (e >> (LOGE - u))]);
+        });
+    });
+}
+template <int LOGE, int NST>
+TFHE_HD void inv_pass(cplx *x, const cplx *tw) {
+    static_for<0, NST>([&](auto ui) {
+        constexpr int u = NST - 1 - decltype(ui)::value;
+        constexpr int bit = 1 << (LOGE - 1 - u);
+        static_for<0, (1 << LOGE)>([&](auto ei) {
+            constexpr int e = decltype(ei)::value;
+            if constexpr ((e & bit) == 0) gs_bfly(x[e], x[e + bit], tw[(1 << u) - 1 + (e >> (LOGE - u))]);
+        });
+    });
+}
+
+// ---------------------------------------------------------------- blind-rotation configuration
+constexpr int kMaxTwA = 15;
+struct TwTablesF {
+    cplx twA[kMaxTwA];   // pass A (stages 0..LOGE-1): the same for every thread -> kernel-parameter constant bank
+    const cplx *twB;     // [2^LOGE (hA)][NB_TW]
+    const cplx *twC;     // [T][NC_TW]
+};
+
+template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int TEAMS_, bool CHECK_ = true>
+struct FftPbsCfg {
+    using F = FftCfg<LOGN_ - 1, LOGE_>;
+    static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2;
+    static constexpr int K = K_, P = K_ + 1, L = L_, LOGB = LOGB_, ROWS = P * L;
+    static constexpr int E = F::E, T = F::T, TEAMS = TEAMS_;
+    static constexpr bool CHECK = CHECK_;
+    static constexpr int WARPS_PER_TEAM = T / 32;
+    static constexpr int THREADS = TEAMS * T;
+    static_assert(LOGB * L <= 32 && 32 % LOGB == 0, "decomposer must divide log_q (SURVEY 9-B H2)");
+    static_assert(LOGB <= 14, "digits are stashed as int16");
+    // exactness: largest limb convolution * 2^9 (error constant incl. safety) must stay below 2^51
+    static_assert((double)ROWS * N * (double)(1 << LOGB) * 32768.0 * 512.0 < 2251799813685248.0, "FP64 exactness bound");
+    // key stream: one SLOT = one limb of one GGSW row = P polynomials of M complex points (slot order)
+    static constexpr int POLY_BYTES = M * 16, SLOT_BYTES = P * POLY_BYTES, SLOTS_PER_STEP = ROWS * 2, NSLOT = 4;
+    static constexpr size_t GGSW_BYTES = (size_t)SLOTS_PER_STEP * SLOT_BYTES;
+    // shared memory per team
+    static constexpr int TM_ACC = 0;                                   // u32 acc[P][N]
+    static constexpr int TM_STASH = TM_ACC + P * N * 4;                // int16 stash[(L-1)*2E][T]
+    static constexpr int STASH_BYTES = ((L > 1 ? (L - 1) : 1) * 2 * E * T * 2 + 15) & ~15;
+    static constexpr int TM_BUF = TM_STASH + STASH_BYTES;              // cplx buf[2][MPAD]
+    static constexpr int TM_AT = TM_BUF + 2 * F::MPAD * 16;            // u16 at[n+1] (size known at launch)
+    static constexpr int team_bytes(int n) { return (TM_AT + (n + 1) * 2 + 127) & ~127; }
+    static_assert(TEAMS >= 3 || TEAMS == 1, "single-ciphertext modes borrow the accumulators of teams 1 and 2");
+};
+
+template <class K>
+struct FftRegs {
+    cplx x[K::E];
+    cplx acc[2][K::P][K::E];  // [limb][column][point]
+};
+template <class K>
+TFHE_HD void zero_acc(FftRegs<K> &r) {
+#pragma unroll
+    for (int l = 0; l < 2; l++)
+#pragma unroll
+        for (int c = 0; c < K::P; c++)
+#pragma unroll
+            for (int e = 0; e < K::E; e++) r.acc[l][c][e] = cplx{0.0, 0.0};
+}
+
+// centred limbs of a key word (see header): s = lo + 2^16 hi
+TFHE_HD int32_t key_limb(uint32_t g, int limb) {
+    const int32_t s = (int32_t)g;
+    const int32_t lo = (int32_t)(int16_t)(uint16_t)(g & 0xFFFFu);
+    return limb == 0 ? lo : (int32_t)(((int64_t)s - lo) >> 16);
+}
+
+// ---- F1: digits of row `row` = (polynomial p, level lev), folded to complex, pass A, store to buf0.
+// minuend(p, j) - subtrahend(p, j) is coefficient j of polynomial p of the GLWE to decompose (glwe.rs:69-108).  The
+// decomposition (decomposer.rs:27-80) of a thread's 2E coefficients is done once per polynomial, at level 0; the
+// other levels' digits wait in a thread-private stash (no barrier: written and read by the same thread).
+template <class K, class DiffFn>
+TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, int16_t *stash, const cplx *twA, cplx *buf0, DiffFn diff) {
+    using C = typename K::F;
+    if (lev == 0) {
+#pragma unroll
+        for (int e = 0; e < K::E; e++) {
+            int32_t v[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint32_t j = (((uint32_t)e << C::LOGT) | t) + (uint32_t)h * K::M;
+                int32_t d[K::L];
+                decompose_signed<K::LOGB, K::L>(diff(p, j), d);
+                v[h] = d[0];
+#pragma unroll
+                for (int l = 1; l < K::L; l++) stash[(((l - 1) * 2 * K::E) + 2 * e + h) * K::T + t] = (int16_t)d[l];
+            }
+            r.x[e] = cplx{i2d(v[0]), i2d(v[1])};
+        }
+    } else {
+        const int16_t *s = stash + (size_t)(lev - 1) * 2 * K::E * K::T + t;
+#pragma unroll
+        for (int e = 0; e < K::E; e++) r.x[e] = cplx{i2d(s[(2 * e) * K::T]), i2d(s[(2 * e + 1) * K::T])};
+    }
+    fwd_pass<C::LOGE, C::LOGE>(r.x, twA);
+    store_A<C>(r.x, buf0, t);
+}
+template <class C>
+TFHE_HD void load_tw(cplx *dst, const cplx *src, int n) {
+#pragma unroll
+    for (int i = 0; i < n; i++) dst[i] = src[i];
+}
+// F2: layout B, pass B.   F3: layout C, pass C.
+template <class K>
+TFHE_HD void phase_F2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {
+    using C = typename K::F;
+    cplx tw[C::NB_TW];
+#pragma unroll
+    for (int i = 0; i < C::NB_TW; i++) tw[i] = twB_thread[i];
+    load_B<C>(r.x, buf0, jbB);
+    fwd_pass<C::LOGE, C::QB>(r.x, tw);
+    store_B<C>(r.x, buf1, jbB);
+}
+template <class K>
+TFHE_HD void phase_F3(FftRegs<K> &r, uint32_t t, const cplx *twC_thread, const cplx *buf1) {
+    using C = typename K::F;
+    cplx tw[C::NC_TW];
+#pragma unroll
+    for (int i = 0; i < C::NC_TW; i++) tw[i] = twC_thread[i];
+    load_C<C>(r.x, buf1, t);
+    fwd_pass<C::LOGE, C::LOGE>(r.x, tw);
+}
+// multiply-accumulate against one limb of a GGSW row: slot = [P][M] complex in slot order (point (t<<LOGE)|e of
+// column c at c*M + e*T + t, so consecutive lanes read consecutive 16 bytes)
+template <class K, int LIMB>
+TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, const cplx *slot) {
+#pragma unroll
+    for (int c = 0; c < K::P; c++)
+#pragma unroll
+        for (int e = 0; e < K::E; e++) {
+            const cplx g = slot[c * K::M + e * K::T + t];
+            cplx &a = r.acc[LIMB][c][e];
+            a.re = fma_d(-r.x[e].im, g.im, fma_d(r.x[e].re, g.re, a.re));
+            a.im = fma_d(r.x[e].im, g.re, fma_d(r.x[e].re, g.im, a.im));
+        }
+}
+// I1: accumulator (limb, c) -> inverse pass C -> buf0;  I2: pass B;  I3: pass A, result z in r.x (layout A)
+template <class K>
+TFHE_HD void phase_I1(FftRegs<K> &r, uint32_t t, int sel /* = c*2 + limb */, const cplx *twC_thread, cplx *buf0) {
+    using C = typename K::F;
+    cplx tw[C::NC_TW];
+#pragma unroll
+    for (int i = 0; i < C::NC_TW; i++) tw[i] = twC_thread[i];
+    static_for<0, 2 * K::P>([&](auto si) {
+        constexpr int s = decltype(si)::value;
+        if (sel == s) {
+#pragma unroll
+            for (int e = 0; e < K::E; e++) r.x[e] = r.acc[s & 1][s >> 1][e];
+        }
+    });
+    inv_pass<C::LOGE, C::LOGE>(r.x, tw);
+    store_C<C>(r.x, buf0, t);
+}
+template <class K>
+TFHE_HD void phase_I2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {
+    using C = typename K::F;
+    cplx tw[C::NB_TW];
+#pragma unroll
+    for (int i = 0; i < C::NB_TW; i++) tw[i] = twB_thread[i];
+    load_B<C>(r.x, buf0, jbB);
+    inv_pass<C::LOGE, C::QB>(r.x, tw);
+    store_B<C>(r.x, buf1, jbB);
+}
+template <class K>
+TFHE_HD void phase_I3(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf1) {
+    using C = typename K::F;
+    load_A<C>(r.x, buf1, t);
+    inv_pass<C::LOGE, C::LOGE>(r.x, twA);
+}
+// R: low limb -> keep the rounded words; high limb -> acc[c] += lo + (hi << 16)   (ggsw.rs:175 `res += ct0`)
+template <class K>
+TFHE_HD void phase_round_lo(const FftRegs<K> &r, uint32_t *lo, double &maxfrac) {
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        lo[2 * e] = round_u32<K::CHECK>(r.x[e].re, maxfrac);
+        lo[2 * e + 1] = round_u32<K::CHECK>(r.x[e].im, maxfrac);
+    }
+}
+template <class K>
+TFHE_HD void phase_round_hi(const FftRegs<K> &r, uint32_t t, const uint32_t *lo, uint32_t *acc_c, double &maxfrac) {
+    using C = typename K::F;
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+        acc_c[j] += lo[2 * e] + (round_u32<K::CHECK>(r.x[e].re, maxfrac) << 16);
+        acc_c[j + K::M] += lo[2 * e + 1] + (round_u32<K::CHECK>(r.x[e].im, maxfrac) << 16);
+    }
+}
+
+// ---- one-off key transform: raw GGSW polynomial g[N] (u32) -> limb `limb`, folded, forward FFT, scaled by 1/M,
+// stored in slot order.  T1 -> (barrier) -> F2 -> (barrier) -> T3.
+template <class K>
+TFHE_HD void phase_T1(FftRegs<K> &r, uint32_t t, int limb, const uint32_t *g, const cplx *twA, cplx *buf0) {
+    using C = typename K::F;
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+        r.x[e] = cplx{i2d(key_limb(g[j], limb)), i2d(key_limb(g[j + K::M], limb))};
+    }
+    fwd_pass<C::LOGE, C::LOGE>(r.x, twA);
+    store_A<C>(r.x, buf0, t);
+}
+template <class K>
+TFHE_HD void phase_T3(FftRegs<K> &r, uint32_t t, const cplx *twC_thread, const cplx *buf1, cplx *out) {
+    phase_F3<K>(r, t, twC_thread, buf1);
+    constexpr double scale = 1.0 / (double)K::M;  // power of two: exact
+#pragma unroll
+    for (int e = 0; e < K::E; e++) out[e * K::T + t] = cplx{mul_d(r.x[e].re, scale), mul_d(r.x[e].im, scale)};
+}
+
+}  // namespace fft
+}  // namespace tfhe

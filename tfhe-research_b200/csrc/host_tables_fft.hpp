@@ -1,0 +1,41 @@
+// host_tables_fft.hpp -- host-side twiddle tables of the FP64 FFT path (fft_team.cuh).  Pure C++, shared by the
+// product library and tests/emu.  Twiddles are evaluated in long double (64-bit mantissa) and rounded once.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "fft_team.cuh"
+
+namespace tfhe {
+namespace fft {
+
+// forward twiddle of stage st (0-based), block b in [0, 2^st):  zeta^((M >> (st+1)) * (1 + 4*brv_st(b))),
+// zeta = exp(2 pi i / 4M)   (root tree of X^M - i, see fft_team.cuh)
+inline cplx fft_twiddle(int logm, int st, uint32_t b) {
+    const uint64_t M = 1ull << logm;
+    const uint64_t ex = ((M >> (st + 1)) * (1ull + 4ull * brv_c(b, st))) % (4 * M);
+    const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)ex / (long double)(4 * M);
+    return cplx{(double)cosl(ang), (double)sinl(ang)};
+}
+
+struct HostFftTw {
+    std::vector<cplx> A, B, C;  // A: [E-1]; B: [2^LOGE][NB_TW]; C: [T][E-1]
+};
+inline void build_fft_tables(int logm, int loge, HostFftTw &out) {
+    const int qb = logm - 2 * loge;
+    const int T = 1 << (logm - loge);
+    out.A.clear(); out.B.clear(); out.C.clear();
+    for (int u = 0; u < loge; u++)
+        for (uint32_t m = 0; m < (1u << u); m++) out.A.push_back(fft_twiddle(logm, u, m));
+    for (uint32_t hA = 0; hA < (1u << loge); hA++)
+        for (int u = 0; u < qb; u++)
+            for (uint32_t m = 0; m < (1u << u); m++) out.B.push_back(fft_twiddle(logm, loge + u, (hA << u) | m));
+    for (uint32_t t = 0; t < (uint32_t)T; t++)
+        for (int u = 0; u < loge; u++)
+            for (uint32_t m = 0; m < (1u << u); m++) out.C.push_back(fft_twiddle(logm, loge + qb + u, (t << u) | m));
+}
+
+}  // namespace fft
+}  // namespace tfhe

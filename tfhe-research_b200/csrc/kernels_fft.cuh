@@ -1,0 +1,249 @@
+// kernels_fft.cuh -- sm_100a kernels of the FP64-FFT arithmetic path (see fft_team.cuh for the arithmetic).
+//
+//   pbs_fft_kernel        blind rotation: ONE CTA = TEAMS ciphertexts (one team of T threads each, the GLWE
+//                         accumulator of every team resident in shared memory for all n CMUX steps); thread 0
+//                         streams the FFT-domain bootstrapping key global -> shared with TMA bulk copies
+//                         into a 4-slot ring (full/empty mbarriers).  Every key byte fetched from L2 is used by
+//                         all TEAMS ciphertexts of the CTA, so the L2 -> SM traffic per ciphertext is 1/TEAMS of
+//                         the key size.  Also runs one external product / CMUX for the sub-operation entry points.
+//   bsk_fft_transform_kernel   raw BSK -> limb-split FFT domain (one-off at key upload)
+//
+// Reference: bootstrapping.rs:58-105 (blind rotation), ggsw.rs:132-178 (external product, cmux).
+#pragma once
+#include "fft_team.cuh"
+#include "kernels.cuh"
+
+namespace tfhe {
+namespace fft {
+
+struct FftArgs {
+    TwTablesF tw;
+    const cplx *bsk_fft;       // [n][ROWS][2 limbs][P][M] slot order, pre-scaled by 1/M
+    const uint32_t *lwe_in;    // mode 0: [B][n+1]
+    const uint32_t *luts;      // [T][N] unencoded
+    const uint32_t *lut_idx;   // [B] or nullptr
+    const uint32_t *in0, *in1; // mode 1 (out = ExtProd(G, in0)) / mode 2 (out = ExtProd(G, in1-in0)+in0): [B][P][N]
+    const uint32_t *ggsw_index;
+    uint32_t *glwe_out;        // [B][P][N]
+    uint32_t *err_flag;        // bit 0: test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out
+    unsigned long long *margin;  // largest |x - rint(x)| before rounding (bits of a non-negative double), CHECK only
+    uint32_t n, batch, mode, log_p, enc_shift;
+};
+
+__device__ __forceinline__ void team_bar_id(uint32_t id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_constant__ FftArgs a) {
+    using C = typename K::F;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t team_bytes = (uint32_t)K::team_bytes((int)a.n);
+    uint8_t *ring = smem + K::TEAMS * team_bytes;
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
+
+    const bool single = a.mode != 0;   // sub-operation entry points: one ciphertext (team 0) per CTA, its own GGSW
+    const uint32_t ct0 = single ? blockIdx.x : blockIdx.x * K::TEAMS;
+    const uint32_t active = single ? 1u : min((uint32_t)K::TEAMS, a.batch - ct0);
+    const uint32_t n_steps = single ? 1u : a.n;
+    const uint32_t total_slots = n_steps * K::SLOTS_PER_STEP;
+
+    if (tid == 0) {
+        for (int s = 0; s < K::NSLOT; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, active * K::WARPS_PER_TEAM);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // the only CTA-wide barrier: roles split below
+
+    const uint32_t team = tid / K::T, t = tid % K::T;
+    if (team >= active) return;
+    const uint32_t ct = ct0 + team;
+    uint8_t *tm = smem + team * team_bytes;
+    uint32_t *acc = reinterpret_cast<uint32_t *>(tm + K::TM_ACC);
+    int16_t *stash = reinterpret_cast<int16_t *>(tm + K::TM_STASH);
+    cplx *buf0 = reinterpret_cast<cplx *>(tm + K::TM_BUF), *buf1 = buf0 + C::MPAD;
+    uint16_t *at = reinterpret_cast<uint16_t *>(tm + K::TM_AT);
+    const uint32_t bar_id = team + 1;
+    const uint32_t jbB = jbase_B<C>(t);
+    const cplx *twB = a.tw.twB + (t >> C::QB) * C::NB_TW;
+    const cplx *twC = a.tw.twC + t * C::NC_TW;
+    // operands of the decomposed difference  minuend(p, (j - rot)) - subtrahend(p, j)
+    const uint32_t *mbase = acc, *sbase = acc;
+
+    if (!single) {
+        // utils.rs:23-33 mod switch of (a_0..a_{n-1}, b) to 2N
+        const uint32_t *lwe = a.lwe_in + (size_t)ct * (a.n + 1);
+        for (uint32_t i = t; i <= a.n; i += K::T) at[i] = (uint16_t)mod_switch(__ldg(lwe + i), K::LOGN);
+        team_bar_id(bar_id, K::T);
+        // acc = trivial GLWE of the encoded test vector times X^{-b~}  (bootstrapping.rs:79-86)
+        const uint32_t b = at[a.n];
+        const uint32_t *lut = a.luts + (size_t)(a.lut_idx ? __ldg(a.lut_idx + ct) : 0u) * K::N;
+        for (uint32_t idx = t; idx < (uint32_t)(K::P * K::N); idx += K::T) {
+            const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
+            uint32_t v = 0;
+            if (p == (uint32_t)K::K) {
+                const uint32_t src = (j + b) & (2u * K::N - 1u);
+                const uint32_t m = __ldg(lut + (src & (K::N - 1u)));
+                if (m >> a.log_p) atomicOr(a.err_flag, 1u);
+                v = m << a.enc_shift;
+                if (src & K::N) v = 0u - v;
+            }
+            acc[idx] = v;
+        }
+    } else {
+        // single-ciphertext modes borrow the (idle) accumulators of teams 1 and 2 for the polynomial to decompose
+        // and for a zero subtrahend, so the step below is the same code as the blind rotation with rot = 0
+        uint32_t *din = reinterpret_cast<uint32_t *>(smem + 1 * team_bytes + K::TM_ACC);
+        uint32_t *zero = reinterpret_cast<uint32_t *>(smem + 2 * team_bytes + K::TM_ACC);
+        const uint32_t *x0 = a.in0 + (size_t)ct * K::P * K::N, *x1 = a.in1 + (size_t)ct * K::P * K::N;
+        for (uint32_t idx = t; idx < (uint32_t)(K::P * K::N); idx += K::T) {
+            const uint32_t v0 = __ldg(x0 + idx);
+            acc[idx] = a.mode == 2 ? v0 : 0u;
+            din[idx] = a.mode == 2 ? __ldg(x1 + idx) - v0 : v0;
+            zero[idx] = 0u;
+        }
+        mbase = din;
+        sbase = zero;
+    }
+    team_bar_id(bar_id, K::T);
+
+    FftRegs<K> R;
+    double maxfrac = 0.0;
+    uint32_t it = 0;   // position in the key stream (the same sequence in every warp)
+
+    // ---- key stream producer: thread 0 of team 0 issues the TMA bulk copies (SASS UBLKCP) in consumption order, up to
+    // NSLOT slots ahead of its own position.  pump(need) returns with slots [0, need) issued (blocking on the ring's
+    // `empty` barriers if it must) and opportunistically issues further slots whose ring entry is already free.
+    const bool producer = tid == 0;
+    const uint8_t *ksrc = reinterpret_cast<const uint8_t *>(a.bsk_fft) + (single ? (size_t)__ldg(a.ggsw_index + ct0) * K::GGSW_BYTES : 0);
+    uint32_t issued = 0;
+    auto pump = [&](uint32_t need) {
+        while (issued < total_slots && issued < it + (uint32_t)K::NSLOT) {
+            const uint32_t s = issued % K::NSLOT;
+            if (issued >= (uint32_t)K::NSLOT) {
+                const uint32_t par = ((issued / K::NSLOT) - 1u) & 1u;
+                if (issued < need) mbar_wait(empty + s, par, a.err_flag);
+                else if (!mbar_try(empty + s, par)) break;
+            }
+            mbar_expect_tx(full + s, K::SLOT_BYTES);
+            bulk_g2s(ring + s * K::SLOT_BYTES, ksrc + (size_t)issued * K::SLOT_BYTES, K::SLOT_BYTES, full + s);
+            issued++;
+        }
+    };
+#pragma unroll 1
+    for (uint32_t i = 0; i < n_steps; i++) {
+        const uint32_t rot = single ? 0u : at[i];
+        if (!single && rot == 0) {
+            // diff == 0 => external product == 0 exactly: consume this step's slots without using them
+#pragma unroll 1
+            for (int s = 0; s < K::SLOTS_PER_STEP; s++, it++) {
+                if (producer) pump(it + 1);
+                mbar_wait(full + (it % K::NSLOT), (it / K::NSLOT) & 1u, a.err_flag);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + (it % K::NSLOT));
+            }
+            continue;
+        }
+        zero_acc<K>(R);
+#pragma unroll 1
+        for (uint32_t p = 0; p < (uint32_t)K::P; p++) {
+#pragma unroll 1
+            for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) {
+                phase_F1<K>(R, t, p, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) {
+                    return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - sbase[pp * K::N + j];
+                });
+                team_bar_id(bar_id, K::T);
+                phase_F2<K>(R, jbB, twB, buf0, buf1);
+                team_bar_id(bar_id, K::T);
+                phase_F3<K>(R, t, twC, buf1);
+                {
+                    const uint32_t s = it % K::NSLOT;
+                    if (producer) pump(it + 1);
+                    mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
+                    phase_mac<K, 0>(R, t, reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + s);
+                    it++;
+                }
+                {
+                    const uint32_t s = it % K::NSLOT;
+                    if (producer) pump(it + 1);
+                    mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
+                    phase_mac<K, 1>(R, t, reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + s);
+                    it++;
+                }
+            }
+        }
+        // inverse transforms: for every column the low-limb product, then the high-limb product, combined in registers
+        auto inverse = [&](int sel) {
+            phase_I1<K>(R, t, sel, twC, buf0);
+            team_bar_id(bar_id, K::T);
+            phase_I2<K>(R, jbB, twB, buf0, buf1);
+            if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
+            team_bar_id(bar_id, K::T);
+            phase_I3<K>(R, t, a.tw.twA, buf1);
+        };
+#pragma unroll 1
+        for (int c = 0; c < K::P; c++) {
+            uint32_t lo[2 * K::E];
+            inverse(2 * c);
+            phase_round_lo<K>(R, lo, maxfrac);
+            inverse(2 * c + 1);
+            phase_round_hi<K>(R, t, lo, acc + c * K::N, maxfrac);
+        }
+        team_bar_id(bar_id, K::T);   // accumulator updates visible to the whole team before the next step reads them
+    }
+    uint32_t *out = a.glwe_out + (size_t)ct * K::P * K::N;
+    for (uint32_t idx = t; idx < (uint32_t)(K::P * K::N); idx += K::T) out[idx] = acc[idx];
+    if constexpr (K::CHECK) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxfrac = fmax(maxfrac, __shfl_xor_sync(0xFFFFFFFFu, maxfrac, o));
+        if (lane == 0) atomicMax(a.margin, (unsigned long long)__double_as_longlong(maxfrac));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ key transform
+// grid = number of polynomials (n*ROWS*P); block = 2T (one team per limb); in natural [n][ROWS][P][N] u32,
+// out [n][ROWS][2][P][M] complex.
+struct FftTransformArgs {
+    TwTablesF tw;
+    const uint32_t *raw;
+    cplx *out;
+};
+template <class K>
+__global__ void __launch_bounds__(2 * K::T) bsk_fft_transform_kernel(const __grid_constant__ FftTransformArgs a) {
+    using C = typename K::F;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, limb = tid / K::T, t = tid % K::T;
+    cplx *buf0 = reinterpret_cast<cplx *>(smem) + limb * 2 * C::MPAD, *buf1 = buf0 + C::MPAD;
+    const size_t poly = blockIdx.x;  // = (i*ROWS + r)*P + c
+    const size_t ir = poly / K::P, c = poly % K::P;
+    const uint32_t *g = a.raw + poly * K::N;
+    cplx *o = a.out + ((ir * 2 + limb) * K::P + c) * K::M;
+    FftRegs<K> R;
+    phase_T1<K>(R, t, (int)limb, g, a.tw.twA, buf0);
+    team_bar_id(limb + 1, K::T);
+    phase_F2<K>(R, jbase_B<C>(t), a.tw.twB + (t >> C::QB) * C::NB_TW, buf0, buf1);
+    team_bar_id(limb + 1, K::T);
+    phase_T3<K>(R, t, a.tw.twC + t * C::NC_TW, buf1, o);
+}
+
+}  // namespace fft
+}  // namespace tfhe

@@ -11,7 +11,9 @@
 #include "../../include/tfhe_b200.h"
 #include "api_internal.hpp"
 #include "host_tables.hpp"
+#include "host_tables_fft.hpp"
 #include "kernels.cuh"
+#include "kernels_fft.cuh"
 
 using namespace tfhe;
 
@@ -39,6 +41,10 @@ struct tfhe_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = true;
     int pbs_id = -1, ks_id = -1;
+    int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
+    fft::cplx *d_ftw[2] = {};                // FFT pass-B / pass-C twiddle tables
+    fft::TwTablesF ftw;
+    unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
     std::string err;
     uint32_t *d_tw[2][4] = {};
     TwTables tw[2];
@@ -59,7 +65,9 @@ struct tfhe_ctx {
 
 struct tfhe_bk {
     tfhe_ctx *ctx = nullptr;
-    uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]
+    int path = TFHE_PATH_NTT;
+    uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]                      (TFHE_PATH_NTT)
+    fft::cplx *d_bsk_fft = nullptr; // [n][ROWS][2 limbs][P][N/2], scaled 2/N  (TFHE_PATH_FFT)
     uint32_t *d_ksk = nullptr;      // [kN*l_ks][n+1]
 };
 
@@ -108,6 +116,9 @@ int finish_out(tfhe_ctx *ctx, void *dst, size_t bytes, const void *dev) {
     return TFHE_OK;
 }
 
+#ifndef TFHE_DEFAULT_PATH
+#define TFHE_DEFAULT_PATH TFHE_PATH_NTT   // path chosen for parameter sets that have both instantiations
+#endif
 // ---- kernel configurations (must match api_internal.hpp) ----
 #ifndef TFHE_STAGE_P0
 #define TFHE_STAGE_P0 1
@@ -149,7 +160,58 @@ int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
     ctx->launches++;
     return TFHE_OK;
 }
-int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a) {
+// ---- FP64-FFT path (kernels_fft.cuh): instantiated parameter sets
+#ifndef TFHE_FFT_CHECK
+#define TFHE_FFT_CHECK 1
+#endif
+#ifndef TFHE_FFT_TEAMS_P1
+#define TFHE_FFT_TEAMS_P1 4
+#endif
+using KF1 = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_TEAMS_P1, TFHE_FFT_CHECK != 0>;
+bool fft_available(int pbs_id) { return pbs_id == 1; }
+
+template <class K>
+int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
+    fft::FftArgs f = {};
+    f.tw = ctx->ftw;
+    f.bsk_fft = key;
+    f.lwe_in = a.lwe_in; f.luts = a.luts; f.lut_idx = a.lut_idx;
+    f.in0 = a.in0; f.in1 = a.in1; f.ggsw_index = a.ggsw_index;
+    f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
+    f.n = a.n; f.batch = a.batch; f.mode = a.mode; f.log_p = a.log_p; f.enc_shift = a.enc_shift;
+    const size_t smem = (size_t)K::TEAMS * K::team_bytes((int)a.n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8;
+    if (smem > 227 * 1024) return fail(ctx, TFHE_E_PARAM, "lwe_dimension too large for the FFT path's shared-memory layout");
+    auto kern = fft::pbs_fft_kernel<K>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = a.mode == 0 ? (unsigned)((a.batch + K::TEAMS - 1) / K::TEAMS) : (unsigned)a.batch;
+    kern<<<grid, K::THREADS, smem, ctx->stream>>>(f);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return TFHE_OK;
+}
+template <class K>
+int launch_fft_transform_t(tfhe_ctx *ctx, const uint32_t *raw, fft::cplx *out, size_t n) {
+    fft::FftTransformArgs ta;
+    ta.tw = ctx->ftw; ta.raw = raw; ta.out = out;
+    const size_t smem = (size_t)2 * 2 * K::F::MPAD * 16;
+    auto kern = fft::bsk_fft_transform_kernel<K>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)(n * K::ROWS * K::P), 2 * K::T, smem, ctx->stream>>>(ta);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return TFHE_OK;
+}
+size_t fft_key_bytes(const tfhe_ctx *ctx) {
+    return ctx->n() * (ctx->k() + 1) * ctx->p.pbs_levels * 2 * (ctx->k() + 1) * (ctx->N() / 2) * sizeof(fft::cplx);
+}
+
+int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
+    if (bk->path == TFHE_PATH_FFT) {
+        switch (ctx->pbs_id) {
+        case 1: return launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
+        }
+        return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
+    }
     switch (ctx->pbs_id) {
     case 0: return launch_pbs_t<K0>(ctx, a);
     case 1: return launch_pbs_t<K1>(ctx, a);
@@ -241,7 +303,7 @@ int run_bootstrap(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *d_in, const 
         if (const char *m = getenv("TFHE_B200_SKEW_MOD")) a.skew_mod = (uint32_t)atoi(m);
     }
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-    int rc = launch_pbs(ctx, a);
+    int rc = launch_pbs(ctx, a, bk);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev[2], ctx->stream));
     rc = run_key_switch(ctx, bk, (const uint32_t *)ctx->glwe.p, 0, batch, d_out);
@@ -321,6 +383,26 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         ctx->tw[pr].invB = (const uint2 *)ctx->d_tw[pr][2];
         ctx->tw[pr].invC = (const uint2 *)ctx->d_tw[pr][3];
     }
+    if (fft_available(ctx->pbs_id)) {
+        const int logm = (int)p->glwe_poly_degree - 1, floge = 3;
+        fft::HostFftTw ft;
+        fft::build_fft_tables(logm, floge, ft);
+        for (size_t i = 0; i < ft.A.size(); i++) ctx->ftw.twA[i] = ft.A[i];
+        const std::vector<fft::cplx> *fsrc[2] = {&ft.B, &ft.C};
+        for (int i = 0; i < 2; i++) {
+            if (cudaMalloc(&ctx->d_ftw[i], fsrc[i]->size() * sizeof(fft::cplx)) != cudaSuccess) return bail("cudaMalloc");
+            if (cudaMemcpy(ctx->d_ftw[i], fsrc[i]->data(), fsrc[i]->size() * sizeof(fft::cplx), cudaMemcpyHostToDevice) != cudaSuccess)
+                return bail("cudaMemcpy");
+        }
+        ctx->ftw.twB = ctx->d_ftw[0];
+        ctx->ftw.twC = ctx->d_ftw[1];
+        if (cudaMalloc(&ctx->d_margin, 8) != cudaSuccess || cudaMemset(ctx->d_margin, 0, 8) != cudaSuccess) return bail("cudaMalloc");
+        ctx->path = TFHE_DEFAULT_PATH;
+    }
+    if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
+        if (!strcmp(e, "fft") && fft_available(ctx->pbs_id)) ctx->path = TFHE_PATH_FFT;
+        if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
+    }
     *out = ctx;
     return TFHE_OK;
 }
@@ -334,6 +416,9 @@ void tfhe_ctx_destroy(tfhe_ctx *ctx) {
         for (int i = 0; i < 4; i++)
             if (ctx->d_tw[pr][i]) cudaFree(ctx->d_tw[pr][i]);
     if (ctx->d_err) cudaFree(ctx->d_err);
+    for (int i = 0; i < 2; i++)
+        if (ctx->d_ftw[i]) cudaFree(ctx->d_ftw[i]);
+    if (ctx->d_margin) cudaFree(ctx->d_margin);
     for (auto &e : ctx->ev)
         if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -354,6 +439,26 @@ int tfhe_ctx_set_stream(tfhe_ctx *ctx, void *s) {
 }
 uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path) {
+    if (!ctx) return TFHE_E_PARAM;
+    if (path == TFHE_PATH_NTT) { ctx->path = path; return TFHE_OK; }
+    if (path == TFHE_PATH_FFT && fft_available(ctx->pbs_id)) { ctx->path = path; return TFHE_OK; }
+    return fail(ctx, TFHE_E_PARAM, "arithmetic path not instantiated for this parameter set");
+}
+int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx) { return ctx ? ctx->path : TFHE_E_PARAM; }
+int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out) {
+    if (!ctx || !out) return TFHE_E_PARAM;
+    *out = 0.0;
+    if (!ctx->d_margin) return TFHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    unsigned long long bits = 0;
+    CU(cudaMemcpy(&bits, ctx->d_margin, 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemset(ctx->d_margin, 0, 8));
+    memcpy(out, &bits, 8);
+    return TFHE_OK;
+}
+
 int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe_bk **out) {
     if (!ctx || !bsk || !ksk || !out) return TFHE_E_PARAM;
     CU(cudaSetDevice(ctx->device));
@@ -361,9 +466,11 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     const size_t ksk_words = ctx->kd() * (ctx->n() + 1);
     tfhe_bk *bk = new tfhe_bk();
     bk->ctx = ctx;
+    bk->path = ctx->path;
     auto cleanup = [&]() { tfhe_bk_free(bk); };
     cudaError_t e;
-    if ((e = cudaMalloc(&bk->d_bsk_ntt, bsk_words * 2 * 4)) != cudaSuccess || (e = cudaMalloc(&bk->d_ksk, ksk_words * 4)) != cudaSuccess) {
+    e = bk->path == TFHE_PATH_FFT ? cudaMalloc(&bk->d_bsk_fft, fft_key_bytes(ctx)) : cudaMalloc(&bk->d_bsk_ntt, bsk_words * 2 * 4);
+    if (e != cudaSuccess || (e = cudaMalloc(&bk->d_ksk, ksk_words * 4)) != cudaSuccess) {
         cleanup();
         return fail(ctx, TFHE_E_OOM, cudaGetErrorString(e));
     }
@@ -378,7 +485,10 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
         raw_dev = d_raw;
     }
     e = cudaMemcpyAsync(bk->d_ksk, ksk, ksk_words * 4, is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
-    int rc = (e == cudaSuccess) ? launch_transform(ctx, raw_dev, bk->d_bsk_ntt, ctx->n()) : fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
+    int rc;
+    if (e != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
+    else if (bk->path == TFHE_PATH_FFT) rc = launch_fft_transform_t<KF1>(ctx, raw_dev, bk->d_bsk_fft, ctx->n());
+    else rc = launch_transform(ctx, raw_dev, bk->d_bsk_ntt, ctx->n());
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (d_raw) cudaFree(d_raw);
     if (rc == TFHE_OK && es != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(es));
@@ -391,8 +501,22 @@ void tfhe_bk_free(tfhe_bk *bk) {
     if (!bk) return;
     if (bk->ctx) cudaSetDevice(bk->ctx->device);
     if (bk->d_bsk_ntt) cudaFree(bk->d_bsk_ntt);
+    if (bk->d_bsk_fft) cudaFree(bk->d_bsk_fft);
     if (bk->d_ksk) cudaFree(bk->d_ksk);
     delete bk;
+}
+
+size_t tfhe_bk_transformed_bytes(const tfhe_bk *bk) {
+    if (!bk || !bk->ctx) return 0;
+    return bk->path == TFHE_PATH_FFT ? fft_key_bytes(bk->ctx) : bk->ctx->n() * bk->ctx->ggsw_words() * 2 * 4;
+}
+int tfhe_bk_read_transformed(const tfhe_bk *bk, void *out, size_t bytes) {
+    if (!bk || !bk->ctx || !out || bytes != tfhe_bk_transformed_bytes(bk)) return TFHE_E_PARAM;
+    tfhe_ctx *ctx = bk->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(out, bk->path == TFHE_PATH_FFT ? (const void *)bk->d_bsk_fft : (const void *)bk->d_bsk_ntt, bytes, cudaMemcpyDeviceToHost));
+    return TFHE_OK;
 }
 
 int tfhe_bootstrap_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, const uint32_t *luts, size_t n_luts,
@@ -554,7 +678,7 @@ static int ext_or_cmux(tfhe_ctx *ctx, const tfhe_bk *bk, int mode, const uint32_
     a.glwe_out = (uint32_t *)d_out;
     a.err_flag = ctx->d_err;
     a.n = (uint32_t)ctx->n(); a.batch = (uint32_t)batch; a.mode = (uint32_t)mode;
-    if ((rc = launch_pbs(ctx, a))) return rc;
+    if ((rc = launch_pbs(ctx, a, bk))) return rc;
     if ((rc = finish_out(ctx, out, bytes, d_out))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     return TFHE_OK;
@@ -590,7 +714,7 @@ int tfhe_blind_rotate(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, 
     a.n = (uint32_t)ctx->n(); a.batch = (uint32_t)batch; a.mode = 0;
     a.log_p = ctx->p.log_p;
     a.enc_shift = ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits);
-    if ((rc = launch_pbs(ctx, a))) return rc;
+    if ((rc = launch_pbs(ctx, a, bk))) return rc;
     if ((rc = finish_out(ctx, glwe_out, out_bytes, d_out))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     uint32_t flag = 0;
