@@ -105,8 +105,11 @@ uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx);
 #define TFHE_PATH_FFT 1
 int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path);
 int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx);
-/* FFT path only: the largest distance to the nearest integer of any value rounded by the blind rotation since the
- * ctx was created or this function was last called (resets it).  The a-priori bound is 2^-9; exactness needs < 1/2. */
+/* FFT path only.  Exactness rests on the a-priori error bound (2^-9 before rounding).  With checking
+ * switched on (env TFHE_B200_FFT_CHECK=1 or tfhe_ctx_set_fft_check) the blind rotation runs a kernel variant that also
+ * records the largest distance to the nearest integer of every value it rounds (about 5 % slower);
+ * tfhe_fft_rounding_margin returns that maximum since the last call and resets it (0 when nothing was recorded). */
+int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on);
 int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out);
 
 /* Copies BSK+KSK (host or device pointers) to the ctx's device and transforms the BSK into the domain of the ctx's

@@ -19,60 +19,77 @@ template <class K>
 struct EmuF {
     using C = typename K::F;
     HostFftTw tw;
-    std::vector<FftRegs<K>> regs;
+    std::vector<FftRegs<K>> regs;            // [P sub-teams][T]
     std::vector<uint32_t> acc;
-    std::vector<int16_t> stash;
-    std::vector<cplx> buf;
+    std::vector<int16_t> stash;              // [P][(L-1)*2E*T]
+    std::vector<cplx> buf;                   // [P][2][MPAD]
     double maxfrac = 0.0;
-    EmuF() : regs(K::T), acc(K::P * K::N), stash((K::L > 1 ? K::L - 1 : 1) * 2 * K::E * K::T), buf(2 * C::MPAD) {
+    static constexpr size_t STASH = (K::L > 1 ? K::L - 1 : 1) * 2 * K::E * K::T;
+    EmuF() : regs(K::P * K::T), acc(K::P * K::N), stash(K::P * STASH), buf(K::P * 2 * C::MPAD) {
         build_fft_tables(C::LOGM, C::LOGE, tw);
     }
-    cplx *b0() { return buf.data(); }
-    cplx *b1() { return buf.data() + C::MPAD; }
+    FftRegs<K> &R(int s, uint32_t t) { return regs[s * K::T + t]; }
+    cplx *b0(int s) { return buf.data() + (size_t)s * 2 * C::MPAD; }
+    cplx *b1(int s) { return b0(s) + C::MPAD; }
     const cplx *twB(uint32_t t) const { return tw.B.data() + (t >> C::QB) * C::NB_TW; }
-    const cplx *twC(uint32_t t) const { return tw.C.data() + t * C::NC_TW; }
+    const cplx *twC() const { return tw.C.data(); }
 
-    // raw GGSW [ROWS][P][N] -> [ROWS][2 limbs][P][M] complex, slot order, scaled by 1/M
+    // raw GGSW [ROWS][P][N] -> [ROWS (level-major)][2 limbs][P][M] complex, slot order, scaled by 1/M
     void transform_ggsw(const uint32_t *raw, cplx *out) {
         for (int r = 0; r < K::ROWS; r++)
             for (int limb = 0; limb < 2; limb++)
                 for (int c = 0; c < K::P; c++) {
                     const uint32_t *g = raw + ((size_t)r * K::P + c) * K::N;
-                    cplx *o = out + (((size_t)r * 2 + limb) * K::P + c) * K::M;
-                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_T1<K>(regs[t], t, limb, g, tw.A.data(), b0());
-                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2<K>(regs[t], jbase_B<C>(t), twB(t), b0(), b1());
-                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_T3<K>(regs[t], t, twC(t), b1(), o);
+                    const size_t row = key_row_index<K>(r / K::L, r % K::L);
+                    cplx *o = out + ((row * 2 + limb) * K::P + c) * K::M;
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_T1<K>(R(0, t), t, limb, g, tw.A.data(), b0(0));
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2<K>(R(0, t), jbase_B<C>(t), twB(t), b0(0), b1(0));
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_T3<K>(R(0, t), t, twC(), b1(0), o);
                 }
     }
     template <class DiffFn>
     void step(const cplx *key, DiffFn diff) {
-        for (uint32_t t = 0; t < (uint32_t)K::T; t++) zero_acc<K>(regs[t]);
-        for (int r = 0; r < K::ROWS; r++) {
-            const uint32_t p = r / K::L, lev = r % K::L;
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F1<K>(regs[t], t, p, lev, stash.data(), tw.A.data(), b0(), diff);
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2<K>(regs[t], jbase_B<C>(t), twB(t), b0(), b1());
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
-                phase_F3<K>(regs[t], t, twC(t), b1());
-                phase_mac<K, 0>(regs[t], t, key + ((size_t)r * 2 + 0) * K::P * K::M);
-                phase_mac<K, 1>(regs[t], t, key + ((size_t)r * 2 + 1) * K::P * K::M);
+        for (auto &r : regs) zero_acc<K>(r);
+        for (int lev = 0; lev < K::L; lev++) {
+            for (int s = 0; s < K::P; s++) {   // sub-teams run concurrently on the GPU; any order between barriers is legal
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++)
+                    phase_F1<K>(R(s, t), t, s, lev, stash.data() + s * STASH, tw.A.data(), b0(s), diff);
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
+                    phase_F3<K>(R(s, t), t, twC(), b1(s));
+                    phase_xstore<K>(R(s, t), t, b0(s));
+                }
+            }
+            for (int p = 0; p < K::P; p++) {
+                const cplx *slot = key + (size_t)key_row_index<K>(p, lev) * 2 * K::P * K::M;
+                for (int s = 0; s < K::P; s++)
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
+                        if (p == s) phase_mac<K, true>(R(s, t), t, s, slot, nullptr);
+                        else phase_mac<K, false>(R(s, t), t, s, slot, b0(p));
+                    }
             }
         }
         std::vector<uint32_t> lo((size_t)K::T * 2 * K::E);
-        for (int sel = 0; sel < 2 * K::P; sel++) {
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I1<K>(regs[t], t, sel, twC(t), b0());
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I2<K>(regs[t], jbase_B<C>(t), twB(t), b0(), b1());
+        for (int s = 0; s < K::P; s++) {
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I1<K, 0>(R(s, t), t, twC(), b0(s));
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I2<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
             for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
-                phase_I3<K>(regs[t], t, tw.A.data(), b1());
-                if ((sel & 1) == 0) phase_round_lo<K>(regs[t], lo.data() + (size_t)t * 2 * K::E, maxfrac);
-                else phase_round_hi<K>(regs[t], t, lo.data() + (size_t)t * 2 * K::E, acc.data() + (size_t)(sel >> 1) * K::N, maxfrac);
+                phase_I3<K>(R(s, t), t, tw.A.data(), b1(s));
+                phase_round_lo<K>(R(s, t), lo.data() + (size_t)t * 2 * K::E, maxfrac);
+            }
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I1<K, 1>(R(s, t), t, twC(), b0(s));
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I2<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
+                phase_I3<K>(R(s, t), t, tw.A.data(), b1(s));
+                phase_round_hi<K>(R(s, t), t, lo.data() + (size_t)t * 2 * K::E, acc.data() + (size_t)s * K::N, maxfrac);
             }
         }
     }
 };
 
 using F_P0 = FftPbsCfg<9, 3, 2, 6, 4, 4>;
-using F_P1 = FftPbsCfg<10, 3, 1, 3, 8, 4>;
-using F_P2 = FftPbsCfg<11, 4, 1, 3, 8, 4>;
+using F_P1 = FftPbsCfg<10, 3, 1, 3, 8, 3>;
+using F_P2 = FftPbsCfg<11, 4, 1, 3, 8, 3>;
 
 template <class K>
 int run_transform(const uint32_t *raw, double *out) {

@@ -25,6 +25,8 @@ class Env:
         self.o = orc.params(**{f: getattr(self.p, f) for f in FIELDS})
         self.lwe_sk, self.glwe_sk, self.bsk, self.ksk = T.bootstrapping_key_gen(self.p, 0xB200)
         self.ctx = T.Context(self.p, 0, path=T.PATH_FFT if path == "fft" else T.PATH_NTT)
+        if path == "fft":
+            self.ctx.set_fft_check(True)   # also record the distance-to-integer of every rounded value
         self.bk = self.ctx.upload_key(self.bsk, self.ksk)
 
     def enc(self, m, idx):
@@ -69,8 +71,12 @@ def test_p1_batch_4096_identity(which):
     if which.endswith(":fft"):
         # a-posteriori exactness certificate: no value was further than 2^-6 from an integer before rounding
         # (a-priori bound 2^-9); and the two arithmetic paths agree bit for bit on the whole batch
-        assert e.ctx.fft_rounding_margin() < 2.0 ** -6
+        m = e.ctx.fft_rounding_margin()
+        assert 0.0 < m < 2.0 ** -6, m
         assert np.array_equal(out, env("P1").ctx.bootstrap(env("P1").bk, cts, tv))
+        e.ctx.set_fft_check(False)          # the production kernel (no margin recording) gives the same bits
+        assert np.array_equal(out, e.ctx.bootstrap(e.bk, cts, tv))
+        e.ctx.set_fft_check(True)
 
 
 @pytest.mark.parametrize("which", ["P1", "P1:fft"])

@@ -29,6 +29,8 @@ class Env:
         self.o = oparams(self.p)
         self.lwe_sk, self.glwe_sk, self.bsk, self.ksk = T.bootstrapping_key_gen(self.p, seed)
         self.ctx = T.Context(self.p, 0, path=T.PATH_FFT if path == "fft" else T.PATH_NTT)
+        if path == "fft":
+            self.ctx.set_fft_check(True)   # also record the distance-to-integer of every rounded value
         self.bk = self.ctx.upload_key(self.bsk, self.ksk)
 
     def enc(self, m, idx, seed=1):

@@ -108,7 +108,7 @@ def lib():
         "tfhe_lwe_decrypt": [VP, SZ, VP, C.POINTER(C.c_uint32)],
         "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP],
         "tfhe_ctx_create": [PP, C.c_int, C.POINTER(VP)], "tfhe_ctx_set_stream": [VP, VP],
-        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP],
+        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_fft_check": [VP, C.c_int],
         "tfhe_fft_rounding_margin": [VP, C.POINTER(C.c_double)],
         "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)], "tfhe_bk_read_transformed": [VP, VP, SZ],
         "tfhe_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP],
@@ -142,7 +142,7 @@ EXPORTS = [
     "tfhe_ctx_launch_count", "tfhe_bk_upload", "tfhe_bk_free", "tfhe_bootstrap_batch", "tfhe_gate_batch",
     "tfhe_gates_batch", "tfhe_switch_modulus", "tfhe_decompose", "tfhe_glwe_mul_monomial", "tfhe_external_product",
     "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
-    "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin",
+    "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check",
     "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed",
 ]
 
@@ -298,6 +298,10 @@ class Context:
     @property
     def pbs_path(self) -> int:
         return int(lib().tfhe_ctx_get_pbs_path(self._h))
+
+    def set_fft_check(self, on: bool = True):
+        """FFT path: run the kernel variant that records the rounding margin (see fft_rounding_margin)."""
+        self._ck(lib().tfhe_ctx_set_fft_check(self._h, 1 if on else 0))
 
     def fft_rounding_margin(self) -> float:
         """Largest distance to an integer of any value rounded by the FFT path since the last call (must be << 0.5)."""

@@ -29,6 +29,11 @@
 
 #include "tfhe_core.cuh"
 
+// slots of the key ring (see FftPbsCfg): one slot = one GGSW row (both limbs)
+#ifndef TFHE_FFT_NSLOT
+#define TFHE_FFT_NSLOT 2
+#endif
+
 namespace tfhe {
 namespace fft {
 
@@ -178,48 +183,56 @@ constexpr int kMaxTwA = 15;
 struct TwTablesF {
     cplx twA[kMaxTwA];   // pass A (stages 0..LOGE-1): the same for every thread -> kernel-parameter constant bank
     const cplx *twB;     // [2^LOGE (hA)][NB_TW]
-    const cplx *twC;     // [T][NC_TW]
+    const cplx *twC;     // [NC_TW][T]  (consecutive lanes read consecutive 16 bytes)
 };
 
-template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int TEAMS_, bool CHECK_ = true>
+// Work split of one ciphertext (one "team"): P = k+1 SUB-TEAMS of T threads.  Sub-team s owns polynomial s of the GLWE
+// being decomposed (its digits and their L forward transforms) AND column s of the result (its multiply-accumulate
+// against column s of every GGSW row, its two inverse transforms -- low and high key limb -- and the update of acc[s]).
+// Per level the sub-teams exchange their transformed digit rows through shared memory (xbuf), so every forward
+// transform is computed once and every thread carries only 2 x E complex accumulators.
+template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true>
 struct FftPbsCfg {
     using F = FftCfg<LOGN_ - 1, LOGE_>;
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2;
     static constexpr int K = K_, P = K_ + 1, L = L_, LOGB = LOGB_, ROWS = P * L;
-    static constexpr int E = F::E, T = F::T, TEAMS = TEAMS_;
+    static constexpr int E = F::E, T = F::T;
+    static constexpr int CTS = CTS_;                    // ciphertexts (teams) per CTA, sharing one key stream
     static constexpr bool CHECK = CHECK_;
-    static constexpr int WARPS_PER_TEAM = T / 32;
-    static constexpr int THREADS = TEAMS * T;
+    static constexpr int WARPS_PER_SUB = T / 32, TEAM_THREADS = P * T, THREADS = CTS * TEAM_THREADS;
     static_assert(LOGB * L <= 32 && 32 % LOGB == 0, "decomposer must divide log_q (SURVEY 9-B H2)");
     static_assert(LOGB <= 14, "digits are stashed as int16");
     // exactness: largest limb convolution * 2^9 (error constant incl. safety) must stay below 2^51
     static_assert((double)ROWS * N * (double)(1 << LOGB) * 32768.0 * 512.0 < 2251799813685248.0, "FP64 exactness bound");
-    // key stream: one SLOT = one limb of one GGSW row = P polynomials of M complex points (slot order)
-    static constexpr int POLY_BYTES = M * 16, SLOT_BYTES = P * POLY_BYTES, SLOTS_PER_STEP = ROWS * 2, NSLOT = 4;
+    // key stream: one SLOT = one GGSW row, both limbs: [2 limbs][P columns][M] complex in slot order; rows are stored
+    // in consumption order (level-major: row index lev*P + p for polynomial p, level lev)
+    static constexpr int POLY_BYTES = M * 16, LIMB_BYTES = P * POLY_BYTES, SLOT_BYTES = 2 * LIMB_BYTES, SLOTS_PER_STEP = ROWS;
+    static constexpr int NSLOT = TFHE_FFT_NSLOT;
     static constexpr size_t GGSW_BYTES = (size_t)SLOTS_PER_STEP * SLOT_BYTES;
-    // shared memory per team
+    // shared memory per team: acc, then per sub-team {stash, buf0, buf1}, then the mod-switched mask
     static constexpr int TM_ACC = 0;                                   // u32 acc[P][N]
-    static constexpr int TM_STASH = TM_ACC + P * N * 4;                // int16 stash[(L-1)*2E][T]
-    static constexpr int STASH_BYTES = ((L > 1 ? (L - 1) : 1) * 2 * E * T * 2 + 15) & ~15;
-    static constexpr int TM_BUF = TM_STASH + STASH_BYTES;              // cplx buf[2][MPAD]
-    static constexpr int TM_AT = TM_BUF + 2 * F::MPAD * 16;            // u16 at[n+1] (size known at launch)
+    static constexpr int STASH_BYTES = ((L > 1 ? (L - 1) : 1) * 2 * E * T * 2 + 15) & ~15;  // int16 [(L-1)*2E][T]
+    static constexpr int SUB_BYTES = STASH_BYTES + 2 * F::MPAD * 16;   // + cplx buf[2][MPAD]
+    static constexpr int TM_SUB = TM_ACC + P * N * 4;
+    static constexpr int TM_AT = TM_SUB + P * SUB_BYTES;               // u16 at[n+1] (size known at launch)
     static constexpr int team_bytes(int n) { return (TM_AT + (n + 1) * 2 + 127) & ~127; }
-    static_assert(TEAMS >= 3 || TEAMS == 1, "single-ciphertext modes borrow the accumulators of teams 1 and 2");
+    static_assert(CTS >= 2 || CTS == 1, "teams per CTA");  // single-ciphertext modes borrow the accumulators of teams 1 and 2 (need CTS >= 3)
 };
+// index of GGSW row (polynomial p, level lev) in the stored key = its position in the consumption order
+template <class K>
+TFHE_HD constexpr uint32_t key_row_index(uint32_t p, uint32_t lev) { return lev * K::P + p; }
 
 template <class K>
 struct FftRegs {
     cplx x[K::E];
-    cplx acc[2][K::P][K::E];  // [limb][column][point]
+    cplx acc[2][K::E];  // [limb][point] of this sub-team's column
 };
 template <class K>
 TFHE_HD void zero_acc(FftRegs<K> &r) {
 #pragma unroll
     for (int l = 0; l < 2; l++)
 #pragma unroll
-        for (int c = 0; c < K::P; c++)
-#pragma unroll
-            for (int e = 0; e < K::E; e++) r.acc[l][c][e] = cplx{0.0, 0.0};
+        for (int e = 0; e < K::E; e++) r.acc[l][e] = cplx{0.0, 0.0};
 }
 
 // centred limbs of a key word (see header): s = lo + 2^16 hi
@@ -259,59 +272,68 @@ TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, int16
     fwd_pass<C::LOGE, C::LOGE>(r.x, twA);
     store_A<C>(r.x, buf0, t);
 }
-template <class C>
-TFHE_HD void load_tw(cplx *dst, const cplx *src, int n) {
-#pragma unroll
-    for (int i = 0; i < n; i++) dst[i] = src[i];
+// Twiddles of a pass, tw[2^u - 1 + m] for stage u and m in [0, 2^u).  Siblings satisfy w(st, 2b+1) = i * w(st, 2b)
+// (exponents differ by M and zeta^M = i), so only the even-m entries are loaded (stride = element stride of the table)
+// and the odd ones are formed by a swap and a sign flip: halves the twiddle traffic on the L1/shared-memory data pipe.
+template <int NST>
+TFHE_HD void load_pass_tw(cplx *tw, const cplx *table, uint32_t stride) {
+    static_for<0, NST>([&](auto ui) {
+        constexpr int u = decltype(ui)::value;
+        static_for<0, (1 << u)>([&](auto mi) {
+            constexpr int m = decltype(mi)::value, i = (1 << u) - 1 + m;
+            if constexpr (u == 0 || (m & 1) == 0) tw[i] = table[(size_t)i * stride];
+            else tw[i] = cplx{-tw[i - 1].im, tw[i - 1].re};
+        });
+    });
 }
 // F2: layout B, pass B.   F3: layout C, pass C.
 template <class K>
 TFHE_HD void phase_F2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NB_TW];
-#pragma unroll
-    for (int i = 0; i < C::NB_TW; i++) tw[i] = twB_thread[i];
+    load_pass_tw<C::QB>(tw, twB_thread, 1);
     load_B<C>(r.x, buf0, jbB);
     fwd_pass<C::LOGE, C::QB>(r.x, tw);
     store_B<C>(r.x, buf1, jbB);
 }
 template <class K>
-TFHE_HD void phase_F3(FftRegs<K> &r, uint32_t t, const cplx *twC_thread, const cplx *buf1) {
+TFHE_HD void phase_F3(FftRegs<K> &r, uint32_t t, const cplx *twC, const cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NC_TW];
-#pragma unroll
-    for (int i = 0; i < C::NC_TW; i++) tw[i] = twC_thread[i];
+    load_pass_tw<C::LOGE>(tw, twC + t, C::T);
     load_C<C>(r.x, buf1, t);
     fwd_pass<C::LOGE, C::LOGE>(r.x, tw);
 }
-// multiply-accumulate against one limb of a GGSW row: slot = [P][M] complex in slot order (point (t<<LOGE)|e of
-// column c at c*M + e*T + t, so consecutive lanes read consecutive 16 bytes)
-template <class K, int LIMB>
-TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, const cplx *slot) {
-#pragma unroll
-    for (int c = 0; c < K::P; c++)
-#pragma unroll
-        for (int e = 0; e < K::E; e++) {
-            const cplx g = slot[c * K::M + e * K::T + t];
-            cplx &a = r.acc[LIMB][c][e];
-            a.re = fma_d(-r.x[e].im, g.im, fma_d(r.x[e].re, g.re, a.re));
-            a.im = fma_d(r.x[e].im, g.re, fma_d(r.x[e].re, g.im, a.im));
-        }
-}
-// I1: accumulator (limb, c) -> inverse pass C -> buf0;  I2: pass B;  I3: pass A, result z in r.x (layout A)
+// X: publish this sub-team's transformed digit row for the other sub-teams (slot order: point (t<<LOGE)|e at e*T + t)
 template <class K>
-TFHE_HD void phase_I1(FftRegs<K> &r, uint32_t t, int sel /* = c*2 + limb */, const cplx *twC_thread, cplx *buf0) {
+TFHE_HD void phase_xstore(const FftRegs<K> &r, uint32_t t, cplx *xbuf) {
+#pragma unroll
+    for (int e = 0; e < K::E; e++) xbuf[e * K::T + t] = r.x[e];
+}
+// multiply-accumulate of one transformed digit row against column `col` of one GGSW row, both limbs:
+// slot = [2 limbs][P][M] complex in slot order (consecutive lanes read consecutive 16 bytes); xsrc = this thread's own
+// r.x (OWN) or the publishing sub-team's xbuf.
+template <class K, bool OWN>
+TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot, const cplx *xbuf) {
+    const cplx *g0 = slot + col * K::M + t, *g1 = g0 + K::P * K::M;
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const cplx xv = OWN ? r.x[e] : xbuf[e * K::T + t];
+        const cplx a = g0[e * K::T], b = g1[e * K::T];
+        r.acc[0][e].re = fma_d(-xv.im, a.im, fma_d(xv.re, a.re, r.acc[0][e].re));
+        r.acc[0][e].im = fma_d(xv.im, a.re, fma_d(xv.re, a.im, r.acc[0][e].im));
+        r.acc[1][e].re = fma_d(-xv.im, b.im, fma_d(xv.re, b.re, r.acc[1][e].re));
+        r.acc[1][e].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e].im));
+    }
+}
+// I1: accumulator of limb LIMB -> inverse pass C -> buf0;  I2: pass B;  I3: pass A, result z in r.x (layout A)
+template <class K, int LIMB>
+TFHE_HD void phase_I1(FftRegs<K> &r, uint32_t t, const cplx *twC, cplx *buf0) {
     using C = typename K::F;
     cplx tw[C::NC_TW];
+    load_pass_tw<C::LOGE>(tw, twC + t, C::T);
 #pragma unroll
-    for (int i = 0; i < C::NC_TW; i++) tw[i] = twC_thread[i];
-    static_for<0, 2 * K::P>([&](auto si) {
-        constexpr int s = decltype(si)::value;
-        if (sel == s) {
-#pragma unroll
-            for (int e = 0; e < K::E; e++) r.x[e] = r.acc[s & 1][s >> 1][e];
-        }
-    });
+    for (int e = 0; e < K::E; e++) r.x[e] = r.acc[LIMB][e];
     inv_pass<C::LOGE, C::LOGE>(r.x, tw);
     store_C<C>(r.x, buf0, t);
 }
@@ -319,8 +341,7 @@ template <class K>
 TFHE_HD void phase_I2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NB_TW];
-#pragma unroll
-    for (int i = 0; i < C::NB_TW; i++) tw[i] = twB_thread[i];
+    load_pass_tw<C::QB>(tw, twB_thread, 1);
     load_B<C>(r.x, buf0, jbB);
     inv_pass<C::LOGE, C::QB>(r.x, tw);
     store_B<C>(r.x, buf1, jbB);
@@ -365,8 +386,8 @@ TFHE_HD void phase_T1(FftRegs<K> &r, uint32_t t, int limb, const uint32_t *g, co
     store_A<C>(r.x, buf0, t);
 }
 template <class K>
-TFHE_HD void phase_T3(FftRegs<K> &r, uint32_t t, const cplx *twC_thread, const cplx *buf1, cplx *out) {
-    phase_F3<K>(r, t, twC_thread, buf1);
+TFHE_HD void phase_T3(FftRegs<K> &r, uint32_t t, const cplx *twC, const cplx *buf1, cplx *out) {
+    phase_F3<K>(r, t, twC, buf1);
     constexpr double scale = 1.0 / (double)K::M;  // power of two: exact
 #pragma unroll
     for (int e = 0; e < K::E; e++) out[e * K::T + t] = cplx{mul_d(r.x[e].re, scale), mul_d(r.x[e].im, scale)};

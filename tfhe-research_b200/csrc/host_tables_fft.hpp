@@ -21,7 +21,7 @@ inline cplx fft_twiddle(int logm, int st, uint32_t b) {
 }
 
 struct HostFftTw {
-    std::vector<cplx> A, B, C;  // A: [E-1]; B: [2^LOGE][NB_TW]; C: [T][E-1]
+    std::vector<cplx> A, B, C;  // A: [E-1]; B: [2^LOGE][NB_TW]; C: [E-1][T]
 };
 inline void build_fft_tables(int logm, int loge, HostFftTw &out) {
     const int qb = logm - 2 * loge;
@@ -32,9 +32,9 @@ inline void build_fft_tables(int logm, int loge, HostFftTw &out) {
     for (uint32_t hA = 0; hA < (1u << loge); hA++)
         for (int u = 0; u < qb; u++)
             for (uint32_t m = 0; m < (1u << u); m++) out.B.push_back(fft_twiddle(logm, loge + u, (hA << u) | m));
-    for (uint32_t t = 0; t < (uint32_t)T; t++)
-        for (int u = 0; u < loge; u++)
-            for (uint32_t m = 0; m < (1u << u); m++) out.C.push_back(fft_twiddle(logm, loge + qb + u, (t << u) | m));
+    for (int u = 0; u < loge; u++)   // layout [NC_TW][T]
+        for (uint32_t m = 0; m < (1u << u); m++)
+            for (uint32_t t = 0; t < (uint32_t)T; t++) out.C.push_back(fft_twiddle(logm, loge + qb + u, (t << u) | m));
 }
 
 }  // namespace fft

@@ -1,11 +1,12 @@
 // kernels_fft.cuh -- sm_100a kernels of the FP64-FFT arithmetic path (see fft_team.cuh for the arithmetic).
 //
-//   pbs_fft_kernel        blind rotation: ONE CTA = TEAMS ciphertexts (one team of T threads each, the GLWE
-//                         accumulator of every team resident in shared memory for all n CMUX steps); thread 0
-//                         streams the FFT-domain bootstrapping key global -> shared with TMA bulk copies
-//                         into a 4-slot ring (full/empty mbarriers).  Every key byte fetched from L2 is used by
-//                         all TEAMS ciphertexts of the CTA, so the L2 -> SM traffic per ciphertext is 1/TEAMS of
-//                         the key size.  Also runs one external product / CMUX for the sub-operation entry points.
+//   pbs_fft_kernel        blind rotation: ONE CTA = CTS ciphertexts; each ciphertext is a team of P = k+1 sub-teams
+//                         of T threads (sub-team s: digits + forward transforms of polynomial s, multiply-accumulate +
+//                         inverse transforms of result column s); the GLWE accumulator of every team is resident in
+//                         shared memory for all n CMUX steps; thread 0 streams the FFT-domain bootstrapping key
+//                         global -> shared with TMA bulk copies into a ring (full/empty mbarriers).  Every key byte
+//                         fetched from L2 is used by all CTS ciphertexts of the CTA.  Also runs one external product /
+//                         CMUX for the sub-operation entry points.
 //   bsk_fft_transform_kernel   raw BSK -> limb-split FFT domain (one-off at key upload)
 //
 // Reference: bootstrapping.rs:58-105 (blind rotation), ggsw.rs:132-178 (external product, cmux).
@@ -30,8 +31,18 @@ struct FftArgs {
     uint32_t n, batch, mode, log_p, enc_shift;
 };
 
+// TFHE_FFT_ABLATE (bit mask, measurement only -- results are WRONG when set): 1 = constant digits instead of the
+// decomposition, 2 = no multiply-accumulate, 4 = no team barriers, 16 = no inverse transforms.  Used to attribute the
+// step time of the latency-bound kernel to its phases (profiles/r01_fft_ablation.log).
+#ifndef TFHE_FFT_ABLATE
+#define TFHE_FFT_ABLATE 0
+#endif
 __device__ __forceinline__ void team_bar_id(uint32_t id, int nthreads) {
+#if (TFHE_FFT_ABLATE & 4)
+    __syncwarp();
+#else
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
 }
 __device__ __forceinline__ bool mbar_try(uint64_t *bar, uint32_t parity) {
     uint32_t done;
@@ -50,50 +61,54 @@ template <class K>
 __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_constant__ FftArgs a) {
     using C = typename K::F;
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t team = tid / K::TEAM_THREADS, tt = tid % K::TEAM_THREADS, sub = tt / K::T, t = tt % K::T;
     const uint32_t team_bytes = (uint32_t)K::team_bytes((int)a.n);
-    uint8_t *ring = smem + K::TEAMS * team_bytes;
+    uint8_t *ring = smem + K::CTS * team_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
 
     const bool single = a.mode != 0;   // sub-operation entry points: one ciphertext (team 0) per CTA, its own GGSW
-    const uint32_t ct0 = single ? blockIdx.x : blockIdx.x * K::TEAMS;
-    const uint32_t active = single ? 1u : min((uint32_t)K::TEAMS, a.batch - ct0);
+    // blind rotation: the batch is split over the grid as evenly as possible (CTA b gets base or base+1 ciphertexts,
+    // base+1 <= CTS), so a partially filled last wave shortens every CTA instead of leaving SMs idle
+    const uint32_t base = a.batch / gridDim.x, rem = a.batch % gridDim.x;
+    const uint32_t ct0 = single ? blockIdx.x : blockIdx.x * base + min(blockIdx.x, rem);
+    const uint32_t active = single ? 1u : base + (blockIdx.x < rem ? 1u : 0u);
     const uint32_t n_steps = single ? 1u : a.n;
     const uint32_t total_slots = n_steps * K::SLOTS_PER_STEP;
 
     if (tid == 0) {
         for (int s = 0; s < K::NSLOT; s++) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, active * K::WARPS_PER_TEAM);
+            mbar_init(empty + s, active * K::P * K::WARPS_PER_SUB);   // every warp of every active team consumes every slot
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();   // the only CTA-wide barrier: roles split below
+    __syncthreads();   // the only CTA-wide barrier: teams are independent below
 
-    const uint32_t team = tid / K::T, t = tid % K::T;
     if (team >= active) return;
     const uint32_t ct = ct0 + team;
     uint8_t *tm = smem + team * team_bytes;
     uint32_t *acc = reinterpret_cast<uint32_t *>(tm + K::TM_ACC);
-    int16_t *stash = reinterpret_cast<int16_t *>(tm + K::TM_STASH);
-    cplx *buf0 = reinterpret_cast<cplx *>(tm + K::TM_BUF), *buf1 = buf0 + C::MPAD;
+    uint8_t *sb = tm + K::TM_SUB + sub * K::SUB_BYTES;
+    int16_t *stash = reinterpret_cast<int16_t *>(sb);
+    cplx *buf0 = reinterpret_cast<cplx *>(sb + K::STASH_BYTES), *buf1 = buf0 + C::MPAD;
     uint16_t *at = reinterpret_cast<uint16_t *>(tm + K::TM_AT);
-    const uint32_t bar_id = team + 1;
+    const uint32_t team_bar = 1 + team * (K::P + 1), sub_bar = team_bar + 1 + sub;   // named barriers
     const uint32_t jbB = jbase_B<C>(t);
     const cplx *twB = a.tw.twB + (t >> C::QB) * C::NB_TW;
-    const cplx *twC = a.tw.twC + t * C::NC_TW;
+    const cplx *twC = a.tw.twC;
     // operands of the decomposed difference  minuend(p, (j - rot)) - subtrahend(p, j)
     const uint32_t *mbase = acc, *sbase = acc;
 
     if (!single) {
         // utils.rs:23-33 mod switch of (a_0..a_{n-1}, b) to 2N
         const uint32_t *lwe = a.lwe_in + (size_t)ct * (a.n + 1);
-        for (uint32_t i = t; i <= a.n; i += K::T) at[i] = (uint16_t)mod_switch(__ldg(lwe + i), K::LOGN);
-        team_bar_id(bar_id, K::T);
+        for (uint32_t i = tt; i <= a.n; i += K::TEAM_THREADS) at[i] = (uint16_t)mod_switch(__ldg(lwe + i), K::LOGN);
+        team_bar_id(team_bar, K::TEAM_THREADS);
         // acc = trivial GLWE of the encoded test vector times X^{-b~}  (bootstrapping.rs:79-86)
         const uint32_t b = at[a.n];
         const uint32_t *lut = a.luts + (size_t)(a.lut_idx ? __ldg(a.lut_idx + ct) : 0u) * K::N;
-        for (uint32_t idx = t; idx < (uint32_t)(K::P * K::N); idx += K::T) {
+        for (uint32_t idx = tt; idx < (uint32_t)(K::P * K::N); idx += K::TEAM_THREADS) {
             const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
             uint32_t v = 0;
             if (p == (uint32_t)K::K) {
@@ -111,7 +126,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         uint32_t *din = reinterpret_cast<uint32_t *>(smem + 1 * team_bytes + K::TM_ACC);
         uint32_t *zero = reinterpret_cast<uint32_t *>(smem + 2 * team_bytes + K::TM_ACC);
         const uint32_t *x0 = a.in0 + (size_t)ct * K::P * K::N, *x1 = a.in1 + (size_t)ct * K::P * K::N;
-        for (uint32_t idx = t; idx < (uint32_t)(K::P * K::N); idx += K::T) {
+        for (uint32_t idx = tt; idx < (uint32_t)(K::P * K::N); idx += K::TEAM_THREADS) {
             const uint32_t v0 = __ldg(x0 + idx);
             acc[idx] = a.mode == 2 ? v0 : 0u;
             din[idx] = a.mode == 2 ? __ldg(x1 + idx) - v0 : v0;
@@ -120,15 +135,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         mbase = din;
         sbase = zero;
     }
-    team_bar_id(bar_id, K::T);
+    team_bar_id(team_bar, K::TEAM_THREADS);
 
     FftRegs<K> R;
     double maxfrac = 0.0;
     uint32_t it = 0;   // position in the key stream (the same sequence in every warp)
 
-    // ---- key stream producer: thread 0 of team 0 issues the TMA bulk copies (SASS UBLKCP) in consumption order, up to
-    // NSLOT slots ahead of its own position.  pump(need) returns with slots [0, need) issued (blocking on the ring's
-    // `empty` barriers if it must) and opportunistically issues further slots whose ring entry is already free.
+    // ---- key stream producer: thread 0 issues the TMA bulk copies (SASS UBLKCP) in consumption order, up to NSLOT
+    // slots ahead of its own position.  pump(need) returns with slots [0, need) issued (blocking on the ring's `empty`
+    // barriers if it must) and opportunistically issues further slots whose ring entry is already free.
     const bool producer = tid == 0;
     const uint8_t *ksrc = reinterpret_cast<const uint8_t *>(a.bsk_fft) + (single ? (size_t)__ldg(a.ggsw_index + ct0) * K::GGSW_BYTES : 0);
     uint32_t issued = 0;
@@ -141,10 +156,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 else if (!mbar_try(empty + s, par)) break;
             }
             mbar_expect_tx(full + s, K::SLOT_BYTES);
-            bulk_g2s(ring + s * K::SLOT_BYTES, ksrc + (size_t)issued * K::SLOT_BYTES, K::SLOT_BYTES, full + s);
+            bulk_g2s(ring + s * K::SLOT_BYTES, ksrc + (size_t)issued * K::SLOT_BYTES, K::LIMB_BYTES, full + s);
+            bulk_g2s(ring + s * K::SLOT_BYTES + K::LIMB_BYTES, ksrc + (size_t)issued * K::SLOT_BYTES + K::LIMB_BYTES, K::LIMB_BYTES, full + s);
             issued++;
         }
     };
+    auto diff = [&](uint32_t pp, uint32_t j, uint32_t rot) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - sbase[pp * K::N + j]; };
 #pragma unroll 1
     for (uint32_t i = 0; i < n_steps; i++) {
         const uint32_t rot = single ? 0u : at[i];
@@ -161,57 +178,56 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
         zero_acc<K>(R);
 #pragma unroll 1
-        for (uint32_t p = 0; p < (uint32_t)K::P; p++) {
+        for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) {
+            // forward transform of this sub-team's digit row (polynomial `sub`, level `lev`)
+#if (TFHE_FFT_ABLATE & 1)
+            phase_F1<K>(R, t, sub, 1u, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return 0u; });
+#else
+            phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
+#endif
+            team_bar_id(sub_bar, K::T);
+            phase_F2<K>(R, jbB, twB, buf0, buf1);
+            team_bar_id(sub_bar, K::T);
+            phase_F3<K>(R, t, twC, buf1);
+            phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its pass-B loads
+            team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
 #pragma unroll 1
-            for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) {
-                phase_F1<K>(R, t, p, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) {
-                    return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - sbase[pp * K::N + j];
-                });
-                team_bar_id(bar_id, K::T);
-                phase_F2<K>(R, jbB, twB, buf0, buf1);
-                team_bar_id(bar_id, K::T);
-                phase_F3<K>(R, t, twC, buf1);
-                {
-                    const uint32_t s = it % K::NSLOT;
-                    if (producer) pump(it + 1);
-                    mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
-                    phase_mac<K, 0>(R, t, reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES));
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty + s);
-                    it++;
-                }
-                {
-                    const uint32_t s = it % K::NSLOT;
-                    if (producer) pump(it + 1);
-                    mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
-                    phase_mac<K, 1>(R, t, reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES));
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(empty + s);
-                    it++;
-                }
+            for (uint32_t p = 0; p < (uint32_t)K::P; p++) {
+                const uint32_t s = it % K::NSLOT;
+                if (producer) pump(it + 1);
+                mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
+#if !(TFHE_FFT_ABLATE & 2)
+                const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
+                if (p == sub) phase_mac<K, true>(R, t, sub, slot, nullptr);
+                else phase_mac<K, false>(R, t, sub, slot, reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES));
+#endif
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty + s);
+                it++;
             }
+            team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
         }
-        // inverse transforms: for every column the low-limb product, then the high-limb product, combined in registers
-        auto inverse = [&](int sel) {
-            phase_I1<K>(R, t, sel, twC, buf0);
-            team_bar_id(bar_id, K::T);
-            phase_I2<K>(R, jbB, twB, buf0, buf1);
-            if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
-            team_bar_id(bar_id, K::T);
-            phase_I3<K>(R, t, a.tw.twA, buf1);
-        };
-#pragma unroll 1
-        for (int c = 0; c < K::P; c++) {
-            uint32_t lo[2 * K::E];
-            inverse(2 * c);
-            phase_round_lo<K>(R, lo, maxfrac);
-            inverse(2 * c + 1);
-            phase_round_hi<K>(R, t, lo, acc + c * K::N, maxfrac);
-        }
-        team_bar_id(bar_id, K::T);   // accumulator updates visible to the whole team before the next step reads them
+#if !(TFHE_FFT_ABLATE & 16)
+        // inverse transforms of this sub-team's column: low-limb product, then high-limb product, combined in registers
+        uint32_t lo[2 * K::E];
+        phase_I1<K, 0>(R, t, twC, buf0);
+        team_bar_id(sub_bar, K::T);
+        phase_I2<K>(R, jbB, twB, buf0, buf1);
+        if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
+        team_bar_id(sub_bar, K::T);
+        phase_I3<K>(R, t, a.tw.twA, buf1);
+        phase_round_lo<K>(R, lo, maxfrac);
+        phase_I1<K, 1>(R, t, twC, buf0);
+        team_bar_id(sub_bar, K::T);
+        phase_I2<K>(R, jbB, twB, buf0, buf1);
+        team_bar_id(sub_bar, K::T);
+        phase_I3<K>(R, t, a.tw.twA, buf1);
+        phase_round_hi<K>(R, t, lo, acc + sub * K::N, maxfrac);
+#endif
+        team_bar_id(sub_bar, K::T);   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
     }
-    uint32_t *out = a.glwe_out + (size_t)ct * K::P * K::N;
-    for (uint32_t idx = t; idx < (uint32_t)(K::P * K::N); idx += K::T) out[idx] = acc[idx];
+    uint32_t *out = a.glwe_out + ((size_t)ct * K::P + sub) * K::N;
+    for (uint32_t idx = t; idx < (uint32_t)K::N; idx += K::T) out[idx] = acc[sub * K::N + idx];
     if constexpr (K::CHECK) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxfrac = fmax(maxfrac, __shfl_xor_sync(0xFFFFFFFFu, maxfrac, o));
@@ -221,7 +237,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 
 // ------------------------------------------------------------------------------------------ key transform
 // grid = number of polynomials (n*ROWS*P); block = 2T (one team per limb); in natural [n][ROWS][P][N] u32,
-// out [n][ROWS][2][P][M] complex.
+// out [n][ROWS (level-major)][2][P][M] complex.
 struct FftTransformArgs {
     TwTablesF tw;
     const uint32_t *raw;
@@ -233,16 +249,17 @@ __global__ void __launch_bounds__(2 * K::T) bsk_fft_transform_kernel(const __gri
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, limb = tid / K::T, t = tid % K::T;
     cplx *buf0 = reinterpret_cast<cplx *>(smem) + limb * 2 * C::MPAD, *buf1 = buf0 + C::MPAD;
-    const size_t poly = blockIdx.x;  // = (i*ROWS + r)*P + c
-    const size_t ir = poly / K::P, c = poly % K::P;
+    const size_t poly = blockIdx.x;  // = (i*ROWS + r)*P + c, r = p*L + lev (ggsw.rs:37-41)
+    const size_t ir = poly / K::P, c = poly % K::P, i = ir / K::ROWS, r = ir % K::ROWS;
     const uint32_t *g = a.raw + poly * K::N;
-    cplx *o = a.out + ((ir * 2 + limb) * K::P + c) * K::M;
+    const size_t row = i * K::ROWS + key_row_index<K>((uint32_t)(r / K::L), (uint32_t)(r % K::L));   // consumption order
+    cplx *o = a.out + ((row * 2 + limb) * K::P + c) * K::M;
     FftRegs<K> R;
     phase_T1<K>(R, t, (int)limb, g, a.tw.twA, buf0);
     team_bar_id(limb + 1, K::T);
     phase_F2<K>(R, jbase_B<C>(t), a.tw.twB + (t >> C::QB) * C::NB_TW, buf0, buf1);
     team_bar_id(limb + 1, K::T);
-    phase_T3<K>(R, t, a.tw.twC + t * C::NC_TW, buf1, o);
+    phase_T3<K>(R, t, a.tw.twC, buf1, o);
 }
 
 }  // namespace fft

@@ -42,6 +42,7 @@ struct tfhe_ctx {
     bool own_stream = true;
     int pbs_id = -1, ks_id = -1;
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
+    bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
     fft::cplx *d_ftw[2] = {};                // FFT pass-B / pass-C twiddle tables
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
@@ -117,7 +118,7 @@ int finish_out(tfhe_ctx *ctx, void *dst, size_t bytes, const void *dev) {
 }
 
 #ifndef TFHE_DEFAULT_PATH
-#define TFHE_DEFAULT_PATH TFHE_PATH_NTT   // path chosen for parameter sets that have both instantiations
+#define TFHE_DEFAULT_PATH TFHE_PATH_FFT   // path chosen for parameter sets that have both instantiations (measured faster)
 #endif
 // ---- kernel configurations (must match api_internal.hpp) ----
 #ifndef TFHE_STAGE_P0
@@ -161,13 +162,11 @@ int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
     return TFHE_OK;
 }
 // ---- FP64-FFT path (kernels_fft.cuh): instantiated parameter sets
-#ifndef TFHE_FFT_CHECK
-#define TFHE_FFT_CHECK 1
+#ifndef TFHE_FFT_CTS_P1
+#define TFHE_FFT_CTS_P1 3
 #endif
-#ifndef TFHE_FFT_TEAMS_P1
-#define TFHE_FFT_TEAMS_P1 4
-#endif
-using KF1 = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_TEAMS_P1, TFHE_FFT_CHECK != 0>;
+using KF1 = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, false>;   // production: a-priori exactness bound only
+using KF1C = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true>;   // + records the rounding margin (tests, validation)
 bool fft_available(int pbs_id) { return pbs_id == 1; }
 
 template <class K>
@@ -179,11 +178,17 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     f.in0 = a.in0; f.in1 = a.in1; f.ggsw_index = a.ggsw_index;
     f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
     f.n = a.n; f.batch = a.batch; f.mode = a.mode; f.log_p = a.log_p; f.enc_shift = a.enc_shift;
-    const size_t smem = (size_t)K::TEAMS * K::team_bytes((int)a.n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8;
+    const size_t smem = (size_t)K::CTS * K::team_bytes((int)a.n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8;
     if (smem > 227 * 1024) return fail(ctx, TFHE_E_PARAM, "lwe_dimension too large for the FFT path's shared-memory layout");
     auto kern = fft::pbs_fft_kernel<K>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = a.mode == 0 ? (unsigned)((a.batch + K::TEAMS - 1) / K::TEAMS) : (unsigned)a.batch;
+    unsigned grid = (unsigned)a.batch;
+    if (a.mode == 0) {
+        // whole waves of one CTA per SM; the kernel spreads the batch evenly over them (<= CTS ciphertexts per CTA)
+        const unsigned ctas = (unsigned)((a.batch + K::CTS - 1) / K::CTS), sms = (unsigned)ctx->sm_count;
+        grid = ctas <= sms ? ctas : ((ctas + sms - 1) / sms) * sms;
+        if (grid > a.batch) grid = (unsigned)a.batch;
+    }
     kern<<<grid, K::THREADS, smem, ctx->stream>>>(f);
     CU(cudaGetLastError());
     ctx->launches++;
@@ -208,7 +213,7 @@ size_t fft_key_bytes(const tfhe_ctx *ctx) {
 int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
     if (bk->path == TFHE_PATH_FFT) {
         switch (ctx->pbs_id) {
-        case 1: return launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
+        case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
         }
         return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
     }
@@ -399,6 +404,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         if (cudaMalloc(&ctx->d_margin, 8) != cudaSuccess || cudaMemset(ctx->d_margin, 0, 8) != cudaSuccess) return bail("cudaMalloc");
         ctx->path = TFHE_DEFAULT_PATH;
     }
+    if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
         if (!strcmp(e, "fft") && fft_available(ctx->pbs_id)) ctx->path = TFHE_PATH_FFT;
         if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
@@ -446,6 +452,11 @@ int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path) {
     return fail(ctx, TFHE_E_PARAM, "arithmetic path not instantiated for this parameter set");
 }
 int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx) { return ctx ? ctx->path : TFHE_E_PARAM; }
+int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on) {
+    if (!ctx) return TFHE_E_PARAM;
+    ctx->fft_check = on != 0;
+    return TFHE_OK;
+}
 int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out) {
     if (!ctx || !out) return TFHE_E_PARAM;
     *out = 0.0;

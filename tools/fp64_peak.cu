@@ -35,6 +35,33 @@ __global__ void __launch_bounds__(256) k_rate(double *sink, double a, double b, 
     if (s == 1.2345 || t == 77) sink[0] = s + t;
 }
 
+// DFMA with three distinct register operands (as in the FFT butterflies / multiply-accumulate): does operand
+// collection sustain the full rate?  KIND 0: x = fma(x, y, z) (3 register pairs); 1: x = fma(x, y, c) (2 + constant);
+// 2: like 0 with 16 independent chains per thread
+template <int KIND>
+__global__ void __launch_bounds__(256) k_rate3(double *sink, double a, double b, int iters) {
+    constexpr int NCH = KIND == 2 ? 16 : 8;
+    double x[NCH], y[8], z[8];
+#pragma unroll
+    for (int i = 0; i < NCH; i++) x[i] = a + threadIdx.x + i;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { y[i] = 1.0 + 1e-9 * (threadIdx.x + i); z[i] = 1e-9 * (threadIdx.x * 3 + i); }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < (KIND == 2 ? 2 : 4); u++) {
+#pragma unroll
+            for (int i = 0; i < NCH; i++) {
+                if (KIND == 1) x[i] = fma(x[i], y[(i + u) & 7], b);
+                else x[i] = fma(x[i], y[(i + u) & 7], z[(i + 2 * u + 1) & 7]);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; i++) s += x[i];
+    if (s == 1.2345) sink[0] = s;
+}
+
 // dependent chain latency: one warp per SM, one chain
 template <int KIND>
 __global__ void k_lat(double *sink, double a, double b, int iters, long long *cycles) {
@@ -111,6 +138,32 @@ int main() {
         }
         const double ops = (double)blocks * 256 * iters * 32.0;  // per pipe: 32 ops per thread per iteration
         printf(", \"%s_Tops\": %.3f", names[kind], ops / (best * 1e-3) / 1e12);
+    }
+    const char *n3[3] = {"dfma_3reg", "dfma_2reg_const", "dfma_3reg_16chains"};
+    for (int kind = 0; kind < 3; kind++) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(e0);
+            if (kind == 0) k_rate3<0><<<blocks, 256>>>(sink, 1.0000001, 1e-9, iters);
+            else if (kind == 1) k_rate3<1><<<blocks, 256>>>(sink, 1.0000001, 1e-9, iters);
+            else k_rate3<2><<<blocks, 256>>>(sink, 1.0000001, 1e-9, iters);
+            cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < best) best = ms;
+        }
+        const double ops = (double)blocks * 256 * iters * 32.0;
+        printf(", \"%s_Tops\": %.3f", n3[kind], ops / (best * 1e-3) / 1e12);
+    }
+    for (int w = 1; w <= 4; w++) {   // rate vs resident warps per scheduler (3-register DFMA, 8 chains): 128-thread CTAs, w per SM
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; rep++) {
+            cudaEventRecord(e0);
+            k_rate3<0><<<pr.multiProcessorCount * w, 128>>>(sink, 1.0000001, 1e-9, iters);
+            cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (rep && ms < best) best = ms;
+        }
+        printf(", \"dfma_3reg_%dwarps_per_sched_Tops\": %.3f", w, (double)pr.multiProcessorCount * w * 128 * iters * 32.0 / (best * 1e-3) / 1e12);
     }
     {
         float best = 1e30f;
