@@ -171,6 +171,10 @@ int tfhe_gate_linear(tfhe_ctx *ctx, const uint32_t *ct0, const uint32_t *ct1, si
  * out[6..7] = FMA-bound butterfly stream (16 values, 8 twiddle pairs in registers, no corrections) with 128-thread
  * CTAs at 3 and at 8 CTAs per SM -- the blind-rotation kernel's own residency and a saturating one. */
 int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[8]);
+/* FP64 pipe of this device (the FFT path's arithmetic): out[0] = DFMA/s with two register operands + a constant (the
+ * pipe's issue rate), out[1] = DFMA/s with three distinct register operands (as in the multiply-accumulate),
+ * out[2] = forward FFT butterflies/s (6 DFMA each) issued from registers, out[3] reserved. */
+int tfhe_measure_fp64_peak(tfhe_ctx *ctx, double out[4]);
 /* Device time (ms, CUDA events on the ctx stream) of the last tfhe_bootstrap_batch / tfhe_gate(s)_batch:
  * out[0] blind rotation kernel, out[1] key-switch kernels, out[2] whole call incl. copies. */
 int tfhe_last_timing(const tfhe_ctx *ctx, double out[3]);

@@ -120,7 +120,7 @@ def lib():
         "tfhe_blind_rotate": [VP, VP, VP, VP, SZ, VP, SZ, VP],
         "tfhe_sample_extract": [VP, VP, SZ, VP], "tfhe_key_switch": [VP, VP, VP, SZ, VP],
         "tfhe_gate_linear": [VP, VP, VP, SZ, VP],
-        "tfhe_measure_int_peak": [VP, C.POINTER(C.c_double * 8)], "tfhe_last_timing": [VP, C.POINTER(C.c_double * 3)],
+        "tfhe_measure_int_peak": [VP, C.POINTER(C.c_double * 8)], "tfhe_measure_fp64_peak": [VP, C.POINTER(C.c_double * 4)], "tfhe_last_timing": [VP, C.POINTER(C.c_double * 3)],
     }
     for name, args in sig.items():
         f = getattr(L, name)
@@ -142,7 +142,7 @@ EXPORTS = [
     "tfhe_ctx_launch_count", "tfhe_bk_upload", "tfhe_bk_free", "tfhe_bootstrap_batch", "tfhe_gate_batch",
     "tfhe_gates_batch", "tfhe_switch_modulus", "tfhe_decompose", "tfhe_glwe_mul_monomial", "tfhe_external_product",
     "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
-    "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check",
+    "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
     "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed",
 ]
 
@@ -447,6 +447,11 @@ class Context:
         return {"imad": out[0], "imad_hi": out[1], "imad_wide": out[2], "shoup_butterfly_shared_tw": out[3],
                 "shoup_butterfly": out[4], "shoup_butterfly_imm_q": out[5],
                 "butterfly_stream_3cta": out[6], "butterfly_stream_8cta": out[7]}
+
+    def measure_fp64_peak(self):
+        out = (C.c_double * 4)()
+        self._ck(lib().tfhe_measure_fp64_peak(self._h, C.byref(out)))
+        return {"dfma": out[0], "dfma_3reg": out[1], "fft_butterfly": out[2]}
 
     def last_timing(self):
         out = (C.c_double * 3)()

@@ -262,5 +262,38 @@ __global__ void __launch_bounds__(2 * K::T) bsk_fft_transform_kernel(const __gri
     phase_T3<K>(R, t, a.tw.twC, buf1, o);
 }
 
+// ------------------------------------------------------------------------------------------ FP64 pipe peaks
+// Dependent-free DFMA loops: KIND 0 = two register operands + a constant (the pipe's issue rate, 64 lanes/clk/SM);
+// KIND 1 = three distinct register operands, as in the multiply-accumulate and the pass-B/C butterflies (measured
+// 2/3 of KIND 0 on B200: the third 64-bit register operand costs a cycle); KIND 2 = the forward butterfly stream
+// (4 three-register + 2 two-register DFMA per butterfly) from registers.
+template <int KIND>
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *sink, double a, double b, int iters) {
+    double x[8], y[8], z[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x[i] = a + threadIdx.x + i; y[i] = 1.0 + 1e-9 * (threadIdx.x + i); z[i] = 1e-9 * (threadIdx.x * 3 + i); }
+    for (int it = 0; it < iters; it++) {
+        if (KIND == 2) {
+            cplx *c = reinterpret_cast<cplx *>(x);   // 4 complex points, 2 stages
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                ct_bfly(c[0], c[2], cplx{y[u], z[u]});
+                ct_bfly(c[1], c[3], cplx{y[u + 1], z[u + 1]});
+                ct_bfly(c[0], c[1], cplx{y[u + 2], z[u + 2]});
+                ct_bfly(c[2], c[3], cplx{y[u + 3], z[u + 3]});
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int i = 0; i < 8; i++) x[i] = KIND == 0 ? __fma_rn(x[i], y[(i + u) & 7], b) : __fma_rn(x[i], y[(i + u) & 7], z[(i + 2 * u + 1) & 7]);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 1.2345) sink[0] = s;
+}
+
 }  // namespace fft
 }  // namespace tfhe

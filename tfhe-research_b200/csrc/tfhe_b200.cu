@@ -866,6 +866,41 @@ int tfhe_measure_int_peak(tfhe_ctx *ctx, double out[8]) {
     return TFHE_OK;
 }
 
+int tfhe_measure_fp64_peak(tfhe_ctx *ctx, double out[4]) {
+    if (!ctx || !out) return TFHE_E_PARAM;
+    CU(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, iters = 4096;
+    double *sink = nullptr;
+    CU(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int kind = 0; kind < 3; kind++) {
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) {
+            CU(cudaEventRecord(e0, ctx->stream));
+            if (kind == 0) fft::fp64_peak_kernel<0><<<blocks, 256, 0, ctx->stream>>>(sink, 1.0000001, 1e-9, iters);
+            else if (kind == 1) fft::fp64_peak_kernel<1><<<blocks, 256, 0, ctx->stream>>>(sink, 1.0000001, 1e-9, iters);
+            else fft::fp64_peak_kernel<2><<<blocks, 256, 0, ctx->stream>>>(sink, 1.0000001, 1e-9, iters);
+            CU(cudaEventRecord(e1, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            // kinds 0/1: 32 DFMA per thread per iteration; kind 2: 16 butterflies (6 DFMA each) per thread per iteration
+            const double units = (double)blocks * 256.0 * iters * (kind == 2 ? 16.0 : 32.0);
+            const double rate = units / (ms * 1e-3);
+            if (rep > 0 && rate > best) best = rate;
+            ctx->launches++;
+        }
+        out[kind] = best;
+    }
+    out[3] = 0;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return TFHE_OK;
+}
+
 int tfhe_last_timing(const tfhe_ctx *ctx, double out[3]) {
     if (!ctx || !out) return TFHE_E_PARAM;
     for (int i = 0; i < 3; i++) out[i] = ctx->last_ms[i];
