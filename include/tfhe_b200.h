@@ -134,6 +134,37 @@ int tfhe_gate_batch(tfhe_ctx *ctx, const tfhe_bk *bk, int gate, const uint32_t *
 int tfhe_gates_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint8_t *gates /* [B], host */, const uint32_t *ct0,
                      const uint32_t *ct1, size_t batch, uint32_t *out);
 
+/* ------------------------------------------------------------------ compositions of the same kernels */
+/* Key-switch-FIRST ordering (notes/TFHE.md:365-400): input and output live under the GLWE-derived LWE key
+ * (dimension kN, lwe.rs:62-73 `LweSecretKey::from(&glwe_sk)`): key_switch_lwe -> mod switch + blind rotation ->
+ * sample_extract.  Same kernels as tfhe_bootstrap_batch, composed in the other order. */
+int tfhe_bootstrap_batch_ks_first(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in /* [B][kN+1] */,
+                                  const uint32_t *luts /* [T][N] */, size_t n_luts, const uint32_t *lut_idx /* [B] or NULL */,
+                                  size_t batch, uint32_t *lwe_out /* [B][kN+1] */);
+/* k-input boolean gate (notes/Boolean Gates.md:9-11): ct_in = sum_i 2^i * cts[i] (Horner steps of lwe.rs:9-23 as in
+ * boolean.rs:18), then one PBS with the LUT of f.  truth_table bit j = f(j) for j = sum_i 2^i * bit_i, j < 2^k.
+ * Needs 2 <= k <= log_p (TFHE_E_PARAM otherwise).  f(0) = 1 is served as trivial(1) - gate(1 - f), because the
+ * reference's LUT construction is only sound for f(0) = 0. */
+int tfhe_gate_k_batch(tfhe_ctx *ctx, const tfhe_bk *bk, uint32_t k_inputs, uint32_t truth_table,
+                      const uint32_t *const *cts /* k_inputs pointers to [B][n+1] */, size_t batch, uint32_t *out);
+
+/* ------------------------------------------------------------------ flat wire / on-disk format */
+/* The reference has no serialisation.  One little-endian file = header {magic "TFHEB200", u32 version = 1,
+ * u32 kind, tfhe_params, u64 count: see tfhe_file_header, 80 bytes} + `count` u32 words in
+ * exactly the layouts listed at the top of this header.  Lets an outside party with cargo exchange golden vectors. */
+typedef enum tfhe_file_kind { TFHE_FILE_LWE_BATCH = 1, TFHE_FILE_GLWE_BATCH = 2, TFHE_FILE_BSK = 3, TFHE_FILE_KSK = 4,
+                              TFHE_FILE_LWE_SK = 5, TFHE_FILE_GLWE_SK = 6, TFHE_FILE_TEST_VECTOR = 7 } tfhe_file_kind;
+typedef struct tfhe_file_header {
+    char magic[8];       /* "TFHEB200" */
+    uint32_t version;    /* 1 */
+    uint32_t kind;       /* tfhe_file_kind */
+    tfhe_params params;  /* 56 bytes */
+    uint64_t count;      /* number of u32 words that follow */
+} tfhe_file_header;      /* 80 bytes */
+int tfhe_file_write(const char *path, int kind, const tfhe_params *p, const uint32_t *words, uint64_t count);
+/* Reads the header (always) and, when words != NULL, up to `capacity` words (TFHE_E_PARAM if the file holds more). */
+int tfhe_file_read(const char *path, tfhe_file_header *hdr_out, uint32_t *words, uint64_t capacity);
+
 /* ------------------------------------------------------------------ sub-operations (parity tests) */
 /* utils.rs:23-33 switch_modulus(values, 32, log2(N)+1) */
 int tfhe_switch_modulus(tfhe_ctx *ctx, const uint32_t *values, size_t len, uint32_t *out);

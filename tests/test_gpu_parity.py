@@ -221,3 +221,58 @@ def test_negacyclic_mul_utils_rs_155(preset, n):
     with pytest.raises(T.TfheError) as ei:
         e.ctx.negacyclic_mul(np.full((1, N), 5000, dtype=np.int32), g[:1])
     assert ei.value.code == T.TFHE_E_PARAM
+
+
+@pytest.mark.parametrize("preset,n", [("P0", 4), ("P1", 3), ("P1:fft", 3)])
+def test_ks_first_ordering_notes_tfhe_md_365(preset, n):
+    """key switch FIRST, then blind rotation + sample extraction (input/output under the kN-dim key)."""
+    import ctypes as C
+    e = env(preset, n)
+    L = orc.lib()
+    p = e.p
+    kN = p.k * p.N
+    big_sk = T.lwe_secret_key_from_glwe(e.glwe_sk)                 # lwe.rs:62-73
+    pm = 1 << p.log_p
+    B = 6
+    cts = np.stack([T.encrypt_lwe_plaintext(p, big_sk, T.encode_message(p, i % pm), 5, i) for i in range(B)])
+    tv = T.construct_identity_test_vector(p)
+    out = e.ctx.bootstrap_ks_first(e.bk, cts, tv)
+    assert out.shape == (B, kN + 1)
+    for b in range(B):
+        ks = orc.z(n + 1)
+        L.orc_key_switch_lwe(C.byref(e.o), cts[b], e.ksk, ks)
+        acc = orc.blind_rotate(e.o, ks, e.bsk, tv)
+        ext = orc.z(kN + 1)
+        L.orc_sample_extract(C.byref(e.o), acc.reshape(-1), 0, ext)
+        assert np.array_equal(out[b], ext), b
+        assert T.decode_rounded(p, T.decrypt_lwe(big_sk, out[b])) == b % pm
+
+
+@pytest.mark.parametrize("preset,n", [("P2", 2)])
+def test_k_input_gates_notes_boolean_gates_md(preset, n):
+    """3- and 4-input gates on a 4-bit message space; ct_in = sum 2^i c_i (Horner steps of boolean.rs:18)."""
+    e = env(preset, n)
+    p = e.p
+    pm = 1 << p.log_p
+    delta = 1 << (p.log_q - p.log_p - p.padding_bits)
+    for k, tt in ((3, 0b11101000), (3, 0b00000001), (4, 0x6996), (4, 0x8001)):   # majority3, NOR3, parity4, (all-equal)4
+        B = 1 << k
+        cts = [np.stack([e.enc((j >> i) & 1, 300 + 16 * i + j) for j in range(B)]) for i in range(k)]
+        out = e.ctx.gate_k(e.bk, tt, cts)
+        neg = tt & 1
+        lut = np.zeros(pm, dtype=np.uint32)
+        for j in range(1 << k):
+            lut[j] = ((tt >> j) & 1) ^ neg
+        tv = T.construct_test_from_lut(p, lut)
+        for j in range(B):
+            lin = np.zeros(n + 1, dtype=np.uint32)
+            for i in range(k):
+                lin = (lin + (cts[i][j].astype(np.uint64) << np.uint64(i)).astype(np.uint32)).astype(np.uint32)
+            exp = orc.bootstrap(e.o, lin, e.bsk, e.ksk, tv)
+            if neg:
+                exp = (0 - exp.astype(np.int64)).astype(np.uint32)
+                exp[n] = np.uint32((int(exp[n]) + delta) & 0xFFFFFFFF)
+            assert np.array_equal(out[j], exp), (k, hex(tt), j)
+            assert e.dec(out[j]) == (tt >> j) & 1, (k, hex(tt), j)
+    with pytest.raises(T.TfheError):
+        e.ctx.gate_k(e.bk, 0b10, [cts[0]] * 5)      # k > log_p

@@ -109,3 +109,22 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liborc" not in src and "import orc" not in src and "tfhe_oracle.h" not in src, f
+
+
+def test_wire_format_round_trip(tmp_path):
+    """flat little-endian u32 files (header + words in the reference's ndarray layouts)."""
+    p = T.TfheParams.default(test_cfg=True)
+    lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 7)
+    for kind, arr in ((T.FILE_BSK, bsk), (T.FILE_KSK, ksk), (T.FILE_LWE_SK, lwe_sk), (T.FILE_GLWE_SK, glwe_sk)):
+        path = str(tmp_path / f"k{kind}.tfhe")
+        T.save_words(path, kind, p, arr)
+        k2, p2, w = T.load_words(path)
+        assert k2 == kind and same_params(p, p2) and np.array_equal(w, arr)
+        raw = open(path, "rb").read()
+        assert raw[:8] == b"TFHEB200" and len(raw) == 80 + 4 * arr.size
+        assert np.array_equal(np.frombuffer(raw[80:], dtype="<u4"), arr)     # plain LE words, readable without this library
+    # a truncated or foreign file is rejected, not mis-read
+    bad = tmp_path / "bad.tfhe"
+    bad.write_bytes(b"NOTATFHE" + bytes(100))
+    with pytest.raises(T.TfheError):
+        T.load_words(str(bad))

@@ -112,6 +112,9 @@ def lib():
         "tfhe_fft_rounding_margin": [VP, C.POINTER(C.c_double)],
         "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)], "tfhe_bk_read_transformed": [VP, VP, SZ],
         "tfhe_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP],
+        "tfhe_bootstrap_batch_ks_first": [VP, VP, VP, VP, SZ, VP, SZ, VP],
+        "tfhe_gate_k_batch": [VP, VP, C.c_uint32, C.c_uint32, VP, SZ, VP],
+        "tfhe_file_write": [C.c_char_p, C.c_int, PP, VP, C.c_uint64], "tfhe_file_read": [C.c_char_p, VP, VP, C.c_uint64],
         "tfhe_gate_batch": [VP, VP, C.c_int, VP, VP, SZ, VP], "tfhe_gates_batch": [VP, VP, VP, VP, VP, SZ, VP],
         "tfhe_switch_modulus": [VP, VP, SZ, VP], "tfhe_decompose": [VP, C.c_int, VP, SZ, VP],
         "tfhe_glwe_mul_monomial": [VP, VP, VP, SZ, VP],
@@ -143,7 +146,8 @@ EXPORTS = [
     "tfhe_gates_batch", "tfhe_switch_modulus", "tfhe_decompose", "tfhe_glwe_mul_monomial", "tfhe_external_product",
     "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
     "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
-    "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed",
+    "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed", "tfhe_bootstrap_batch_ks_first", "tfhe_gate_k_batch",
+    "tfhe_file_write", "tfhe_file_read",
 ]
 
 
@@ -251,6 +255,36 @@ def bootstrapping_key_gen(params: TfheParams, seed: int):
     return lwe_sk, glwe_sk, bsk, ksk
 
 
+# ------------------------------------------------------------------ flat wire / on-disk format (include/tfhe_b200.h)
+FILE_LWE_BATCH, FILE_GLWE_BATCH, FILE_BSK, FILE_KSK, FILE_LWE_SK, FILE_GLWE_SK, FILE_TEST_VECTOR = range(1, 8)
+
+
+class FileHeader(C.Structure):
+    _fields_ = [("magic", C.c_char * 8), ("version", C.c_uint32), ("kind", C.c_uint32), ("params", TfheParams), ("count", C.c_uint64)]
+
+
+def save_words(path: str, kind: int, params: TfheParams, words) -> None:
+    """Write one array in the flat little-endian format (header + u32 words in the reference's ndarray layout)."""
+    w = np.ascontiguousarray(words, dtype=np.uint32).reshape(-1)
+    _check(lib().tfhe_file_write(os.fsencode(path), kind, C.byref(params), w.ctypes.data, w.size), f"cannot write {path}")
+
+
+def load_words(path: str):
+    """-> (kind, TfheParams, flat uint32 array)."""
+    h = FileHeader()
+    _check(lib().tfhe_file_read(os.fsencode(path), C.byref(h), None, 0), f"cannot read {path}")
+    w = np.empty(h.count, dtype=np.uint32)
+    _check(lib().tfhe_file_read(os.fsencode(path), C.byref(h), w.ctypes.data, w.size), f"cannot read {path}")
+    p = TfheParams()
+    C.memmove(C.byref(p), C.byref(h.params), C.sizeof(TfheParams))
+    return int(h.kind), p, w
+
+
+def lwe_secret_key_from_glwe(glwe_sk) -> np.ndarray:
+    """LweSecretKey::from(&GlweSecretKey) lwe.rs:62-73: the row-major flattening (dimension kN)."""
+    return np.ascontiguousarray(glwe_sk, dtype=np.uint32).reshape(-1).copy()
+
+
 # ------------------------------------------------------------------ device side
 class BootstrappingKey:
     """Device-resident BootstrappingKey (bootstrapping.rs:18-21): NTT-domain BSK + KSK."""
@@ -354,6 +388,27 @@ class Context:
             ops = np.ascontiguousarray(op, dtype=np.uint8)
             assert len(ops) == B
             self._ck(lib().tfhe_gates_batch(self._h, bk._h, ops.ctypes.data, _ptr(ct0), _ptr(ct1), B, _ptr(out)))
+        return out
+
+    # -- notes/TFHE.md:365-400: key switch first, then blind rotation + sample extraction (input/output dimension kN)
+    def bootstrap_ks_first(self, bk: BootstrappingKey, lwe_in, test_vectors, lut_idx=None, out=None):
+        p = self.params
+        lwe_in, tvs = _u32(lwe_in), _u32(test_vectors)
+        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
+        T = tvs.shape[0] if tvs.ndim == 2 else 1
+        idx = None if lut_idx is None else _u32(lut_idx)
+        out = _like(lwe_in, (B, p.k * p.N + 1)) if out is None else out
+        self._ck(lib().tfhe_bootstrap_batch_ks_first(self._h, bk._h, _ptr(lwe_in), _ptr(tvs), T, _ptr(idx), B, _ptr(out)))
+        return out
+
+    # -- notes/Boolean Gates.md:9-11: k-input gate, ct_in = sum 2^i * cts[i]; truth_table bit j = f(j)
+    def gate_k(self, bk: BootstrappingKey, truth_table: int, cts, out=None):
+        p = self.params
+        cts = [_u32(c) for c in cts]
+        B = cts[0].shape[0] if cts[0].ndim == 2 else 1
+        out = _like(cts[0], (B, p.n + 1)) if out is None else out
+        ptrs = (C.c_void_p * len(cts))(*[_ptr(c) for c in cts])
+        self._ck(lib().tfhe_gate_k_batch(self._h, bk._h, len(cts), truth_table, ptrs, B, _ptr(out)))
         return out
 
     def and_(self, bk, ct0, ct1):

@@ -3,6 +3,7 @@
 // encrypt/decrypt (lwe.rs:83-173) and key generation (bootstrapping.rs:23-56, ggsw.rs:76-130,
 // key_switching.rs:20-60).  No CUDA here; no dependency on oracle/.
 #include <math.h>
+#include <stdio.h>
 #include <string.h>
 
 #include <atomic>
@@ -267,6 +268,40 @@ int tfhe_keygen(const tfhe_params *pp, uint64_t seed, uint32_t *lwe_sk, uint32_t
         for (auto &t : th) t.join();
     }
     return TFHE_OK;
+}
+
+// ---- flat wire / on-disk format: header + little-endian u32 words
+int tfhe_file_write(const char *path, int kind, const tfhe_params *p, const uint32_t *words, uint64_t count) {
+    if (!path || !p || (!words && count)) return TFHE_E_PARAM;
+    static_assert(sizeof(tfhe_file_header) == 80, "wire header layout");
+    tfhe_file_header h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, "TFHEB200", 8);
+    h.version = 1;
+    h.kind = (uint32_t)kind;
+    h.params = *p;
+    h.count = count;
+    FILE *f = fopen(path, "wb");
+    if (!f) return TFHE_E_PARAM;
+    const bool ok = fwrite(&h, sizeof h, 1, f) == 1 && (count == 0 || fwrite(words, 4, count, f) == count);
+    return (fclose(f) == 0 && ok) ? TFHE_OK : TFHE_E_PARAM;
+}
+int tfhe_file_read(const char *path, tfhe_file_header *hdr_out, uint32_t *words, uint64_t capacity) {
+    if (!path || !hdr_out) return TFHE_E_PARAM;
+    FILE *f = fopen(path, "rb");
+    if (!f) return TFHE_E_PARAM;
+    tfhe_file_header h;
+    int rc = TFHE_OK;
+    if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "TFHEB200", 8) != 0 || h.version != 1) rc = TFHE_E_PARAM;
+    if (rc == TFHE_OK) {
+        *hdr_out = h;
+        if (words) {
+            if (h.count > capacity) rc = TFHE_E_PARAM;
+            else if (h.count && fread(words, 4, h.count, f) != h.count) rc = TFHE_E_PARAM;
+        }
+    }
+    fclose(f);
+    return rc;
 }
 
 }  // extern "C"

@@ -604,6 +604,108 @@ int tfhe_gate_batch(tfhe_ctx *ctx, const tfhe_bk *bk, int gate, const uint32_t *
     return tfhe_gates_batch(ctx, bk, g.data(), ct0, ct1, batch, out);
 }
 
+// ------------------------------------------------------------------ compositions
+int tfhe_bootstrap_batch_ks_first(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, const uint32_t *luts, size_t n_luts,
+                                  const uint32_t *lut_idx, size_t batch, uint32_t *lwe_out) {
+    int rc = check_bk(ctx, bk);
+    if (rc) return rc;
+    if (!lwe_in || !luts || !lwe_out || n_luts == 0) return fail(ctx, TFHE_E_PARAM, "null argument");
+    if (batch == 0) return TFHE_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    const size_t kN1 = ctx->k() * ctx->N() + 1, io_bytes = batch * kN1 * 4;
+    const void *d_in, *d_luts, *d_idx = nullptr;
+    void *d_out;
+    if ((rc = stage_in(ctx, lwe_in, io_bytes, ctx->in0, &d_in))) return rc;
+    if ((rc = stage_in(ctx, luts, n_luts * ctx->N() * 4, ctx->luts, &d_luts))) return rc;
+    if (lut_idx && (rc = stage_in(ctx, lut_idx, batch * 4, ctx->lutidx, &d_idx))) return rc;
+    if ((rc = stage_out(ctx, lwe_out, io_bytes, ctx->out, &d_out))) return rc;
+    // key_switching.rs:63-103 first: [B][kN+1] -> [B][n+1]
+    CU(ctx->in2.ensure(batch * (ctx->n() + 1) * 4));
+    CU(ctx->glwe.ensure(batch * ctx->glwe_words() * 4));
+    CU(cudaMemsetAsync(ctx->d_err, 0, 4, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+    if ((rc = run_key_switch(ctx, bk, (const uint32_t *)d_in, 1, batch, (uint32_t *)ctx->in2.p))) return rc;
+    CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+    // bootstrapping.rs:67-105 blind rotation, then :122-156 sample extraction
+    PbsArgs a = {};
+    a.bsk_ntt = bk->d_bsk_ntt;
+    a.tw[0] = ctx->tw[0]; a.tw[1] = ctx->tw[1];
+    a.prime[0] = ctx->prime[0]; a.prime[1] = ctx->prime[1];
+    a.lwe_in = (const uint32_t *)ctx->in2.p; a.luts = (const uint32_t *)d_luts; a.lut_idx = (const uint32_t *)d_idx;
+    a.glwe_out = (uint32_t *)ctx->glwe.p;
+    a.err_flag = ctx->d_err;
+    a.n = (uint32_t)ctx->n(); a.batch = (uint32_t)batch; a.mode = 0;
+    a.log_p = ctx->p.log_p;
+    a.enc_shift = ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits);
+    if ((rc = launch_pbs(ctx, a, bk))) return rc;
+    const size_t total = batch * kN1;
+    sample_extract_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)ctx->glwe.p, (uint32_t *)d_out, (uint32_t)ctx->k(),
+                                                                                     (int)ctx->p.glwe_poly_degree, (uint32_t)batch);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    // timing slots: [0] = blind rotation + extraction, [1] = key switch (ev[1] closes the rotation interval)
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if ((rc = finish_out(ctx, lwe_out, io_bytes, d_out))) return rc;
+    CU(cudaEventRecord(ctx->ev[4], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float t = 0;
+    CU(cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[1])); ctx->last_ms[0] = t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3])); ctx->last_ms[1] = t;
+    CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4])); ctx->last_ms[2] = t;
+    uint32_t flag = 0;
+    CU(cudaMemcpy(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost));
+    if (flag & 2u) return fail(ctx, TFHE_E_CUDA, "TMA bulk copy wait timed out in the blind-rotation kernel");
+    if (flag) return fail(ctx, TFHE_E_ASSERT, "test vector entry >= 2^log_p (reference assert! glwe.rs:144)");
+    return TFHE_OK;
+}
+
+int tfhe_gate_k_batch(tfhe_ctx *ctx, const tfhe_bk *bk, uint32_t k_inputs, uint32_t truth_table, const uint32_t *const *cts, size_t batch,
+                      uint32_t *out) {
+    int rc = check_bk(ctx, bk);
+    if (rc) return rc;
+    if (!cts || !out) return fail(ctx, TFHE_E_PARAM, "null argument");
+    if (k_inputs < 2 || k_inputs > ctx->p.log_p) return fail(ctx, TFHE_E_PARAM, "k-input gate needs 2 <= k <= log_p");
+    for (uint32_t i = 0; i < k_inputs; i++)
+        if (!cts[i]) return fail(ctx, TFHE_E_PARAM, "null argument");
+    if (batch == 0) return TFHE_OK;
+    const uint32_t pm = 1u << ctx->p.log_p, nf = 1u << k_inputs;
+    const bool negate = truth_table & 1u;   // f(0) = 1: bootstrap 1 - f, then trivial(1) - result
+    std::vector<uint32_t> lut(pm, 0u);
+    for (uint32_t j = 0; j < nf; j++) lut[j] = (((truth_table >> j) & 1u) ^ (negate ? 1u : 0u));
+    const size_t N = ctx->N();
+    std::vector<uint32_t> tv(N);
+    if ((rc = tfhe_test_vector_from_lut(&ctx->p, lut.data(), lut.size(), tv.data()))) return fail(ctx, rc, "test vector construction failed");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    const size_t len = batch * (ctx->n() + 1), io_bytes = len * 4;
+    void *d_out;
+    if ((rc = stage_out(ctx, out, io_bytes, ctx->out, &d_out))) return rc;
+    CU(ctx->in2.ensure(io_bytes));
+    CU(ctx->luts.ensure(N * 4));
+    CU(cudaMemcpyAsync(ctx->luts.p, tv.data(), N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // Horner: acc = c_{k-1}; acc = 2*acc + c_i  (each step is boolean.rs:18's `2*ct1 + ct0`)
+    const void *d_acc;
+    if ((rc = stage_in(ctx, cts[k_inputs - 1], io_bytes, ctx->in1, &d_acc))) return rc;
+    for (int i = (int)k_inputs - 2; i >= 0; i--) {
+        const void *d_ci;
+        if ((rc = stage_in(ctx, cts[i], io_bytes, ctx->in0, &d_ci))) return rc;
+        gate_linear_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)d_ci, (const uint32_t *)d_acc, (uint32_t *)ctx->in2.p, len);
+        CU(cudaGetLastError());
+        ctx->launches++;
+        d_acc = ctx->in2.p;   // in place from the second step on: element-wise, each thread reads before it writes
+    }
+    if ((rc = run_bootstrap(ctx, bk, (const uint32_t *)d_acc, (const uint32_t *)ctx->luts.p, nullptr, batch, (uint32_t *)d_out))) return rc;
+    if (negate) {
+        const uint32_t one = 1u << (ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits));
+        gate_negate_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>((uint32_t *)d_out, nullptr, 1, (uint32_t)ctx->n(), (uint32_t)batch, one);
+        CU(cudaGetLastError());
+        ctx->launches++;
+    }
+    if ((rc = finish_out(ctx, out, io_bytes, d_out))) return rc;
+    return finish_timed(ctx);   // synchronises: the pageable tv vector outlives its async copy
+}
+
 // ------------------------------------------------------------------ sub-operations
 int tfhe_switch_modulus(tfhe_ctx *ctx, const uint32_t *values, size_t len, uint32_t *out) {
     if (!ctx || !values || !out) return TFHE_E_PARAM;
