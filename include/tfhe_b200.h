@@ -115,6 +115,16 @@ int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out);
 /* Copies BSK+KSK (host or device pointers) to the ctx's device and transforms the BSK into the domain of the ctx's
  * arithmetic path (2-prime NTT: kernel K0; or limb-split FFT).  The caller keeps ownership of the inputs. */
 int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe_bk **out);
+/* BMMP variant (notes/BMMP Bootstrapping.md:13-25; the reference holds prose only, so parity with the
+ * Rust crate is UNPINNED): blind rotation unrolled by two with key triples
+ *   bk[3i] = GGSW(s_2i s_2i+1), bk[3i+1] = GGSW(s_2i (1 - s_2i+1)), bk[3i+2] = GGSW(s_2i+1 (1 - s_2i)),
+ *   acc += ExtProd((X^(a+a') - 1) bk[3i] + (X^a - 1) bk[3i+1] + (X^a' - 1) bk[3i+2], acc).
+ * tfhe_keygen_bmmp derives the same secret keys and KSK as tfhe_keygen from the seed; bsk3 = u32[3n/2][(k+1)l][k+1][N].
+ * A key uploaded with tfhe_bk_upload_bmmp is used through the ordinary entry points (tfhe_bootstrap_batch,
+ * tfhe_blind_rotate, tfhe_gate(s)_batch, ...); needs an even n and an FFT-path instantiation. */
+int tfhe_keygen_bmmp(const tfhe_params *p, uint64_t seed, uint32_t *lwe_sk /* n */, uint32_t *glwe_sk /* k*N */,
+                     uint32_t *bsk3, uint32_t *ksk);
+int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk, tfhe_bk **out);
 void tfhe_bk_free(tfhe_bk *bk);
 /* Inspection (parity tests of the one-off key transform): size in bytes of the transformed BSK held on the device,
  * and a copy of it to host memory.  NTT path: u32[n][2][(k+1)l][k+1][N]; FFT path: f64 pairs[n][(k+1)l][2][k+1][N/2]. */

@@ -88,6 +88,8 @@ def lib():
         "orc_key_switch_lwe": (None, [PP, u32p, u32p, u32p]),
         "orc_blind_rotate": (C.c_int, [PP, u32p, u32p, u32p, u32p]),
         "orc_bootstrap": (C.c_int, [PP, u32p, u32p, u32p, u32p, u32p]),
+        "orc_blind_rotate_bmmp": (C.c_int, [PP, u32p, u32p, u32p, u32p]),
+        "orc_bootstrap_bmmp": (C.c_int, [PP, u32p, u32p, u32p, u32p, u32p]),
         "orc_bootstrap_batch": (C.c_int, [PP, u32p, C.c_size_t, u32p, u32p, u32p, u32p, C.c_int]),
         "orc_test_vector_from_lut": (C.c_int, [PP, u32p, C.c_size_t, u32p]),
         "orc_test_vector_identity": (None, [PP, u32p]),
@@ -158,6 +160,21 @@ def blind_rotate(p: OrcParams, lwe_in, bsk, tv):
     if rc != 0:
         raise AssertionError("reference assert!: test vector entry >= 2^log_p (glwe.rs:144)")
     return out.reshape(p.k + 1, p.N)
+
+
+def blind_rotate_bmmp(p: OrcParams, lwe_in, bsk3, tv):
+    """notes/BMMP Bootstrapping.md:13-25 (unrolled by two; no reference code: parity unpinned)."""
+    out = z(p.k + 1, p.N)
+    rc = lib().orc_blind_rotate_bmmp(C.byref(p), np.ascontiguousarray(lwe_in), bsk3, np.ascontiguousarray(tv), out.reshape(-1))
+    assert rc == 0, rc
+    return out
+
+
+def bootstrap_bmmp(p: OrcParams, lwe_in, bsk3, ksk, tv):
+    out = z(p.n + 1)
+    rc = lib().orc_bootstrap_bmmp(C.byref(p), np.ascontiguousarray(lwe_in), bsk3, ksk, np.ascontiguousarray(tv), out)
+    assert rc == 0, rc
+    return out
 
 
 def bootstrap_batch(p: OrcParams, lwe_in, bsk, ksk, tv, nthreads: int):

@@ -275,6 +275,58 @@ done:
     return rc;
 }
 
+/* notes/BMMP Bootstrapping.md:13-25 -- blind rotation unrolled by two (the reference holds NO code for it: this is a
+ * restatement of the note with the crate's own building blocks; parity against the Rust crate is UNPINNED).
+ * Per pair (a, a') = (a~_2i, a~_2i+1) and key triple bk[3i..3i+2]:
+ *   bundle = (X^(a+a') - 1) bk[3i] + (X^a - 1) bk[3i+1] + (X^a' - 1) bk[3i+2]   (3 GGSW scalings by a plaintext polynomial,
+ *            2 GGSW additions; exact wrapping u32 arithmetic on every GGSW polynomial)
+ *   acc    = external_product(bundle, acc) + acc                                (1 GLWE addition)                        */
+int orc_blind_rotate_bmmp(const orc_params *p, const uint32_t *lwe_in, const uint32_t *bsk3, const uint32_t *tv, uint32_t *acc) {
+    size_t N = P_N(p), k = P_K(p), n = p->lwe_dimension, l = p->pbs_levels;
+    size_t glwe_sz = (k + 1) * N, ggsw_sz = (k + 1) * l * glwe_sz, polys = (k + 1) * l * (k + 1);
+    if (n & 1) return -2;
+    uint32_t *approx = (uint32_t *)malloc((n + 1) * sizeof(uint32_t));
+    uint32_t *pt = (uint32_t *)malloc(N * sizeof(uint32_t));
+    uint32_t *vx = (uint32_t *)malloc(glwe_sz * sizeof(uint32_t));
+    uint32_t *bundle = (uint32_t *)malloc(ggsw_sz * sizeof(uint32_t));
+    uint32_t *rot = (uint32_t *)malloc(N * sizeof(uint32_t));
+    uint32_t *prod = (uint32_t *)malloc(glwe_sz * sizeof(uint32_t));
+    int rc = 0;
+    orc_switch_modulus(lwe_in, n + 1, p->log_q, p->glwe_poly_degree + 1, approx);
+    if (orc_glwe_encode_message(p, tv, N, pt) != 0) { rc = -1; goto done; }
+    orc_trivial_encrypt_glwe(p, pt, vx);
+    orc_glwe_mul_monomial(p, vx, -(int64_t)approx[n], acc);
+    for (size_t i = 0; i < n / 2; i++) {
+        const int64_t e[3] = {(int64_t)approx[2 * i] + (int64_t)approx[2 * i + 1], (int64_t)approx[2 * i], (int64_t)approx[2 * i + 1]};
+        memset(bundle, 0, ggsw_sz * sizeof(uint32_t));
+        for (int which = 0; which < 3; which++) {
+            const uint32_t *g = bsk3 + (3 * i + which) * ggsw_sz;
+            for (size_t q = 0; q < polys; q++) {
+                orc_poly_mul_monomial(g + q * N, N, e[which], rot);              /* X^e * poly   (utils.rs:183-207) */
+                for (size_t j = 0; j < N; j++) bundle[q * N + j] += rot[j] - g[q * N + j];
+            }
+        }
+        orc_external_product(p, bundle, acc, prod);                               /* ggsw.rs:132-161 */
+        for (size_t j = 0; j < glwe_sz; j++) acc[j] += prod[j];                   /* glwe.rs:37-41   */
+    }
+done:
+    free(approx); free(pt); free(vx); free(bundle); free(rot); free(prod);
+    return rc;
+}
+int orc_bootstrap_bmmp(const orc_params *p, const uint32_t *lwe_in, const uint32_t *bsk3, const uint32_t *ksk, const uint32_t *tv,
+                       uint32_t *lwe_out) {
+    size_t N = P_N(p), k = P_K(p);
+    uint32_t *acc = (uint32_t *)malloc((k + 1) * N * sizeof(uint32_t));
+    uint32_t *ext = (uint32_t *)malloc((k * N + 1) * sizeof(uint32_t));
+    int rc = orc_blind_rotate_bmmp(p, lwe_in, bsk3, tv, acc);
+    if (rc == 0) {
+        orc_sample_extract(p, acc, 0, ext);
+        orc_key_switch_lwe(p, ext, ksk, lwe_out);
+    }
+    free(acc); free(ext);
+    return rc;
+}
+
 /* bootstrapping.rs:58-120 */
 int orc_bootstrap(const orc_params *p, const uint32_t *lwe_in, const uint32_t *bsk, const uint32_t *ksk,
                   const uint32_t *tv, uint32_t *lwe_out) {

@@ -47,8 +47,16 @@ struct EmuF {
                     for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_T3<K>(R(0, t), t, twC(), b1(0), o);
                 }
     }
+    // BMMP step (notes/BMMP Bootstrapping.md): key = 3 GGSWs [ROWS][3][2][P][M], exponents ex[3]; acc += ExtProd(bundle, acc)
+    void step_bmmp(const cplx *key, const uint32_t *ex) {
+        std::vector<uint32_t> snap(acc);
+        const uint32_t *a = snap.data();
+        run(key, [=](uint32_t p, uint32_t j) { return a[p * K::N + j]; }, 3, ex);
+    }
     template <class DiffFn>
-    void step(const cplx *key, DiffFn diff) {
+    void step(const cplx *key, DiffFn diff) { run(key, diff, 1, nullptr); }
+    template <class DiffFn>
+    void run(const cplx *key, DiffFn diff, int keys, const uint32_t *ex) {
         for (auto &r : regs) zero_acc<K>(r);
         for (int lev = 0; lev < K::L; lev++) {
             for (int s = 0; s < K::P; s++) {   // sub-teams run concurrently on the GPU; any order between barriers is legal
@@ -60,14 +68,20 @@ struct EmuF {
                     phase_xstore<K>(R(s, t), t, b0(s));
                 }
             }
-            for (int p = 0; p < K::P; p++) {
-                const cplx *slot = key + (size_t)key_row_index<K>(p, lev) * 2 * K::P * K::M;
-                for (int s = 0; s < K::P; s++)
-                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
-                        if (p == s) phase_mac<K, true>(R(s, t), t, s, slot, nullptr);
-                        else phase_mac<K, false>(R(s, t), t, s, slot, b0(p));
-                    }
-            }
+            for (int p = 0; p < K::P; p++)
+                for (int which = 0; which < keys; which++) {
+                    const cplx *slot = key + ((size_t)key_row_index<K>(p, lev) * keys + which) * 2 * K::P * K::M;
+                    for (int s = 0; s < K::P; s++)
+                        for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
+                            if (keys == 3) {
+                                if (p == s) phase_mac_bmmp<K, true>(R(s, t), t, s, slot, nullptr, tw.Z.data(), ex[which], bmmp_base<K>(tw.Z.data(), t, ex[which]));
+                                else phase_mac_bmmp<K, false>(R(s, t), t, s, slot, b0(p), tw.Z.data(), ex[which], bmmp_base<K>(tw.Z.data(), t, ex[which]));
+                            } else {
+                                if (p == s) phase_mac<K, true>(R(s, t), t, s, slot, nullptr);
+                                else phase_mac<K, false>(R(s, t), t, s, slot, b0(p));
+                            }
+                        }
+                }
         }
         std::vector<uint32_t> lo((size_t)K::T * 2 * K::E);
         for (int s = 0; s < K::P; s++) {
@@ -116,9 +130,36 @@ int run_step(int mode, const double *key, uint32_t *glwe, uint32_t a, double *ma
     return 0;
 }
 
+// three raw GGSWs -> [ROWS][3][2][P][M]; then one BMMP step on glwe with exponents (a + a', a, a')
+template <class K>
+int run_bmmp(const uint32_t *raw3, uint32_t *glwe, uint32_t a0, uint32_t a1, double *maxfrac) {
+    EmuF<K> e;
+    const size_t per = (size_t)K::ROWS * 2 * K::P * K::M, gg = (size_t)K::ROWS * K::P * K::N;
+    std::vector<cplx> one(per), key(3 * per);
+    for (int which = 0; which < 3; which++) {
+        e.transform_ggsw(raw3 + which * gg, one.data());
+        for (int row = 0; row < K::ROWS; row++)
+            memcpy(&key[((size_t)row * 3 + which) * 2 * K::P * K::M], &one[(size_t)row * 2 * K::P * K::M], sizeof(cplx) * 2 * K::P * K::M);
+    }
+    memcpy(e.acc.data(), glwe, sizeof(uint32_t) * K::P * K::N);
+    const uint32_t ex[3] = {(a0 + a1) & (2u * K::N - 1u), a0, a1};
+    e.step_bmmp(key.data(), ex);
+    memcpy(glwe, e.acc.data(), sizeof(uint32_t) * K::P * K::N);
+    *maxfrac = e.maxfrac;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
+int emu_fft_step_bmmp(int cfg, const uint32_t *raw3, uint32_t *glwe, uint32_t a0, uint32_t a1, double *maxfrac) {
+    switch (cfg) {
+    case 0: return run_bmmp<F_P0>(raw3, glwe, a0, a1, maxfrac);
+    case 1: return run_bmmp<F_P1>(raw3, glwe, a0, a1, maxfrac);
+    case 2: return run_bmmp<F_P2>(raw3, glwe, a0, a1, maxfrac);
+    }
+    return -1;
+}
 int emu_fft_transform_ggsw(int cfg, const uint32_t *raw, double *out) {
     switch (cfg) {
     case 0: return run_transform<F_P0>(raw, out);

@@ -185,3 +185,35 @@ def test_emulated_fft_worst_case_inputs(emu_fft):
         assert emu_fft.emu_fft_step(cfg, 1, key, got, 0, C.byref(mf)) == 0
         assert got.tolist() == exp.tolist()
         assert mf.value < 2.0 ** -10, mf.value
+
+
+@pytest.mark.parametrize("cfg", [0, 1])
+def test_emulated_fft_bmmp_step_bit_exact(emu_fft, cfg):
+    """BMMP step: acc += ExtProd((X^(a+a')-1) G0 + (X^a-1) G1 + (X^a'-1) G2, acc), the monomial factors
+    applied in the transform domain, vs the oracle's exact u32 bundle (oracle/tfhe_oracle.c orc_blind_rotate_bmmp)."""
+    emu_fft.emu_fft_step_bmmp.argtypes = [C.c_int, u32p, u32p, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
+    p = orc.params(**CFGS[cfg])
+    N, k, l = p.N, p.k, p.pbs_levels
+    rng = np.random.default_rng(300 + cfg)
+    r32 = lambda *s: rng.integers(0, 1 << 32, s, dtype=np.uint64).astype(np.uint32)
+    O = orc.lib()
+    gg = (k + 1) * l * (k + 1) * N
+    raw3 = r32(3 * gg)
+    mf = C.c_double(0.0)
+    for a0, a1 in ((1, 2), (N - 1, N + 7), (0, 5), (2 * N - 1, 2 * N - 1), (N, N), (0, 0)):
+        acc = r32(k + 1, N)
+        e = (a0 + a1, a0, a1)
+        bundle = np.zeros(gg, dtype=np.uint32)
+        rot = orc.z(N)
+        for which in range(3):
+            g = raw3[which * gg:(which + 1) * gg]
+            for q in range(gg // N):
+                O.orc_poly_mul_monomial(g[q * N:(q + 1) * N], N, e[which], rot)
+                bundle[q * N:(q + 1) * N] += rot - g[q * N:(q + 1) * N]
+        prod = orc.z((k + 1) * N)
+        O.orc_external_product(C.byref(p), bundle, acc.reshape(-1), prod)
+        exp = (acc.reshape(-1) + prod).astype(np.uint32)
+        got = acc.copy().reshape(-1)
+        assert emu_fft.emu_fft_step_bmmp(cfg, raw3, got, a0, a1, C.byref(mf)) == 0
+        assert got.tolist() == exp.tolist(), (a0, a1)
+        assert mf.value < 2.0 ** -8, mf.value

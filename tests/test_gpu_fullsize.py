@@ -146,3 +146,24 @@ def test_p0_layered_circuit_and_gate_batch():
     for op in (T.NAND, T.AND, T.XOR):
         b = int(np.argmax(ops == op))
         assert np.array_equal(out[b], orc.gate(e.o, int(op), wires[i0[b]], wires[i1[b]], e.bsk, e.ksk))
+
+
+def test_p1_bmmp_batch_full_n():
+    """BASELINE config #5 (single-GPU slice): BMMP-style unrolled bootstrapping with key switching at n = 630."""
+    p = T.TfheParams.preset("P1")
+    lwe_sk, glwe_sk, bsk3, ksk = T.bootstrapping_key_gen_bmmp(p, 0xB200)
+    ctx = T.Context(p, 0, path=T.PATH_FFT)
+    ctx.set_fft_check(True)
+    bk = ctx.upload_key_bmmp(bsk3, ksk)
+    pm = 1 << p.log_p
+    nu, B = 64, 1024
+    uniq = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(nu)])
+    cts = np.tile(uniq, (B // nu, 1))
+    tv = T.construct_identity_test_vector(p)
+    out = ctx.bootstrap(bk, cts, tv)
+    for i in range(0, B, 17):
+        assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, out[i])) == (i % nu) % pm, i
+    assert np.array_equal(out[:nu], out[nu:2 * nu])                      # batch invariance
+    assert 0.0 < ctx.fft_rounding_margin() < 2.0 ** -6
+    o = orc.params(**{f: getattr(p, f) for f in FIELDS})
+    assert np.array_equal(out[3], orc.bootstrap_bmmp(o, cts[3], bsk3, ksk, tv))   # one full-n oracle run

@@ -276,3 +276,37 @@ def test_k_input_gates_notes_boolean_gates_md(preset, n):
             assert e.dec(out[j]) == (tt >> j) & 1, (k, hex(tt), j)
     with pytest.raises(T.TfheError):
         e.ctx.gate_k(e.bk, 0b10, [cts[0]] * 5)      # k > log_p
+
+
+def test_bmmp_variant_bit_exact_vs_oracle():
+    """SURVEY 8(f) N1 / BASELINE config #5: unrolled-by-two blind rotation with key triples, through the ordinary entry
+    points, bit for bit against oracle/tfhe_oracle.c orc_blind_rotate_bmmp (the reference has prose only: parity with
+    the Rust crate is unpinned; this pins the kernel against the note's restatement)."""
+    n = 6
+    p = T.TfheParams.preset("P1", lwe_dimension=n)
+    o = oparams(p)
+    lwe_sk, glwe_sk, bsk3, ksk = T.bootstrapping_key_gen_bmmp(p, 0xB200)
+    ctx = T.Context(p, 0, path=T.PATH_FFT)
+    ctx.set_fft_check(True)
+    bk = ctx.upload_key_bmmp(bsk3, ksk)
+    rng = np.random.default_rng(11)
+    pm = 1 << p.log_p
+    B = 7                                            # 3 + 3 + 1: a partially filled CTA too
+    cts = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(B)])
+    cts[5] = r32(rng, n + 1)
+    cts[6, :n] = 0                                   # all pairs (0, 0): every step skipped
+    cts[4, 0] = 0                                    # a = 0, a' != 0 in the first pair
+    tvs = np.stack([T.construct_identity_test_vector(p), rng.integers(0, pm, p.N).astype(np.uint32)])
+    idx = np.array([b % 2 for b in range(B)], dtype=np.uint32)
+    acc = ctx.blind_rotate(bk, cts, tvs, idx)
+    out = ctx.bootstrap(bk, cts, tvs, idx)
+    for b in range(B):
+        assert np.array_equal(acc[b], orc.blind_rotate_bmmp(o, cts[b], bsk3, tvs[idx[b]])), b
+        assert np.array_equal(out[b], orc.bootstrap_bmmp(o, cts[b], bsk3, ksk, tvs[idx[b]])), b
+    for b in (0, 2):
+        assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, out[b])) == b % pm
+    assert 0.0 < ctx.fft_rounding_margin() < 2.0 ** -6
+    with pytest.raises(T.TfheError):                 # a BMMP key holds products of key bits: no single external products
+        ctx.external_product(bk, np.array([0], dtype=np.uint32), np.zeros((1, 2, 1024), dtype=np.uint32))
+    with pytest.raises(T.TfheError):                 # odd n
+        T.bootstrapping_key_gen_bmmp(T.TfheParams.preset("P1", lwe_dimension=5), 1)

@@ -255,3 +255,23 @@ def test_keygen_layout_ggsw_rs_83(keys_test_cfg):
             if poly == k:
                 err = (int(body[0]) - factor) & M32
                 assert err < (1 << 12) or err > M32 - (1 << 12)
+
+
+def test_bmmp_unrolled_blind_rotation_decrypts():
+    """SURVEY 8(f) N1 (notes/BMMP Bootstrapping.md; no reference code, parity UNPINNED): the oracle's restatement of the
+    unrolled-by-two blind rotation, on key triples from the host keygen, bootstraps every message correctly."""
+    import tfhe_research_b200 as T
+    for preset, n in (("P0", 4), ("P1", 6)):
+        p = T.TfheParams.preset(preset, lwe_dimension=n)
+        o = orc.params(**{f: getattr(p, f) for f, _ in T.TfheParams._fields_})
+        lwe_sk, glwe_sk, bsk3, ksk = T.bootstrapping_key_gen_bmmp(p, 0xB200)
+        lwe_sk2, glwe_sk2, bsk, ksk2 = T.bootstrapping_key_gen(p, 0xB200)
+        assert np.array_equal(lwe_sk, lwe_sk2) and np.array_equal(glwe_sk, glwe_sk2) and np.array_equal(ksk, ksk2)
+        assert bsk3.size == 3 * (n // 2) * p.ggsw_words
+        tv = T.construct_identity_test_vector(p)
+        for m in range(1 << p.log_p):
+            ct = T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, m), 9, m)
+            out = orc.bootstrap_bmmp(o, ct, bsk3, ksk, tv)
+            assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, out)) == m, (preset, m)
+            # same ciphertext through the standard chain decrypts to the same message (different key material, different bits)
+            assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, orc.bootstrap(o, ct, bsk, ksk, tv))) == m

@@ -106,7 +106,8 @@ def lib():
         "tfhe_lwe_encode": [PP, C.c_uint32, C.POINTER(C.c_uint32)], "tfhe_lwe_decode": [PP, C.c_uint32, C.POINTER(C.c_uint32)],
         "tfhe_lwe_encrypt": [PP, VP, SZ, C.c_uint32, C.c_uint64, C.c_uint64, VP],
         "tfhe_lwe_decrypt": [VP, SZ, VP, C.POINTER(C.c_uint32)],
-        "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP],
+        "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP], "tfhe_keygen_bmmp": [PP, C.c_uint64, VP, VP, VP, VP],
+        "tfhe_bk_upload_bmmp": [VP, VP, VP, C.POINTER(VP)],
         "tfhe_ctx_create": [PP, C.c_int, C.POINTER(VP)], "tfhe_ctx_set_stream": [VP, VP],
         "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_fft_check": [VP, C.c_int],
         "tfhe_fft_rounding_margin": [VP, C.POINTER(C.c_double)],
@@ -147,7 +148,7 @@ EXPORTS = [
     "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
     "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
     "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed", "tfhe_bootstrap_batch_ks_first", "tfhe_gate_k_batch",
-    "tfhe_file_write", "tfhe_file_read",
+    "tfhe_file_write", "tfhe_file_read", "tfhe_keygen_bmmp", "tfhe_bk_upload_bmmp",
 ]
 
 
@@ -253,6 +254,18 @@ def bootstrapping_key_gen(params: TfheParams, seed: int):
     ksk = np.empty(params.ksk_words, dtype=np.uint32)
     _check(lib().tfhe_keygen(C.byref(params), seed, lwe_sk.ctypes.data, glwe_sk.ctypes.data, bsk.ctypes.data, ksk.ctypes.data))
     return lwe_sk, glwe_sk, bsk, ksk
+
+
+def bootstrapping_key_gen_bmmp(params: TfheParams, seed: int):
+    """BMMP key triples (notes/BMMP Bootstrapping.md:21-25): returns (lwe_sk, glwe_sk, bsk3, ksk); same secret keys and
+    KSK as bootstrapping_key_gen(params, seed)."""
+    lwe_sk = np.empty(params.n, dtype=np.uint32)
+    glwe_sk = np.empty(params.k * params.N, dtype=np.uint32)
+    bsk3 = np.empty(3 * (params.n // 2) * params.ggsw_words, dtype=np.uint32)
+    ksk = np.empty(params.ksk_words, dtype=np.uint32)
+    _check(lib().tfhe_keygen_bmmp(C.byref(params), seed, lwe_sk.ctypes.data, glwe_sk.ctypes.data, bsk3.ctypes.data, ksk.ctypes.data),
+           "tfhe_keygen_bmmp (even lwe_dimension required)")
+    return lwe_sk, glwe_sk, bsk3, ksk
 
 
 # ------------------------------------------------------------------ flat wire / on-disk format (include/tfhe_b200.h)
@@ -363,6 +376,13 @@ class Context:
         bsk, ksk = _u32(bsk), _u32(ksk)
         h = C.c_void_p()
         self._ck(lib().tfhe_bk_upload(self._h, _ptr(bsk), _ptr(ksk), C.byref(h)))
+        return BootstrappingKey(self, h)
+
+    def upload_key_bmmp(self, bsk3, ksk) -> BootstrappingKey:
+        """Key triples of the unrolled-by-two blind rotation; use the returned key with bootstrap / gate / blind_rotate."""
+        bsk3, ksk = _u32(bsk3), _u32(ksk)
+        h = C.c_void_p()
+        self._ck(lib().tfhe_bk_upload_bmmp(self._h, _ptr(bsk3), _ptr(ksk), C.byref(h)))
         return BootstrappingKey(self, h)
 
     # -- bootstrapping.rs:58-120, batched

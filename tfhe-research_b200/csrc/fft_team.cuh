@@ -184,6 +184,7 @@ struct TwTablesF {
     cplx twA[kMaxTwA];   // pass A (stages 0..LOGE-1): the same for every thread -> kernel-parameter constant bank
     const cplx *twB;     // [2^LOGE (hA)][NB_TW]
     const cplx *twC;     // [NC_TW][T]  (consecutive lanes read consecutive 16 bytes)
+    const cplx *ztab;    // [2N] zeta^m, zeta = exp(2 pi i / 2N): monomial factors of the BMMP variant
 };
 
 // Work split of one ciphertext (one "team"): P = k+1 SUB-TEAMS of T threads.  Sub-team s owns polynomial s of the GLWE
@@ -325,6 +326,49 @@ TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot
         r.acc[1][e].re = fma_d(-xv.im, b.im, fma_d(xv.re, b.re, r.acc[1][e].re));
         r.acc[1][e].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e].im));
     }
+}
+// bit reversal of the low `bits` bits
+TFHE_HD uint32_t brv_bits(uint32_t x, int bits) {
+#if defined(__CUDA_ARCH__)
+    return __brev(x) >> (32 - bits);
+#else
+    return brv_c(x, bits);
+#endif
+}
+// BMMP variant (notes/BMMP Bootstrapping.md:13-25): multiply-accumulate against (X^ex - 1) * G.  In the transform
+// domain the plaintext polynomial X^ex - 1 is a pointwise factor: spectral position j holds the evaluation at
+// X_j = zeta^(1 + 4 brv(j)) (fft_team.cuh header), so the factor is zeta^((1 + 4 brv(j)) ex mod 2N) - 1, read from ztab.
+// Result bits are unchanged (the factor only adds a relative error of a few ulp to a product that is rounded to an
+// integer with > 2^5 margin; the exact statement is acc += sum_k (X^e_k - 1) ExtProd(bk_k, acc) mod 2^32).
+// The exponent splits as (1 + 4 brv(j)) ex = c_t ex + (brv_LOGE(e) << (LOGT+2)) ex with c_t = 1 + 4 brv_LOGT(t): one
+// per-thread table entry (bmmp_base, fetched once per step and key) times an entry whose address is the same for every
+// thread (a broadcast load) -- no per-element gathers.
+template <class K>
+TFHE_HD cplx bmmp_base(const cplx *ztab, uint32_t t, uint32_t ex) {
+    using C = typename K::F;
+    return ztab[((1u + 4u * brv_bits(t, C::LOGT)) * ex) & (2u * K::N - 1u)];
+}
+template <class K, bool OWN>
+TFHE_HD void phase_mac_bmmp(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot, const cplx *xbuf, const cplx *ztab, uint32_t ex,
+                            const cplx base) {
+    using C = typename K::F;
+    const cplx *g0 = slot + col * K::M + t, *g1 = g0 + K::P * K::M;
+    static_for<0, K::E>([&](auto ei) {
+        constexpr int e = decltype(ei)::value;
+        constexpr uint32_t step = brv_c((uint32_t)e, C::LOGE) << (C::LOGT + 2);
+        const cplx u = ztab[(step * ex) & (2u * K::N - 1u)];
+        const double fr = add_d(fma_d(-base.im, u.im, mul_d(base.re, u.re)), -1.0);   // Re(base * u) - 1
+        const double fi = fma_d(base.im, u.re, mul_d(base.re, u.im));
+        const cplx xs = OWN ? r.x[e] : xbuf[e * K::T + t];
+        cplx xv;
+        xv.re = fma_d(-xs.im, fi, mul_d(xs.re, fr));
+        xv.im = fma_d(xs.im, fr, mul_d(xs.re, fi));
+        const cplx a = g0[e * K::T], b = g1[e * K::T];
+        r.acc[0][e].re = fma_d(-xv.im, a.im, fma_d(xv.re, a.re, r.acc[0][e].re));
+        r.acc[0][e].im = fma_d(xv.im, a.re, fma_d(xv.re, a.im, r.acc[0][e].im));
+        r.acc[1][e].re = fma_d(-xv.im, b.im, fma_d(xv.re, b.re, r.acc[1][e].re));
+        r.acc[1][e].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e].im));
+    });
 }
 // I1: accumulator of limb LIMB -> inverse pass C -> buf0;  I2: pass B;  I3: pass A, result z in r.x (layout A)
 template <class K, int LIMB>

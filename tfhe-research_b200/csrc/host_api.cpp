@@ -94,6 +94,49 @@ static void encrypt_lwe_zero(const uint32_t *sk, size_t n, double std_dev, Rng &
     ct[n] = a_s + error;
 }
 
+// ggsw.rs:76-130: GGSW encryption of the plaintext m (a small integer): (k+1)*l GLWE encryptions of zero, plus
+// m * B^(l_full - (lev+1)) on coefficient 0 of polynomial `poly` of row poly*l + lev (ggsw.rs:96-103)
+static void encrypt_ggsw(const tfhe_params &p, const uint32_t *glwe_sk, uint32_t m, Rng &r, uint32_t *g) {
+    const size_t N = (size_t)1 << p.glwe_poly_degree, k = p.glwe_dimension, l = p.pbs_levels, glwe_sz = (k + 1) * N;
+    const uint32_t lq = p.log_q / p.pbs_log_base;
+    for (size_t poly = 0; poly < k + 1; poly++)
+        for (size_t lev = 0; lev < l; lev++) {
+            uint32_t *row = g + (poly * l + lev) * glwe_sz;
+            encrypt_glwe_zero(p, glwe_sk, r, row);
+            if (m != 0) row[poly * N] += m * (1u << (p.pbs_log_base * (lq - (lev + 1))));
+        }
+}
+static unsigned keygen_threads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return hw ? (hw > 32 ? 32 : hw) : 4;
+}
+template <class F>
+static void parallel_for(size_t count, F f) {
+    std::atomic<size_t> next{0};
+    auto work = [&]() { for (size_t i; (i = next.fetch_add(1)) < count;) f(i); };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < keygen_threads(); t++) th.emplace_back(work);
+    for (auto &t : th) t.join();
+}
+static void gen_secret_keys(const tfhe_params &p, uint64_t seed, uint32_t *lwe_sk, uint32_t *glwe_sk) {
+    const size_t N = (size_t)1 << p.glwe_poly_degree;
+    { Rng r(seed, 3, 0); r.binary(lwe_sk, p.lwe_dimension); }            // lwe.rs:54-58
+    { Rng r(seed, 4, 0); r.binary(glwe_sk, p.glwe_dimension * N); }      // glwe.rs:177-181
+}
+// bootstrapping.rs:41-51 + key_switching.rs:20-60: KSK from the flattened GLWE key to the LWE key
+static void gen_ksk(const tfhe_params &p, uint64_t seed, const uint32_t *lwe_sk, const uint32_t *glwe_sk, uint32_t *ksk) {
+    const size_t N = (size_t)1 << p.glwe_poly_degree, n = p.lwe_dimension, from_n = p.glwe_dimension * N, lks = p.ks_levels;
+    const uint32_t lfull = p.log_q / p.ks_log_base;
+    parallel_for(from_n, [&](size_t s) {
+        Rng r(seed, 2, s);
+        for (size_t lev = 0; lev < lks; lev++) {
+            uint32_t *row = ksk + (s * lks + lev) * (n + 1);
+            encrypt_lwe_zero(lwe_sk, n, p.lwe_std_dev, r, row);
+            row[n] += (1u << (p.ks_log_base * (lfull - (lev + 1)))) * glwe_sk[s];  // key_switching.rs:41-48
+        }
+    });
+}
+
 }  // namespace tfhe_host
 
 using namespace tfhe_host;
@@ -222,51 +265,35 @@ int tfhe_keygen(const tfhe_params *pp, uint64_t seed, uint32_t *lwe_sk, uint32_t
     const tfhe_params p = *pp;
     if (p.log_q != 32 || p.pbs_log_base == 0 || p.ks_log_base == 0) return TFHE_E_PARAM;
     const size_t N = (size_t)1 << p.glwe_poly_degree, k = p.glwe_dimension, n = p.lwe_dimension, l = p.pbs_levels;
-    const size_t glwe_sz = (k + 1) * N, ggsw_sz = (k + 1) * l * glwe_sz;
-    { Rng r(seed, 3, 0); r.binary(lwe_sk, n); }        // lwe.rs:54-58
-    { Rng r(seed, 4, 0); r.binary(glwe_sk, k * N); }   // glwe.rs:177-181
-    const unsigned hw = std::thread::hardware_concurrency();
-    const unsigned nth = hw ? (hw > 32 ? 32 : hw) : 4;
-    // bootstrapping.rs:32-38: GGSW(s_i) for every LWE secret bit (ggsw.rs:76-130)
-    {
-        std::atomic<size_t> next{0};
-        auto work = [&]() {
-            const uint32_t lq = p.log_q / p.pbs_log_base;
-            for (size_t i; (i = next.fetch_add(1)) < n;) {
-                Rng r(seed, 1, i);
-                const uint32_t m = lwe_sk[i];
-                uint32_t *g = bsk + i * ggsw_sz;
-                for (size_t poly = 0; poly < k + 1; poly++)
-                    for (size_t lev = 0; lev < l; lev++) {
-                        uint32_t *row = g + (poly * l + lev) * glwe_sz;
-                        encrypt_glwe_zero(p, glwe_sk, r, row);
-                        if (m != 0) row[poly * N] += m * (1u << (p.pbs_log_base * (lq - (lev + 1))));  // ggsw.rs:96-103
-                    }
-            }
-        };
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nth; t++) th.emplace_back(work);
-        for (auto &t : th) t.join();
-    }
-    // bootstrapping.rs:41-51 + key_switching.rs:20-60: KSK from the flattened GLWE key to the LWE key
-    {
-        const size_t from_n = k * N, lks = p.ks_levels;
-        const uint32_t lfull = p.log_q / p.ks_log_base;
-        std::atomic<size_t> next{0};
-        auto work = [&]() {
-            for (size_t s; (s = next.fetch_add(1)) < from_n;) {
-                Rng r(seed, 2, s);
-                for (size_t lev = 0; lev < lks; lev++) {
-                    uint32_t *row = ksk + (s * lks + lev) * (n + 1);
-                    encrypt_lwe_zero(lwe_sk, n, p.lwe_std_dev, r, row);
-                    row[n] += (1u << (p.ks_log_base * (lfull - (lev + 1)))) * glwe_sk[s];  // key_switching.rs:41-48
-                }
-            }
-        };
-        std::vector<std::thread> th;
-        for (unsigned t = 0; t < nth; t++) th.emplace_back(work);
-        for (auto &t : th) t.join();
-    }
+    const size_t ggsw_sz = (k + 1) * l * (k + 1) * N;
+    gen_secret_keys(p, seed, lwe_sk, glwe_sk);
+    // bootstrapping.rs:32-38: GGSW(s_i) for every LWE secret bit
+    parallel_for(n, [&](size_t i) {
+        Rng r(seed, 1, i);
+        encrypt_ggsw(p, glwe_sk, lwe_sk[i], r, bsk + i * ggsw_sz);
+    });
+    gen_ksk(p, seed, lwe_sk, glwe_sk, ksk);
+    return TFHE_OK;
+}
+
+// notes/BMMP Bootstrapping.md:21-25: the unrolled-by-2 bootstrapping key, 3 GGSWs per pair of LWE secret bits:
+//   bk[3i] = GGSW(s_2i * s_2i+1), bk[3i+1] = GGSW(s_2i * (1 - s_2i+1)), bk[3i+2] = GGSW(s_2i+1 * (1 - s_2i)).
+// Secret keys and KSK are the ones tfhe_keygen derives from the same seed.
+int tfhe_keygen_bmmp(const tfhe_params *pp, uint64_t seed, uint32_t *lwe_sk, uint32_t *glwe_sk, uint32_t *bsk3, uint32_t *ksk) {
+    if (!pp || !lwe_sk || !glwe_sk || !bsk3 || !ksk) return TFHE_E_PARAM;
+    const tfhe_params p = *pp;
+    if (p.log_q != 32 || p.pbs_log_base == 0 || p.ks_log_base == 0 || (p.lwe_dimension & 1u)) return TFHE_E_PARAM;
+    const size_t N = (size_t)1 << p.glwe_poly_degree, k = p.glwe_dimension, n = p.lwe_dimension, l = p.pbs_levels;
+    const size_t ggsw_sz = (k + 1) * l * (k + 1) * N;
+    gen_secret_keys(p, seed, lwe_sk, glwe_sk);
+    parallel_for(3 * (n / 2), [&](size_t g) {
+        const size_t i = g / 3, which = g % 3;
+        const uint32_t s0 = lwe_sk[2 * i], s1 = lwe_sk[2 * i + 1];
+        const uint32_t m = which == 0 ? s0 * s1 : which == 1 ? s0 * (1u - s1) : s1 * (1u - s0);
+        Rng r(seed, 5, g);
+        encrypt_ggsw(p, glwe_sk, m, r, bsk3 + g * ggsw_sz);
+    });
+    gen_ksk(p, seed, lwe_sk, glwe_sk, ksk);
     return TFHE_OK;
 }
 

@@ -22,11 +22,16 @@ inline cplx fft_twiddle(int logm, int st, uint32_t b) {
 
 struct HostFftTw {
     std::vector<cplx> A, B, C;  // A: [E-1]; B: [2^LOGE][NB_TW]; C: [E-1][T]
+    std::vector<cplx> Z;        // [4M = 2N] zeta^m (BMMP monomial factors)
 };
 inline void build_fft_tables(int logm, int loge, HostFftTw &out) {
     const int qb = logm - 2 * loge;
     const int T = 1 << (logm - loge);
-    out.A.clear(); out.B.clear(); out.C.clear();
+    out.A.clear(); out.B.clear(); out.C.clear(); out.Z.clear();
+    for (uint64_t m = 0; m < (4ull << logm); m++) {
+        const long double ang = 2.0L * 3.14159265358979323846264338327950288L * (long double)m / (long double)(4ull << logm);
+        out.Z.push_back(m == 0 ? cplx{1.0, 0.0} : cplx{(double)cosl(ang), (double)sinl(ang)});
+    }
     for (int u = 0; u < loge; u++)
         for (uint32_t m = 0; m < (1u << u); m++) out.A.push_back(fft_twiddle(logm, u, m));
     for (uint32_t hA = 0; hA < (1u << loge); hA++)

@@ -57,7 +57,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <class K>
+// BMMP = true: blind rotation unrolled by two (notes/BMMP Bootstrapping.md): n/2 steps, each consumes the three GGSWs of
+// a key triple (3 slots per row), decomposes acc itself and adds ExtProd(bundle, acc); blind rotation mode only.
+template <class K, bool BMMP = false>
 __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_constant__ FftArgs a) {
     using C = typename K::F;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -73,8 +75,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     const uint32_t base = a.batch / gridDim.x, rem = a.batch % gridDim.x;
     const uint32_t ct0 = single ? blockIdx.x : blockIdx.x * base + min(blockIdx.x, rem);
     const uint32_t active = single ? 1u : base + (blockIdx.x < rem ? 1u : 0u);
-    const uint32_t n_steps = single ? 1u : a.n;
-    const uint32_t total_slots = n_steps * K::SLOTS_PER_STEP;
+    constexpr uint32_t KEYS = BMMP ? 3u : 1u;                 // GGSWs per step
+    constexpr uint32_t STEP_SLOTS = K::SLOTS_PER_STEP * KEYS;
+    const uint32_t n_steps = single ? 1u : (BMMP ? a.n / 2u : a.n);
+    const uint32_t total_slots = n_steps * STEP_SLOTS;
 
     if (tid == 0) {
         for (int s = 0; s < K::NSLOT; s++) {
@@ -164,11 +168,20 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     auto diff = [&](uint32_t pp, uint32_t j, uint32_t rot) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - sbase[pp * K::N + j]; };
 #pragma unroll 1
     for (uint32_t i = 0; i < n_steps; i++) {
-        const uint32_t rot = single ? 0u : at[i];
-        if (!single && rot == 0) {
-            // diff == 0 => external product == 0 exactly: consume this step's slots without using them
+        const uint32_t rot = single ? 0u : (BMMP ? at[2 * i] : at[i]);
+        const uint32_t rot1 = BMMP ? at[2 * i + 1] : 0u;
+        // monomial exponents of the BMMP bundle: X^(a+a') - 1, X^a - 1, X^a' - 1
+        const uint32_t ex0 = (rot + rot1) & (2u * K::N - 1u);
+        cplx zb[3] = {};   // per-thread part of the three monomial factors of this step
+        if constexpr (BMMP) {
+            zb[0] = bmmp_base<K>(a.tw.ztab, t, ex0);
+            zb[1] = bmmp_base<K>(a.tw.ztab, t, rot);
+            zb[2] = bmmp_base<K>(a.tw.ztab, t, rot1);
+        }
+        if (!single && rot == 0 && rot1 == 0) {
+            // diff == 0 (bundle == 0) => external product == 0 exactly: consume this step's slots without using them
 #pragma unroll 1
-            for (int s = 0; s < K::SLOTS_PER_STEP; s++, it++) {
+            for (uint32_t s = 0; s < STEP_SLOTS; s++, it++) {
                 if (producer) pump(it + 1);
                 mbar_wait(full + (it % K::NSLOT), (it / K::NSLOT) & 1u, a.err_flag);
                 __syncwarp();
@@ -183,7 +196,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #if (TFHE_FFT_ABLATE & 1)
             phase_F1<K>(R, t, sub, 1u, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return 0u; });
 #else
-            phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
+            if constexpr (BMMP) phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return acc[pp * K::N + j]; });
+            else phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
             team_bar_id(sub_bar, K::T);
             phase_F2<K>(R, jbB, twB, buf0, buf1);
@@ -192,14 +206,22 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its pass-B loads
             team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
 #pragma unroll 1
-            for (uint32_t p = 0; p < (uint32_t)K::P; p++) {
+            for (uint32_t pk = 0; pk < (uint32_t)K::P * KEYS; pk++) {
+                const uint32_t p = pk / KEYS, which = pk % KEYS;
                 const uint32_t s = it % K::NSLOT;
                 if (producer) pump(it + 1);
                 mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
 #if !(TFHE_FFT_ABLATE & 2)
                 const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
-                if (p == sub) phase_mac<K, true>(R, t, sub, slot, nullptr);
-                else phase_mac<K, false>(R, t, sub, slot, reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES));
+                const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
+                if constexpr (BMMP) {
+                    if (p == sub) phase_mac_bmmp<K, true>(R, t, sub, slot, nullptr, a.tw.ztab, which == 0 ? ex0 : which == 1 ? rot : rot1, which == 0 ? zb[0] : which == 1 ? zb[1] : zb[2]);
+                    else phase_mac_bmmp<K, false>(R, t, sub, slot, peer, a.tw.ztab, which == 0 ? ex0 : which == 1 ? rot : rot1, which == 0 ? zb[0] : which == 1 ? zb[1] : zb[2]);
+                } else {
+                    (void)which;
+                    if (p == sub) phase_mac<K, true>(R, t, sub, slot, nullptr);
+                    else phase_mac<K, false>(R, t, sub, slot, peer);
+                }
 #endif
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty + s);
@@ -242,6 +264,7 @@ struct FftTransformArgs {
     TwTablesF tw;
     const uint32_t *raw;
     cplx *out;
+    uint32_t keys_per_step;   // 1: standard key; 3: BMMP key triples, stored [step][row (level-major)][which][limb][P][M]
 };
 template <class K>
 __global__ void __launch_bounds__(2 * K::T) bsk_fft_transform_kernel(const __grid_constant__ FftTransformArgs a) {
@@ -252,7 +275,8 @@ __global__ void __launch_bounds__(2 * K::T) bsk_fft_transform_kernel(const __gri
     const size_t poly = blockIdx.x;  // = (i*ROWS + r)*P + c, r = p*L + lev (ggsw.rs:37-41)
     const size_t ir = poly / K::P, c = poly % K::P, i = ir / K::ROWS, r = ir % K::ROWS;
     const uint32_t *g = a.raw + poly * K::N;
-    const size_t row = i * K::ROWS + key_row_index<K>((uint32_t)(r / K::L), (uint32_t)(r % K::L));   // consumption order
+    const size_t kps = a.keys_per_step, step = i / kps, which = i % kps;
+    const size_t row = (step * K::ROWS + key_row_index<K>((uint32_t)(r / K::L), (uint32_t)(r % K::L))) * kps + which;   // consumption order
     cplx *o = a.out + ((row * 2 + limb) * K::P + c) * K::M;
     FftRegs<K> R;
     phase_T1<K>(R, t, (int)limb, g, a.tw.twA, buf0);

@@ -43,7 +43,7 @@ struct tfhe_ctx {
     int pbs_id = -1, ks_id = -1;
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
-    fft::cplx *d_ftw[2] = {};                // FFT pass-B / pass-C twiddle tables
+    fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
     std::string err;
@@ -67,6 +67,7 @@ struct tfhe_ctx {
 struct tfhe_bk {
     tfhe_ctx *ctx = nullptr;
     int path = TFHE_PATH_NTT;
+    bool bmmp = false;              // key triples of the unrolled-by-two blind rotation (FFT path only)
     uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]                      (TFHE_PATH_NTT)
     fft::cplx *d_bsk_fft = nullptr; // [n][ROWS][2 limbs][P][N/2], scaled 2/N  (TFHE_PATH_FFT)
     uint32_t *d_ksk = nullptr;      // [kN*l_ks][n+1]
@@ -169,7 +170,7 @@ using KF1 = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, false>;   // product
 using KF1C = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true>;   // + records the rounding margin (tests, validation)
 bool fft_available(int pbs_id) { return pbs_id == 1; }
 
-template <class K>
+template <class K, bool BMMP = false>
 int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     fft::FftArgs f = {};
     f.tw = ctx->ftw;
@@ -180,7 +181,7 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     f.n = a.n; f.batch = a.batch; f.mode = a.mode; f.log_p = a.log_p; f.enc_shift = a.enc_shift;
     const size_t smem = (size_t)K::CTS * K::team_bytes((int)a.n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8;
     if (smem > 227 * 1024) return fail(ctx, TFHE_E_PARAM, "lwe_dimension too large for the FFT path's shared-memory layout");
-    auto kern = fft::pbs_fft_kernel<K>;
+    auto kern = fft::pbs_fft_kernel<K, BMMP>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned grid = (unsigned)a.batch;
     if (a.mode == 0) {
@@ -195,9 +196,9 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     return TFHE_OK;
 }
 template <class K>
-int launch_fft_transform_t(tfhe_ctx *ctx, const uint32_t *raw, fft::cplx *out, size_t n) {
+int launch_fft_transform_t(tfhe_ctx *ctx, const uint32_t *raw, fft::cplx *out, size_t n, uint32_t keys_per_step = 1) {
     fft::FftTransformArgs ta;
-    ta.tw = ctx->ftw; ta.raw = raw; ta.out = out;
+    ta.tw = ctx->ftw; ta.raw = raw; ta.out = out; ta.keys_per_step = keys_per_step;
     const size_t smem = (size_t)2 * 2 * K::F::MPAD * 16;
     auto kern = fft::bsk_fft_transform_kernel<K>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -211,6 +212,13 @@ size_t fft_key_bytes(const tfhe_ctx *ctx) {
 }
 
 int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
+    if (bk->bmmp) {
+        if (a.mode != 0) return fail(ctx, TFHE_E_PARAM, "a BMMP key serves blind rotations only (its GGSWs encrypt products of key bits)");
+        switch (ctx->pbs_id) {
+        case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C, true>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1, true>(ctx, a, bk->d_bsk_fft);
+        }
+        return fail(ctx, TFHE_E_PARAM, "no BMMP instantiation for this parameter set");
+    }
     if (bk->path == TFHE_PATH_FFT) {
         switch (ctx->pbs_id) {
         case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
@@ -393,14 +401,15 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         fft::HostFftTw ft;
         fft::build_fft_tables(logm, floge, ft);
         for (size_t i = 0; i < ft.A.size(); i++) ctx->ftw.twA[i] = ft.A[i];
-        const std::vector<fft::cplx> *fsrc[2] = {&ft.B, &ft.C};
-        for (int i = 0; i < 2; i++) {
+        const std::vector<fft::cplx> *fsrc[3] = {&ft.B, &ft.C, &ft.Z};
+        for (int i = 0; i < 3; i++) {
             if (cudaMalloc(&ctx->d_ftw[i], fsrc[i]->size() * sizeof(fft::cplx)) != cudaSuccess) return bail("cudaMalloc");
             if (cudaMemcpy(ctx->d_ftw[i], fsrc[i]->data(), fsrc[i]->size() * sizeof(fft::cplx), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail("cudaMemcpy");
         }
         ctx->ftw.twB = ctx->d_ftw[0];
         ctx->ftw.twC = ctx->d_ftw[1];
+        ctx->ftw.ztab = ctx->d_ftw[2];
         if (cudaMalloc(&ctx->d_margin, 8) != cudaSuccess || cudaMemset(ctx->d_margin, 0, 8) != cudaSuccess) return bail("cudaMalloc");
         ctx->path = TFHE_DEFAULT_PATH;
     }
@@ -422,7 +431,7 @@ void tfhe_ctx_destroy(tfhe_ctx *ctx) {
         for (int i = 0; i < 4; i++)
             if (ctx->d_tw[pr][i]) cudaFree(ctx->d_tw[pr][i]);
     if (ctx->d_err) cudaFree(ctx->d_err);
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < 3; i++)
         if (ctx->d_ftw[i]) cudaFree(ctx->d_ftw[i]);
     if (ctx->d_margin) cudaFree(ctx->d_margin);
     for (auto &e : ctx->ev)
@@ -508,6 +517,43 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     return TFHE_OK;
 }
 
+int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk, tfhe_bk **out) {
+    if (!ctx || !bsk3 || !ksk || !out) return TFHE_E_PARAM;
+    if (!fft_available(ctx->pbs_id)) return fail(ctx, TFHE_E_PARAM, "the BMMP variant runs on the FFT path, which is not instantiated for this parameter set");
+    if (ctx->n() & 1) return fail(ctx, TFHE_E_PARAM, "the BMMP variant needs an even lwe_dimension");
+    CU(cudaSetDevice(ctx->device));
+    const size_t n_ggsw = 3 * (ctx->n() / 2);
+    const size_t bsk_words = n_ggsw * ctx->ggsw_words(), ksk_words = ctx->kd() * (ctx->n() + 1);
+    tfhe_bk *bk = new tfhe_bk();
+    bk->ctx = ctx;
+    bk->path = TFHE_PATH_FFT;
+    bk->bmmp = true;
+    auto cleanup = [&]() { tfhe_bk_free(bk); };
+    cudaError_t e;
+    if ((e = cudaMalloc(&bk->d_bsk_fft, fft_key_bytes(ctx) / ctx->n() * n_ggsw)) != cudaSuccess || (e = cudaMalloc(&bk->d_ksk, ksk_words * 4)) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, TFHE_E_OOM, cudaGetErrorString(e));
+    }
+    uint32_t *d_raw = nullptr;
+    const uint32_t *raw_dev = bsk3;
+    if (!is_device_ptr(bsk3)) {
+        if ((e = cudaMalloc(&d_raw, bsk_words * 4)) != cudaSuccess) { cleanup(); return fail(ctx, TFHE_E_OOM, cudaGetErrorString(e)); }
+        if ((e = cudaMemcpyAsync(d_raw, bsk3, bsk_words * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) {
+            cudaFree(d_raw); cleanup();
+            return fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
+        }
+        raw_dev = d_raw;
+    }
+    e = cudaMemcpyAsync(bk->d_ksk, ksk, ksk_words * 4, is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    int rc = e != cudaSuccess ? fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e)) : launch_fft_transform_t<KF1>(ctx, raw_dev, bk->d_bsk_fft, n_ggsw, 3);
+    cudaError_t es = cudaStreamSynchronize(ctx->stream);
+    if (d_raw) cudaFree(d_raw);
+    if (rc == TFHE_OK && es != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(es));
+    if (rc != TFHE_OK) { cleanup(); return rc; }
+    *out = bk;
+    return TFHE_OK;
+}
+
 void tfhe_bk_free(tfhe_bk *bk) {
     if (!bk) return;
     if (bk->ctx) cudaSetDevice(bk->ctx->device);
@@ -519,6 +565,7 @@ void tfhe_bk_free(tfhe_bk *bk) {
 
 size_t tfhe_bk_transformed_bytes(const tfhe_bk *bk) {
     if (!bk || !bk->ctx) return 0;
+    if (bk->bmmp) return fft_key_bytes(bk->ctx) / bk->ctx->n() * (3 * (bk->ctx->n() / 2));
     return bk->path == TFHE_PATH_FFT ? fft_key_bytes(bk->ctx) : bk->ctx->n() * bk->ctx->ggsw_words() * 2 * 4;
 }
 int tfhe_bk_read_transformed(const tfhe_bk *bk, void *out, size_t bytes) {
