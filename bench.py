@@ -246,9 +246,10 @@ def main():
     P_, l_ = p.k + 1, p.pbs_levels
     M_ = p.N // 2
     # NTT path: 2 primes x 4 bytes per key word, one CTA per ciphertext, 3 CTAs per SM; FFT path: 2 limbs x 16 bytes per
-    # pair of key words, 3 ciphertexts per CTA (one per SM) share each key byte
+    # pair of key words, the 3 (P1) or 4 (P0) ciphertexts of a CTA (one CTA per SM) share each key byte
     bsk_bytes = (p.n * P_ * l_ * 2 * P_ * M_ * 16) if fft_path else 2 * p.bsk_words * 4
-    waves = -(-B // (148 * 3))
+    cts_per_sm = {9: 4, 10: 3}.get(p.glwe_poly_degree, 3) if fft_path else {9: 4, 10: 3, 11: 2}.get(p.glwe_poly_degree, 3)
+    waves = -(-B // (148 * cts_per_sm))
     hbm_alg = bsk_bytes * waves + B * (p.n + 1) * 4 + B * p.glwe_words * 4
     # practical ceiling of this instruction mix: butterflies only, at the measured register-resident
     # Shoup-butterfly rate (IMAD.HI and IMAD.WIDE issue at HALF the plain IMAD rate on B200)

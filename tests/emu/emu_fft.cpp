@@ -21,7 +21,7 @@ struct EmuF {
     HostFftTw tw;
     std::vector<FftRegs<K>> regs;            // [P sub-teams][T]
     std::vector<uint32_t> acc;
-    std::vector<int16_t> stash;              // [P][(L-1)*2E*T]
+    std::vector<typename K::stash_t> stash;  // [P][(L-1)*2E*T]
     std::vector<cplx> buf;                   // [P][2][MPAD]
     double maxfrac = 0.0;
     static constexpr size_t STASH = (K::L > 1 ? K::L - 1 : 1) * 2 * K::E * K::T;

@@ -28,7 +28,7 @@ class Env:
         self.p = T.TfheParams.preset(preset, lwe_dimension=n)
         self.o = oparams(self.p)
         self.lwe_sk, self.glwe_sk, self.bsk, self.ksk = T.bootstrapping_key_gen(self.p, seed)
-        self.ctx = T.Context(self.p, 0, path=T.PATH_FFT if path == "fft" else T.PATH_NTT)
+        self.ctx = T.Context(self.p, 0, path={"fft": T.PATH_FFT, "ntt": T.PATH_NTT}.get(path))   # None: the library's default
         if path == "fft":
             self.ctx.set_fft_check(True)   # also record the distance-to-integer of every rounded value
         self.bk = self.ctx.upload_key(self.bsk, self.ksk)
@@ -50,7 +50,7 @@ def env(preset, n):
     return _envs[key]
 
 
-CASES = [("P0", 4), ("P1", 3), ("P2", 2), ("P1:fft", 3), ("P1:fft", 21)]
+CASES = [("P0:ntt", 4), ("P1:ntt", 3), ("P2", 2), ("P1:fft", 3), ("P1:fft", 21), ("P0:fft", 4), ("P0:fft", 7)]
 
 
 def r32(rng, *shape):
@@ -142,7 +142,7 @@ def test_blind_rotate_extract_keyswitch_bootstrap(preset, n):
         assert np.array_equal(e.ctx.bootstrap(e.bk, cts[:nb], tvs, idx[:nb]), out[:nb]), nb
 
 
-@pytest.mark.parametrize("preset,n", [("P0", 4), ("P1", 3), ("P1:fft", 3)])
+@pytest.mark.parametrize("preset,n", [("P0:ntt", 4), ("P1:ntt", 3), ("P1:fft", 3), ("P0:fft", 4)])
 def test_gates_boolean_rs(preset, n):
     e = env(preset, n)
     fs = [lambda a, b: a & b, lambda a, b: a | b, lambda a, b: a ^ b,
@@ -163,7 +163,7 @@ def test_gates_boolean_rs(preset, n):
 
 
 def test_encode_assert_and_errors():
-    e = env("P0", 4)
+    e = env("P0:ntt", 4)
     bad = np.full(e.p.N, 4, dtype=np.uint32)        # >= 2^log_p: assert! glwe.rs:144
     with pytest.raises(T.TfheError) as ei:
         e.ctx.bootstrap(e.bk, np.zeros((1, 5), dtype=np.uint32), bad)
@@ -223,7 +223,7 @@ def test_negacyclic_mul_utils_rs_155(preset, n):
     assert ei.value.code == T.TFHE_E_PARAM
 
 
-@pytest.mark.parametrize("preset,n", [("P0", 4), ("P1", 3), ("P1:fft", 3)])
+@pytest.mark.parametrize("preset,n", [("P0:ntt", 4), ("P1:ntt", 3), ("P1:fft", 3), ("P0:fft", 4)])
 def test_ks_first_ordering_notes_tfhe_md_365(preset, n):
     """key switch FIRST, then blind rotation + sample extraction (input/output under the kN-dim key)."""
     import ctypes as C

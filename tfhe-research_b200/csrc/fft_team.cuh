@@ -202,7 +202,9 @@ struct FftPbsCfg {
     static constexpr bool CHECK = CHECK_;
     static constexpr int WARPS_PER_SUB = T / 32, TEAM_THREADS = P * T, THREADS = CTS * TEAM_THREADS;
     static_assert(LOGB * L <= 32 && 32 % LOGB == 0, "decomposer must divide log_q (SURVEY 9-B H2)");
-    static_assert(LOGB <= 14, "digits are stashed as int16");
+    // digits of the levels after the first wait in a thread-private stash: int8 when they fit ([-B/2, B], B <= 64)
+    using stash_t = typename std::conditional<(LOGB <= 6), int8_t, int16_t>::type;
+    static_assert(LOGB <= 14, "digits are stashed as int16 at most");
     // exactness: largest limb convolution * 2^9 (error constant incl. safety) must stay below 2^51
     static_assert((double)ROWS * N * (double)(1 << LOGB) * 32768.0 * 512.0 < 2251799813685248.0, "FP64 exactness bound");
     // key stream: one SLOT = one GGSW row, both limbs: [2 limbs][P columns][M] complex in slot order; rows are stored
@@ -212,7 +214,7 @@ struct FftPbsCfg {
     static constexpr size_t GGSW_BYTES = (size_t)SLOTS_PER_STEP * SLOT_BYTES;
     // shared memory per team: acc, then per sub-team {stash, buf0, buf1}, then the mod-switched mask
     static constexpr int TM_ACC = 0;                                   // u32 acc[P][N]
-    static constexpr int STASH_BYTES = ((L > 1 ? (L - 1) : 1) * 2 * E * T * 2 + 15) & ~15;  // int16 [(L-1)*2E][T]
+    static constexpr int STASH_BYTES = ((L > 1 ? (L - 1) : 1) * 2 * E * T * (int)sizeof(stash_t) + 15) & ~15;  // [(L-1)*2E][T]
     static constexpr int SUB_BYTES = STASH_BYTES + 2 * F::MPAD * 16;   // + cplx buf[2][MPAD]
     static constexpr int TM_SUB = TM_ACC + P * N * 4;
     static constexpr int TM_AT = TM_SUB + P * SUB_BYTES;               // u16 at[n+1] (size known at launch)
@@ -248,7 +250,7 @@ TFHE_HD int32_t key_limb(uint32_t g, int limb) {
 // decomposition (decomposer.rs:27-80) of a thread's 2E coefficients is done once per polynomial, at level 0; the
 // other levels' digits wait in a thread-private stash (no barrier: written and read by the same thread).
 template <class K, class DiffFn>
-TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, int16_t *stash, const cplx *twA, cplx *buf0, DiffFn diff) {
+TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, typename K::stash_t *stash, const cplx *twA, cplx *buf0, DiffFn diff) {
     using C = typename K::F;
     if (lev == 0) {
 #pragma unroll
@@ -261,12 +263,12 @@ TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, int16
                 decompose_signed<K::LOGB, K::L>(diff(p, j), d);
                 v[h] = d[0];
 #pragma unroll
-                for (int l = 1; l < K::L; l++) stash[(((l - 1) * 2 * K::E) + 2 * e + h) * K::T + t] = (int16_t)d[l];
+                for (int l = 1; l < K::L; l++) stash[(((l - 1) * 2 * K::E) + 2 * e + h) * K::T + t] = (typename K::stash_t)d[l];
             }
             r.x[e] = cplx{i2d(v[0]), i2d(v[1])};
         }
     } else {
-        const int16_t *s = stash + (size_t)(lev - 1) * 2 * K::E * K::T + t;
+        const typename K::stash_t *s = stash + (size_t)(lev - 1) * 2 * K::E * K::T + t;
 #pragma unroll
         for (int e = 0; e < K::E; e++) r.x[e] = cplx{i2d(s[(2 * e) * K::T]), i2d(s[(2 * e + 1) * K::T])};
     }

@@ -94,10 +94,17 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     uint8_t *tm = smem + team * team_bytes;
     uint32_t *acc = reinterpret_cast<uint32_t *>(tm + K::TM_ACC);
     uint8_t *sb = tm + K::TM_SUB + sub * K::SUB_BYTES;
-    int16_t *stash = reinterpret_cast<int16_t *>(sb);
+    typename K::stash_t *stash = reinterpret_cast<typename K::stash_t *>(sb);
     cplx *buf0 = reinterpret_cast<cplx *>(sb + K::STASH_BYTES), *buf1 = buf0 + C::MPAD;
     uint16_t *at = reinterpret_cast<uint16_t *>(tm + K::TM_AT);
-    const uint32_t team_bar = 1 + team * (K::P + 1), sub_bar = team_bar + 1 + sub;   // named barriers
+    // named barriers: one per team, plus one per sub-team unless a sub-team is a single warp (then __syncwarp)
+    constexpr bool WARP_SUB = K::T == 32;
+    const uint32_t team_bar = 1 + team * (WARP_SUB ? 1 : K::P + 1), sub_bar = team_bar + 1 + sub;
+    static_assert(K::CTS * (WARP_SUB ? 1 : K::P + 1) <= 15, "named barrier ids");
+    auto sub_sync = [&]() {
+        if constexpr (WARP_SUB) __syncwarp();
+        else team_bar_id(sub_bar, K::T);
+    };
     const uint32_t jbB = jbase_B<C>(t);
     const cplx *twB = a.tw.twB + (t >> C::QB) * C::NB_TW;
     const cplx *twC = a.tw.twC;
@@ -199,9 +206,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             if constexpr (BMMP) phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return acc[pp * K::N + j]; });
             else phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
-            team_bar_id(sub_bar, K::T);
+            sub_sync();
             phase_F2<K>(R, jbB, twB, buf0, buf1);
-            team_bar_id(sub_bar, K::T);
+            sub_sync();
             phase_F3<K>(R, t, twC, buf1);
             phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its pass-B loads
             team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
@@ -233,20 +240,20 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         // inverse transforms of this sub-team's column: low-limb product, then high-limb product, combined in registers
         uint32_t lo[2 * K::E];
         phase_I1<K, 0>(R, t, twC, buf0);
-        team_bar_id(sub_bar, K::T);
+        sub_sync();
         phase_I2<K>(R, jbB, twB, buf0, buf1);
         if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
-        team_bar_id(sub_bar, K::T);
+        sub_sync();
         phase_I3<K>(R, t, a.tw.twA, buf1);
         phase_round_lo<K>(R, lo, maxfrac);
         phase_I1<K, 1>(R, t, twC, buf0);
-        team_bar_id(sub_bar, K::T);
+        sub_sync();
         phase_I2<K>(R, jbB, twB, buf0, buf1);
-        team_bar_id(sub_bar, K::T);
+        sub_sync();
         phase_I3<K>(R, t, a.tw.twA, buf1);
         phase_round_hi<K>(R, t, lo, acc + sub * K::N, maxfrac);
 #endif
-        team_bar_id(sub_bar, K::T);   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
+        sub_sync();   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
     }
     uint32_t *out = a.glwe_out + ((size_t)ct * K::P + sub) * K::N;
     for (uint32_t idx = t; idx < (uint32_t)K::N; idx += K::T) out[idx] = acc[sub * K::N + idx];

@@ -168,7 +168,12 @@ int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
 #endif
 using KF1 = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, false>;   // production: a-priori exactness bound only
 using KF1C = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true>;   // + records the rounding margin (tests, validation)
-bool fft_available(int pbs_id) { return pbs_id == 1; }
+#ifndef TFHE_FFT_CTS_P0
+#define TFHE_FFT_CTS_P0 4
+#endif
+using KF0 = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, false>;    // reference defaults (lib.rs:101-123)
+using KF0C = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, true>;
+bool fft_available(int pbs_id) { return pbs_id == 0 || pbs_id == 1; }
 
 template <class K, bool BMMP = false>
 int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
@@ -207,6 +212,13 @@ int launch_fft_transform_t(tfhe_ctx *ctx, const uint32_t *raw, fft::cplx *out, s
     ctx->launches++;
     return TFHE_OK;
 }
+int launch_fft_transform(tfhe_ctx *ctx, const uint32_t *raw, fft::cplx *out, size_t n_ggsw, uint32_t keys_per_step) {
+    switch (ctx->pbs_id) {
+    case 0: return launch_fft_transform_t<KF0>(ctx, raw, out, n_ggsw, keys_per_step);
+    case 1: return launch_fft_transform_t<KF1>(ctx, raw, out, n_ggsw, keys_per_step);
+    }
+    return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
+}
 size_t fft_key_bytes(const tfhe_ctx *ctx) {
     return ctx->n() * (ctx->k() + 1) * ctx->p.pbs_levels * 2 * (ctx->k() + 1) * (ctx->N() / 2) * sizeof(fft::cplx);
 }
@@ -215,12 +227,14 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
     if (bk->bmmp) {
         if (a.mode != 0) return fail(ctx, TFHE_E_PARAM, "a BMMP key serves blind rotations only (its GGSWs encrypt products of key bits)");
         switch (ctx->pbs_id) {
+        case 0: return ctx->fft_check ? launch_pbs_fft_t<KF0C, true>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0, true>(ctx, a, bk->d_bsk_fft);
         case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C, true>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1, true>(ctx, a, bk->d_bsk_fft);
         }
         return fail(ctx, TFHE_E_PARAM, "no BMMP instantiation for this parameter set");
     }
     if (bk->path == TFHE_PATH_FFT) {
         switch (ctx->pbs_id) {
+        case 0: return ctx->fft_check ? launch_pbs_fft_t<KF0C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0>(ctx, a, bk->d_bsk_fft);
         case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
         }
         return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
@@ -507,7 +521,7 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     e = cudaMemcpyAsync(bk->d_ksk, ksk, ksk_words * 4, is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
     int rc;
     if (e != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
-    else if (bk->path == TFHE_PATH_FFT) rc = launch_fft_transform_t<KF1>(ctx, raw_dev, bk->d_bsk_fft, ctx->n());
+    else if (bk->path == TFHE_PATH_FFT) rc = launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, ctx->n(), 1);
     else rc = launch_transform(ctx, raw_dev, bk->d_bsk_ntt, ctx->n());
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (d_raw) cudaFree(d_raw);
@@ -545,7 +559,7 @@ int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk
         raw_dev = d_raw;
     }
     e = cudaMemcpyAsync(bk->d_ksk, ksk, ksk_words * 4, is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
-    int rc = e != cudaSuccess ? fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e)) : launch_fft_transform_t<KF1>(ctx, raw_dev, bk->d_bsk_fft, n_ggsw, 3);
+    int rc = e != cudaSuccess ? fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e)) : launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, n_ggsw, 3);
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (d_raw) cudaFree(d_raw);
     if (rc == TFHE_OK && es != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(es));
