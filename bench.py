@@ -40,41 +40,83 @@ def w_int_per_pbs(p):
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons of one GPU, sampled every 20 ms through NVML from a thread of this process (the
+    `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` fields); falls back to an nvidia-smi
+    subprocess.  start() before the warm-up, mark() at the start of the timed region: samples after the mark are
+    reported (the warm-up runs the same kernels, so for a very short timed region the last warm-up samples stand in)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.samples, self.stop_flag, self.t, self.mark_at, self.how = gpu_index, [], False, None, 0, None
+        self.sm_max = None
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            pr = torch.cuda.get_device_properties(self.idx)
+            bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            return pynvml, pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.idx)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            nv, h = self._nvml_handle()
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    except Exception:
+                        r = 0
+                    self.samples.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(r)))
+                    time.sleep(0.02)
+            self.how = "nvml"
+            self.t = threading.Thread(target=loop, daemon=True)
             self.t.start()
         except Exception:
-            self.proc = None
+            self.how = "nvidia-smi"
+            try:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+
+                def pump():
+                    for ln in self.proc.stdout:
+                        f = [x.strip() for x in ln.split(",")]
+                        try:
+                            bits = sum(m for (_, m), v in zip(self.REASONS, f[2:6]) if v.lower().startswith("active"))
+                            self.samples.append((float(f[0]), bits))
+                            self.sm_max = float(f[1])
+                        except (ValueError, IndexError):
+                            pass
+                self.t = threading.Thread(target=pump, daemon=True)
+                self.t.start()
+            except Exception:
+                self.how = None
+
+    def mark(self):
+        self.mark_at = len(self.samples)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        self.stop_flag = True
+        if self.how == "nvidia-smi":
+            self.proc.terminate()
         self.t.join(timeout=2)
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        timed = self.samples[self.mark_at:]
+        use, src = (timed, "timed region") if len(timed) >= 2 else (self.samples[-8:], "end of warm-up + timed region")
+        if not use:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no samples"]}
+        reasons = sorted({name for _, bits in use for name, m in self.REASONS if bits & m})
+        return {"sm_mhz": float(np.median([c for c, _ in use])), "sm_max_mhz": self.sm_max, "reasons": reasons, "samples": len(use),
+                "sampled": f"{self.how}, {src}"}
 
 
 def cpu_reference_rate(p_fields, seconds_hint, threads, bsk, ksk, cts, tv):  # seconds_hint: number of PBS (0 = one per thread)
@@ -195,11 +237,12 @@ def main():
         return [a.elapsed_time(b) for a, b in evs], kern_ms
 
     # ---- device-resident (value)
-    run("device", args.warmup, False)
     sampler = ClockSampler(local_rank)
+    sampler.start()
+    run("device", args.warmup, False)
     barrier()
     launches0 = ctx.launch_count
-    sampler.start()
+    sampler.mark()
     step_ms, kern = run("device", args.steps, True)
     barrier()
     clocks = sampler.stop()
