@@ -83,20 +83,11 @@ struct EmuF {
                         }
                 }
         }
-        std::vector<uint32_t> lo((size_t)K::T * 2 * K::E);
         for (int s = 0; s < K::P; s++) {
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I1<K, 0>(R(s, t), t, twC(), b0(s));
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I2<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
-                phase_I3<K>(R(s, t), t, tw.A.data(), b1(s));
-                phase_round_lo<K>(R(s, t), lo.data() + (size_t)t * 2 * K::E, maxfrac);
-            }
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I1<K, 1>(R(s, t), t, twC(), b0(s));
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_I2<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
-            for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
-                phase_I3<K>(R(s, t), t, tw.A.data(), b1(s));
-                phase_round_hi<K>(R(s, t), t, lo.data() + (size_t)t * 2 * K::E, acc.data() + (size_t)s * K::N, maxfrac);
-            }
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_J1<K>(R(s, t), t, twC(), b0(s), b1(s));
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_J2a<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_J2b<K>(R(s, t), jbase_B<C>(t), b0(s), b1(s));
+            for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_J3<K>(R(s, t), t, tw.A.data(), b0(s), b1(s), acc.data() + (size_t)s * K::N, maxfrac);
         }
     }
 };

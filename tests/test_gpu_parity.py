@@ -310,3 +310,25 @@ def test_bmmp_variant_bit_exact_vs_oracle():
         ctx.external_product(bk, np.array([0], dtype=np.uint32), np.zeros((1, 2, 1024), dtype=np.uint32))
     with pytest.raises(T.TfheError):                 # odd n
         T.bootstrapping_key_gen_bmmp(T.TfheParams.preset("P1", lwe_dimension=5), 1)
+
+
+def test_fft_path_selection_and_limits():
+    """The FFT path is the default where instantiated; beyond its shared-memory bound on n the NTT path serves."""
+    p = T.TfheParams.preset("P1", lwe_dimension=8)
+    ctx = T.Context(p, 0)
+    assert ctx.pbs_path == T.PATH_FFT
+    assert ctx.fft_rounding_margin() == 0.0              # nothing recorded unless checking is switched on
+    ctx.close()
+    big = T.TfheParams.preset("P1", lwe_dimension=1200)  # mask of 3 resident ciphertexts no longer fits
+    ctx = T.Context(big, 0)
+    assert ctx.pbs_path == T.PATH_NTT
+    with pytest.raises(T.TfheError) as ei:
+        ctx.set_pbs_path(T.PATH_FFT)
+    assert ei.value.code == T.TFHE_E_PARAM
+    ctx.close()
+    p2 = T.TfheParams.preset("P2", lwe_dimension=2)      # no FFT instantiation for N = 2048
+    ctx = T.Context(p2, 0)
+    assert ctx.pbs_path == T.PATH_NTT
+    with pytest.raises(T.TfheError):
+        ctx.set_pbs_path(T.PATH_FFT)
+    ctx.close()

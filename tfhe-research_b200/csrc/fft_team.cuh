@@ -372,52 +372,51 @@ TFHE_HD void phase_mac_bmmp(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx 
         r.acc[1][e].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e].im));
     });
 }
-// I1: accumulator of limb LIMB -> inverse pass C -> buf0;  I2: pass B;  I3: pass A, result z in r.x (layout A)
-template <class K, int LIMB>
-TFHE_HD void phase_I1(FftRegs<K> &r, uint32_t t, const cplx *twC, cplx *buf0) {
+// ---- paired inverse: the low- and high-limb accumulators of the column are transformed TOGETHER, in place in their
+// registers (twice the independent butterflies per pass, three barriers for the pair instead of four): limb 0 travels
+// through buf0, limb 1 through buf1; each buffer is stored, (barrier), loaded, and only re-stored after the next barrier.
+//   J1: pass C on both, store_C        | barrier |  J2a: load_B both, pass B  | barrier |  J2b: store_B both  | barrier |
+//   J3: load_A both, pass A, round both, acc += lo + (hi << 16)
+template <class K>
+TFHE_HD void phase_J1(FftRegs<K> &r, uint32_t t, const cplx *twC, cplx *buf0, cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NC_TW];
     load_pass_tw<C::LOGE>(tw, twC + t, C::T);
-#pragma unroll
-    for (int e = 0; e < K::E; e++) r.x[e] = r.acc[LIMB][e];
-    inv_pass<C::LOGE, C::LOGE>(r.x, tw);
-    store_C<C>(r.x, buf0, t);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], tw);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], tw);
+    store_C<C>(r.acc[0], buf0, t);
+    store_C<C>(r.acc[1], buf1, t);
 }
 template <class K>
-TFHE_HD void phase_I2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {
+TFHE_HD void phase_J2a(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, const cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NB_TW];
     load_pass_tw<C::QB>(tw, twB_thread, 1);
-    load_B<C>(r.x, buf0, jbB);
-    inv_pass<C::LOGE, C::QB>(r.x, tw);
-    store_B<C>(r.x, buf1, jbB);
+    load_B<C>(r.acc[0], buf0, jbB);
+    load_B<C>(r.acc[1], buf1, jbB);
+    inv_pass<C::LOGE, C::QB>(r.acc[0], tw);
+    inv_pass<C::LOGE, C::QB>(r.acc[1], tw);
 }
 template <class K>
-TFHE_HD void phase_I3(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf1) {
+TFHE_HD void phase_J2b(const FftRegs<K> &r, uint32_t jbB, cplx *buf0, cplx *buf1) {
     using C = typename K::F;
-    load_A<C>(r.x, buf1, t);
-    inv_pass<C::LOGE, C::LOGE>(r.x, twA);
-}
-// R: low limb -> keep the rounded words; high limb -> acc[c] += lo + (hi << 16)   (ggsw.rs:175 `res += ct0`)
-template <class K>
-TFHE_HD void phase_round_lo(const FftRegs<K> &r, uint32_t *lo, double &maxfrac) {
-#pragma unroll
-    for (int e = 0; e < K::E; e++) {
-        lo[2 * e] = round_u32<K::CHECK>(r.x[e].re, maxfrac);
-        lo[2 * e + 1] = round_u32<K::CHECK>(r.x[e].im, maxfrac);
-    }
+    store_B<C>(r.acc[0], buf0, jbB);
+    store_B<C>(r.acc[1], buf1, jbB);
 }
 template <class K>
-TFHE_HD void phase_round_hi(const FftRegs<K> &r, uint32_t t, const uint32_t *lo, uint32_t *acc_c, double &maxfrac) {
+TFHE_HD void phase_J3(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf0, const cplx *buf1, uint32_t *acc_c, double &maxfrac) {
     using C = typename K::F;
+    load_A<C>(r.acc[0], buf0, t);
+    load_A<C>(r.acc[1], buf1, t);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], twA);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], twA);
 #pragma unroll
     for (int e = 0; e < K::E; e++) {
         const uint32_t j = ((uint32_t)e << C::LOGT) | t;
-        acc_c[j] += lo[2 * e] + (round_u32<K::CHECK>(r.x[e].re, maxfrac) << 16);
-        acc_c[j + K::M] += lo[2 * e + 1] + (round_u32<K::CHECK>(r.x[e].im, maxfrac) << 16);
+        acc_c[j] += round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
+        acc_c[j + K::M] += round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
     }
 }
-
 // ---- one-off key transform: raw GGSW polynomial g[N] (u32) -> limb `limb`, folded, forward FFT, scaled by 1/M,
 // stored in slot order.  T1 -> (barrier) -> F2 -> (barrier) -> T3.
 template <class K>

@@ -237,21 +237,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
         }
 #if !(TFHE_FFT_ABLATE & 16)
-        // inverse transforms of this sub-team's column: low-limb product, then high-limb product, combined in registers
-        uint32_t lo[2 * K::E];
-        phase_I1<K, 0>(R, t, twC, buf0);
+        // inverse transforms of this sub-team's column: the low- and high-limb products together (fft_team.cuh phase_J*)
+        phase_J1<K>(R, t, twC, buf0, buf1);
         sub_sync();
-        phase_I2<K>(R, jbB, twB, buf0, buf1);
+        phase_J2a<K>(R, jbB, twB, buf0, buf1);
         if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
         sub_sync();
-        phase_I3<K>(R, t, a.tw.twA, buf1);
-        phase_round_lo<K>(R, lo, maxfrac);
-        phase_I1<K, 1>(R, t, twC, buf0);
+        phase_J2b<K>(R, jbB, buf0, buf1);
         sub_sync();
-        phase_I2<K>(R, jbB, twB, buf0, buf1);
-        sub_sync();
-        phase_I3<K>(R, t, a.tw.twA, buf1);
-        phase_round_hi<K>(R, t, lo, acc + sub * K::N, maxfrac);
+        phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
 #endif
         sub_sync();   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
     }

@@ -173,7 +173,15 @@ using KF1C = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true>;   // + recor
 #endif
 using KF0 = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, false>;    // reference defaults (lib.rs:101-123)
 using KF0C = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, true>;
-bool fft_available(int pbs_id) { return pbs_id == 0 || pbs_id == 1; }
+template <class K>
+constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8; }
+// the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
+// resident ciphertext, which bounds the LWE dimension (P1 shape: n <= 1151, P0 shape: n <= 2111; above that the NTT path serves)
+bool fft_available(int pbs_id, size_t n = 0) {
+    if (pbs_id == 0) return fft_smem_bytes<KF0>(n) <= 227 * 1024;
+    if (pbs_id == 1) return fft_smem_bytes<KF1>(n) <= 227 * 1024;
+    return false;
+}
 
 template <class K, bool BMMP = false>
 int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
@@ -184,7 +192,7 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     f.in0 = a.in0; f.in1 = a.in1; f.ggsw_index = a.ggsw_index;
     f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
     f.n = a.n; f.batch = a.batch; f.mode = a.mode; f.log_p = a.log_p; f.enc_shift = a.enc_shift;
-    const size_t smem = (size_t)K::CTS * K::team_bytes((int)a.n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8;
+    const size_t smem = fft_smem_bytes<K>(a.n);
     if (smem > 227 * 1024) return fail(ctx, TFHE_E_PARAM, "lwe_dimension too large for the FFT path's shared-memory layout");
     auto kern = fft::pbs_fft_kernel<K, BMMP>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -410,7 +418,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         ctx->tw[pr].invB = (const uint2 *)ctx->d_tw[pr][2];
         ctx->tw[pr].invC = (const uint2 *)ctx->d_tw[pr][3];
     }
-    if (fft_available(ctx->pbs_id)) {
+    if (fft_available(ctx->pbs_id, ctx->n())) {
         const int logm = (int)p->glwe_poly_degree - 1, floge = 3;
         fft::HostFftTw ft;
         fft::build_fft_tables(logm, floge, ft);
@@ -429,7 +437,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
-        if (!strcmp(e, "fft") && fft_available(ctx->pbs_id)) ctx->path = TFHE_PATH_FFT;
+        if (!strcmp(e, "fft") && fft_available(ctx->pbs_id, ctx->n())) ctx->path = TFHE_PATH_FFT;
         if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
     }
     *out = ctx;
@@ -471,7 +479,7 @@ uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx) { return ctx ? ctx->launches
 int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path) {
     if (!ctx) return TFHE_E_PARAM;
     if (path == TFHE_PATH_NTT) { ctx->path = path; return TFHE_OK; }
-    if (path == TFHE_PATH_FFT && fft_available(ctx->pbs_id)) { ctx->path = path; return TFHE_OK; }
+    if (path == TFHE_PATH_FFT && fft_available(ctx->pbs_id, ctx->n())) { ctx->path = path; return TFHE_OK; }
     return fail(ctx, TFHE_E_PARAM, "arithmetic path not instantiated for this parameter set");
 }
 int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx) { return ctx ? ctx->path : TFHE_E_PARAM; }
@@ -533,7 +541,7 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
 
 int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk, tfhe_bk **out) {
     if (!ctx || !bsk3 || !ksk || !out) return TFHE_E_PARAM;
-    if (!fft_available(ctx->pbs_id)) return fail(ctx, TFHE_E_PARAM, "the BMMP variant runs on the FFT path, which is not instantiated for this parameter set");
+    if (!fft_available(ctx->pbs_id, ctx->n())) return fail(ctx, TFHE_E_PARAM, "the BMMP variant runs on the FFT path, which is not instantiated for this parameter set");
     if (ctx->n() & 1) return fail(ctx, TFHE_E_PARAM, "the BMMP variant needs an even lwe_dimension");
     CU(cudaSetDevice(ctx->device));
     const size_t n_ggsw = 3 * (ctx->n() / 2);
