@@ -108,6 +108,66 @@ __global__ void __launch_bounds__(128) k_bfly(double *sink, double wr, double wi
     if (s == 1.2345) sink[0] = s;
 }
 
+// One FFT-pass-like loop per warp: 8 x LDS.128, 36 forward butterflies (twiddles in registers: 4 of 6 DFMAs have three
+// register operands), 8 x STS.128, conflict-free addresses, NO barriers; `threads` per CTA, one CTA per SM.  Reports
+// cycles per iteration per SM next to what the FP64 pipe alone and the shared-memory pipe alone would need: do the two
+// overlap across warps?
+template <int MODE>   // 0: loads + math + stores, 1: math only, 2: loads + stores only, 3: like 0 + a 64-thread named barrier per pass,
+                      // 4: like 3 + per-pass twiddle loads from global memory (4 x LDG.128 per thread)
+__global__ void k_pass(double *sink, int iters, long long *cycles, const double2 *gtw) {
+    extern __shared__ double2 sm[];
+    double2 x[8], w[4];
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = make_double2(1e-3 * (t + i), 1e-3 * (t - i));
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = make_double2(0.7 + 1e-3 * (t + i), 0.7 - 1e-3 * i);
+    for (int i = 0; i < 8; i++) sm[i * blockDim.x + t] = x[i];
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; it++) {
+        if (MODE >= 3) asm volatile("bar.sync %0, 64;" ::"r"(1 + t / 64) : "memory");
+        if (MODE == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) w[i] = __ldg(gtw + i * blockDim.x + t);
+        }
+        if (MODE != 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = sm[i * blockDim.x + (t ^ 1)];   // a neighbour's data: cannot be forwarded from registers
+        }
+        if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i].x += 1.0;
+        }
+        if (MODE != 2) {
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const int bit = 4 >> s;
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    if (e & bit) continue;
+                    const double2 ww = w[(e + s) & 3];
+                    double2 &X = x[e], &Y = x[e + bit];
+                    const double xr = __fma_rn(-Y.y, ww.y, __fma_rn(Y.x, ww.x, X.x));
+                    const double xi = __fma_rn(Y.y, ww.x, __fma_rn(Y.x, ww.y, X.y));
+                    Y.x = __fma_rn(2.0, X.x, -xr); Y.y = __fma_rn(2.0, X.y, -xi);
+                    X.x = xr; X.y = xi;
+                }
+            }
+        }
+        if (MODE != 1) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) sm[i * blockDim.x + t] = x[i];
+        }
+    }
+    const long long t1 = clock64();
+    if (t == 0 && blockIdx.x == 0) cycles[0] = t1 - t0;
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i].x + x[i].y;
+    if (s == 1.2345) sink[0] = s;
+}
+
 int main() {
     cudaDeviceProp pr;
     CK(cudaGetDeviceProperties(&pr, 0));
@@ -193,6 +253,26 @@ int main() {
         }
         long long c; CK(cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost));
         printf(", \"%s_cycles\": %.2f", ln[kind], (double)c / (li * 16.0));
+    }
+    for (int threads = 128; threads <= 512; threads += 128) {
+        const int it3 = 2000;
+        const size_t smem = (size_t)threads * 8 * 16;
+        long long c[5];
+        double2 *gtw; CK(cudaMalloc(&gtw, 512 * 4 * 16)); CK(cudaMemset(gtw, 0, 512 * 4 * 16));
+        for (int mode = 0; mode < 5; mode++) {
+            for (int rep = 0; rep < 2; rep++) {
+                if (mode == 0) { cudaFuncSetAttribute(k_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_pass<0><<<pr.multiProcessorCount, threads, smem>>>(sink, it3, cyc, gtw); }
+                if (mode == 1) { cudaFuncSetAttribute(k_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_pass<1><<<pr.multiProcessorCount, threads, smem>>>(sink, it3, cyc, gtw); }
+                if (mode == 2) { cudaFuncSetAttribute(k_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_pass<2><<<pr.multiProcessorCount, threads, smem>>>(sink, it3, cyc, gtw); }
+                if (mode == 3) { cudaFuncSetAttribute(k_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_pass<3><<<pr.multiProcessorCount, threads, smem>>>(sink, it3, cyc, gtw); }
+                if (mode == 4) { cudaFuncSetAttribute(k_pass<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); k_pass<4><<<pr.multiProcessorCount, threads, smem>>>(sink, it3, cyc, gtw); }
+                CK(cudaDeviceSynchronize());
+            }
+            CK(cudaMemcpy(&c[mode], cyc, 8, cudaMemcpyDeviceToHost));
+        }
+        printf(", \"pass_loop_%dthr_cycles\": {\"both\": %.0f, \"math_only\": %.0f, \"lds_sts_only\": %.0f, \"both_pair_barrier\": %.0f, \"both_pair_barrier_ldg_twiddles\": %.0f}", threads,
+               (double)c[0] / it3, (double)c[1] / it3, (double)c[2] / it3, (double)c[3] / it3, (double)c[4] / it3);
+        cudaFree(gtw);
     }
     printf("}\n");
     return 0;
