@@ -275,18 +275,46 @@ TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, typen
     fwd_pass<C::LOGE, C::LOGE>(r.x, twA);
     store_A<C>(r.x, buf0, t);
 }
-// Twiddles of a pass, tw[2^u - 1 + m] for stage u and m in [0, 2^u).  Siblings satisfy w(st, 2b+1) = i * w(st, 2b)
-// (exponents differ by M and zeta^M = i), so only the even-m entries are loaded (stride = element stride of the table)
-// and the odd ones are formed by a swap and a sign flip: halves the twiddle traffic on the L1/shared-memory data pipe.
+// Twiddles of a pass, tw[2^u - 1 + m] for stage u and m in [0, 2^u).  With b0 the thread-dependent block index of the
+// pass and S its first stage, w(S+u, (b0 << u) | m) = base_u * rho_u^brv_u(m), rho_u = exp(2 pi i / 2^(u+1)), and
+// base_u = base_(u+1)^2 (the exponent of zeta splits into a b0 part and an m part; zeta^M = i).  So ONE table entry per
+// pass is loaded -- the last stage's m = 0 twiddle -- and the other 2^NST - 2 are derived by squaring and by
+// multiplications with i (a swap) and exp(i pi / 4): a quarter of the twiddle traffic on the shared-memory / L1 data
+// pipe, which is this kernel's binding resource, for ~14 FP64 operations per pass.
+TFHE_HD cplx csq(const cplx a) { return cplx{mul_d(add_d(a.re, -a.im), add_d(a.re, a.im)), mul_d(add_d(a.re, a.re), a.im)}; }
+TFHE_HD cplx cmul_i(const cplx a) { return cplx{-a.im, a.re}; }
+TFHE_HD cplx cmul_w8(const cplx a) {
+    constexpr double r = 0.70710678118654752440;
+    return cplx{mul_d(add_d(a.re, -a.im), r), mul_d(add_d(a.re, a.im), r)};
+}
+TFHE_HD cplx cmul_c(const cplx a, double cr, double ci) {
+    return cplx{fma_d(-a.im, ci, mul_d(a.re, cr)), fma_d(a.im, cr, mul_d(a.re, ci))};
+}
 template <int NST>
 TFHE_HD void load_pass_tw(cplx *tw, const cplx *table, uint32_t stride) {
-    static_for<0, NST>([&](auto ui) {
-        constexpr int u = decltype(ui)::value;
-        static_for<0, (1 << u)>([&](auto mi) {
-            constexpr int m = decltype(mi)::value, i = (1 << u) - 1 + m;
-            if constexpr (u == 0 || (m & 1) == 0) tw[i] = table[(size_t)i * stride];
-            else tw[i] = cplx{-tw[i - 1].im, tw[i - 1].re};
-        });
+    static_assert(NST >= 1 && NST <= 4, "derived twiddles are written out for passes of up to 4 stages");
+    cplx b = table[(size_t)((1 << (NST - 1)) - 1) * stride];
+    static_for<0, NST>([&](auto vi) {
+        constexpr int u = NST - 1 - decltype(vi)::value;
+        if constexpr (u < NST - 1) b = csq(b);
+        constexpr int o = (1 << u) - 1;
+        tw[o] = b;
+        if constexpr (u == 1) tw[o + 1] = cmul_i(b);
+        if constexpr (u == 2) {
+            tw[o + 1] = cmul_i(b);          // brv_2(1) = 2: rho^2 = i
+            tw[o + 2] = cmul_w8(b);         // brv_2(2) = 1
+            tw[o + 3] = cmul_i(tw[o + 2]);  // brv_2(3) = 3
+        }
+        if constexpr (u == 3) {             // rho = exp(2 pi i / 16); brv_3(m) = 0, 4, 2, 6, 1, 5, 3, 7
+            constexpr double c16 = 0.92387953251128675613, s16 = 0.38268343236508977173;
+            tw[o + 1] = cmul_i(b);
+            tw[o + 2] = cmul_w8(b);
+            tw[o + 3] = cmul_i(tw[o + 2]);
+            tw[o + 4] = cmul_c(b, c16, s16);
+            tw[o + 5] = cmul_i(tw[o + 4]);
+            tw[o + 6] = cmul_c(b, s16, c16);
+            tw[o + 7] = cmul_i(tw[o + 6]);
+        }
     });
 }
 // F2: layout B, pass B.   F3: layout C, pass C.
