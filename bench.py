@@ -340,7 +340,7 @@ def main():
         # shared-memory / L1 data-pipe bytes the kernel moves per CMUX step and ciphertext (128-bit accesses, E = 8 points per
         # thread): transform exchanges, key rows read from the TMA ring, published/peer transformed rows, twiddles, digits
         E_, T_ = 8, M_ // 8
-        per_thread = ((l_ + 2) * 32 * 16 + l_ * P_ * 2 * E_ * 16 + l_ * (P_ - 1) * E_ * 16 + l_ * E_ * 16 + (l_ + 2) * 8 * 16
+        per_thread = ((l_ + 2) * 32 * 16 + l_ * P_ * 2 * E_ * 16 + l_ * (P_ - 1) * E_ * 16 + l_ * E_ * 16 + (l_ + 2) * 2 * 16
                       + 2 * E_ * 4 * 2 + (l_ - 1) * 2 * E_ * 2 * 2 + 2 * E_ * 4 * 2)
         smem_bytes = B * p.n * per_thread * P_ * T_
         smem_peak = 148 * 128 * clocks["sm_mhz"] * 1e6 if clocks.get("sm_mhz") else 148 * 128 * 1.965e9
