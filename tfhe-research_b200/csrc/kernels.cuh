@@ -299,35 +299,53 @@ __global__ void ks_digits_kernel(const uint32_t *__restrict__ glwe, int8_t *__re
 }
 
 // out[b][c] = -(sum_r D[b][r] * KSK[r][c]) (+ body[b] at c == n), wrapping u32.
-// CTA tile: 64 ciphertexts x 128 columns, 256 threads, 8x4 register micro-tile, BK = 32.
+// CTA tile: 64 ciphertexts x 128 columns, 256 threads, 8x4 register micro-tile, BK = 32.  The device copy of the KSK has
+// a row stride that is a multiple of 128 words (zero padded), so tiles are read with aligned 128-bit loads and need no
+// column checks; the next tile's global loads are issued into registers before the current tile is multiplied.
 constexpr int KS_BM = 64, KS_BN = 128, KS_BK = 32, KS_THREADS = 256;
 __global__ void __launch_bounds__(KS_THREADS) ks_gemm_kernel(const int8_t *__restrict__ digits, const uint32_t *__restrict__ ksk,
                                                              const uint32_t *__restrict__ body, uint32_t *__restrict__ out,
-                                                             uint32_t KD, uint32_t n, uint32_t batch) {
+                                                             uint32_t KD, uint32_t n, uint32_t batch, uint32_t stride) {
     __shared__ __align__(16) int32_t sD[KS_BK][KS_BM];
     __shared__ __align__(16) uint32_t sK[KS_BK][KS_BN];
     const uint32_t tid = threadIdx.x;
     const uint32_t c0 = blockIdx.x * KS_BN, b0 = blockIdx.y * KS_BM;
     const uint32_t tx = tid % 32, ty = tid / 32;  // tx -> 4 columns, ty -> 8 rows
     const uint32_t ncols = n + 1;
+    // loader roles: digits -- row drow, 8 consecutive k from dk0 (a warp covers 32 rows: conflict-free shared stores);
+    // key -- 4 x uint4, consecutive lanes read consecutive 16 bytes of a KSK row
+    const uint32_t drow = tid % KS_BM, dk0 = (tid / KS_BM) * 8;
+    const bool drow_ok = b0 + drow < batch;
+    const int8_t *dsrc = digits + (size_t)(b0 + (drow_ok ? drow : 0)) * KD + dk0;
+    uint2 dreg = make_uint2(0u, 0u);
+    uint4 kreg[4];
+    auto prefetch = [&](uint32_t k0) {
+        if (drow_ok) dreg = __ldg(reinterpret_cast<const uint2 *>(dsrc + k0));
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t idx = tid + i * KS_THREADS, kk = idx / 32, c4 = idx % 32;
+            kreg[i] = __ldg(reinterpret_cast<const uint4 *>(ksk + (size_t)(k0 + kk) * stride + c0 + c4 * 4));
+        }
+    };
     uint32_t accv[8][4];
 #pragma unroll
     for (int i = 0; i < 8; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) accv[i][j] = 0;
-    for (uint32_t k0 = 0; k0 < KD; k0 += KS_BK) {
-        // digits tile: 64 rows x 32 k -> sD[k][row]
-        for (uint32_t e = tid; e < KS_BM * KS_BK; e += KS_THREADS) {
-            const uint32_t row = e / KS_BK, kk = e % KS_BK;
-            const uint32_t b = b0 + row;
-            sD[kk][row] = (b < batch && k0 + kk < KD) ? (int32_t)digits[(size_t)b * KD + k0 + kk] : 0;
+    prefetch(0);
+    for (uint32_t k0 = 0; k0 < KD; k0 += KS_BK) {   // KD is a multiple of KS_BK (checked on the host)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t w = i < 4 ? dreg.x : dreg.y;
+            sD[dk0 + i][drow] = (int32_t)(int8_t)(w >> (8 * (i & 3)));
         }
-        for (uint32_t e = tid; e < KS_BK * KS_BN; e += KS_THREADS) {
-            const uint32_t kk = e / KS_BN, cc = e % KS_BN;
-            const uint32_t c = c0 + cc;
-            sK[kk][cc] = (c < ncols && k0 + kk < KD) ? __ldg(ksk + (size_t)(k0 + kk) * ncols + c) : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t idx = tid + i * KS_THREADS, kk = idx / 32, c4 = idx % 32;
+            *reinterpret_cast<uint4 *>(&sK[kk][c4 * 4]) = kreg[i];
         }
         __syncthreads();
+        if (k0 + KS_BK < KD) prefetch(k0 + KS_BK);
 #pragma unroll 8
         for (int kk = 0; kk < KS_BK; kk++) {
             int32_t av[8];
@@ -368,7 +386,7 @@ __global__ void ks_init_kernel(const uint32_t *__restrict__ body, uint32_t *__re
 constexpr int KSV_THREADS = 256, KSV_MAXB = 8;
 __global__ void __launch_bounds__(KSV_THREADS) ks_gemv_kernel(const int8_t *__restrict__ digits, const uint32_t *__restrict__ ksk,
                                                               uint32_t *__restrict__ out, uint32_t KD, uint32_t n, uint32_t batch,
-                                                              uint32_t rows_per_cta) {
+                                                              uint32_t rows_per_cta, uint32_t stride) {
     __shared__ int32_t sD[KSV_MAXB][64];
     const uint32_t ncols = n + 1;
     const uint32_t r0 = blockIdx.x * rows_per_cta, r1 = min(KD, r0 + rows_per_cta);
@@ -387,7 +405,7 @@ __global__ void __launch_bounds__(KSV_THREADS) ks_gemv_kernel(const int8_t *__re
             __syncthreads();
             const uint32_t rn = min(64u, r1 - rb);
             for (uint32_t rr = 0; rr < rn; rr++) {
-                const uint32_t *row = ksk + (size_t)(rb + rr) * ncols;
+                const uint32_t *row = ksk + (size_t)(rb + rr) * stride;
                 uint32_t kv[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {

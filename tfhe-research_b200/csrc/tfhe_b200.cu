@@ -70,7 +70,8 @@ struct tfhe_bk {
     bool bmmp = false;              // key triples of the unrolled-by-two blind rotation (FFT path only)
     uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]                      (TFHE_PATH_NTT)
     fft::cplx *d_bsk_fft = nullptr; // [n][ROWS][2 limbs][P][N/2], scaled 2/N  (TFHE_PATH_FFT)
-    uint32_t *d_ksk = nullptr;      // [kN*l_ks][n+1]
+    uint32_t *d_ksk = nullptr;      // [kN*l_ks][ksk_stride], ksk_stride = n+1 rounded up to 128 words, zero padded
+    size_t ksk_stride = 0;
 };
 
 namespace {
@@ -298,16 +299,30 @@ int run_key_switch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *src, int fr
         const uint32_t ctas = (uint32_t)ctx->sm_count * 2;
         const uint32_t rows_per_cta = (uint32_t)((KD + ctas - 1) / ctas);
         ks_gemv_kernel<<<(unsigned)((KD + rows_per_cta - 1) / rows_per_cta), KSV_THREADS, 0, ctx->stream>>>(
-            dg, bk->d_ksk, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch, rows_per_cta);
+            dg, bk->d_ksk, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch, rows_per_cta, (uint32_t)bk->ksk_stride);
         CU(cudaGetLastError());
         ctx->launches += 3;
         return TFHE_OK;
     }
     dim3 grid((unsigned)((ctx->n() + 1 + KS_BN - 1) / KS_BN), (unsigned)((batch + KS_BM - 1) / KS_BM));
-    ks_gemm_kernel<<<grid, KS_THREADS, 0, ctx->stream>>>(dg, bk->d_ksk, bd, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch);
+    if (KD % KS_BK) return fail(ctx, TFHE_E_PARAM, "k*N*ks_levels must be a multiple of 32");
+    ks_gemm_kernel<<<grid, KS_THREADS, 0, ctx->stream>>>(dg, bk->d_ksk, bd, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch, (uint32_t)bk->ksk_stride);
     CU(cudaGetLastError());
     ctx->launches += 2;
     return TFHE_OK;
+}
+
+// device KSK: rows padded with zeros to a multiple of 128 words (aligned 128-bit tile loads in ks_gemm_kernel)
+cudaError_t alloc_ksk(tfhe_ctx *ctx, tfhe_bk *bk) {
+    bk->ksk_stride = (ctx->n() + 1 + 127) / 128 * 128;
+    cudaError_t e = cudaMalloc(&bk->d_ksk, ctx->kd() * bk->ksk_stride * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(bk->d_ksk, 0, ctx->kd() * bk->ksk_stride * 4, ctx->stream);
+    return e;
+}
+cudaError_t copy_ksk(tfhe_ctx *ctx, tfhe_bk *bk, const uint32_t *ksk) {
+    const size_t row = (ctx->n() + 1) * 4;
+    return cudaMemcpy2DAsync(bk->d_ksk, bk->ksk_stride * 4, ksk, row, row, ctx->kd(),
+                             is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
 }
 
 int check_bk(tfhe_ctx *ctx, const tfhe_bk *bk) {
@@ -512,7 +527,7 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     auto cleanup = [&]() { tfhe_bk_free(bk); };
     cudaError_t e;
     e = bk->path == TFHE_PATH_FFT ? cudaMalloc(&bk->d_bsk_fft, fft_key_bytes(ctx)) : cudaMalloc(&bk->d_bsk_ntt, bsk_words * 2 * 4);
-    if (e != cudaSuccess || (e = cudaMalloc(&bk->d_ksk, ksk_words * 4)) != cudaSuccess) {
+    if (e != cudaSuccess || (e = alloc_ksk(ctx, bk)) != cudaSuccess) {
         cleanup();
         return fail(ctx, TFHE_E_OOM, cudaGetErrorString(e));
     }
@@ -526,7 +541,7 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
         }
         raw_dev = d_raw;
     }
-    e = cudaMemcpyAsync(bk->d_ksk, ksk, ksk_words * 4, is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    e = copy_ksk(ctx, bk, ksk);
     int rc;
     if (e != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
     else if (bk->path == TFHE_PATH_FFT) rc = launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, ctx->n(), 1);
@@ -552,7 +567,7 @@ int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk
     bk->bmmp = true;
     auto cleanup = [&]() { tfhe_bk_free(bk); };
     cudaError_t e;
-    if ((e = cudaMalloc(&bk->d_bsk_fft, fft_key_bytes(ctx) / ctx->n() * n_ggsw)) != cudaSuccess || (e = cudaMalloc(&bk->d_ksk, ksk_words * 4)) != cudaSuccess) {
+    if ((e = cudaMalloc(&bk->d_bsk_fft, fft_key_bytes(ctx) / ctx->n() * n_ggsw)) != cudaSuccess || (e = alloc_ksk(ctx, bk)) != cudaSuccess) {
         cleanup();
         return fail(ctx, TFHE_E_OOM, cudaGetErrorString(e));
     }
@@ -566,7 +581,7 @@ int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk
         }
         raw_dev = d_raw;
     }
-    e = cudaMemcpyAsync(bk->d_ksk, ksk, ksk_words * 4, is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    e = copy_ksk(ctx, bk, ksk);
     int rc = e != cudaSuccess ? fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e)) : launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, n_ggsw, 3);
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (d_raw) cudaFree(d_raw);
