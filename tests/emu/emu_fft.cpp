@@ -41,7 +41,7 @@ struct EmuF {
                 for (int c = 0; c < K::P; c++) {
                     const uint32_t *g = raw + ((size_t)r * K::P + c) * K::N;
                     const size_t row = key_row_index<K>(r / K::L, r % K::L);
-                    cplx *o = out + ((row * 2 + limb) * K::P + c) * K::M;
+                    cplx *o = out + ((row * K::HALVES * 2 + limb) * K::P + c) * K::MH;   // half 0; phase_T3 adds the half stride
                     for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_T1<K>(R(0, t), t, limb, g, tw.A.data(), b0(0));
                     for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2<K>(R(0, t), jbase_B<C>(t), twB(t), b0(0), b1(0));
                     for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_T3<K>(R(0, t), t, twC(), b1(0), o);
@@ -49,6 +49,7 @@ struct EmuF {
     }
     // BMMP step (notes/BMMP Bootstrapping.md): key = 3 GGSWs [ROWS][3][2][P][M], exponents ex[3]; acc += ExtProd(bundle, acc)
     void step_bmmp(const cplx *key, const uint32_t *ex) {
+        static_assert(K::HALVES == 1, "whole-row key slots only");
         std::vector<uint32_t> snap(acc);
         const uint32_t *a = snap.data();
         run(key, [=](uint32_t p, uint32_t j) { return a[p * K::N + j]; }, 3, ex);
@@ -62,28 +63,51 @@ struct EmuF {
             for (int s = 0; s < K::P; s++) {   // sub-teams run concurrently on the GPU; any order between barriers is legal
                 for (uint32_t t = 0; t < (uint32_t)K::T; t++)
                     phase_F1<K>(R(s, t), t, s, lev, stash.data() + s * STASH, tw.A.data(), b0(s), diff);
-                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
-                for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
-                    phase_F3<K>(R(s, t), t, twC(), b1(s));
-                    phase_xstore<K>(R(s, t), t, b0(s));
+                if constexpr (K::SINGLE_BUF) {   // the kernel's single-buffer flow: every loop below is one barrier interval
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2a<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s));
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2b<K>(R(s, t), jbase_B<C>(t), b0(s));
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F3<K>(R(s, t), t, twC(), b0(s));
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_xstore<K>(R(s, t), t, b0(s));
+                } else {
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_F2<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
+                    for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
+                        phase_F3<K>(R(s, t), t, twC(), b1(s));
+                        phase_xstore<K>(R(s, t), t, b0(s));
+                    }
                 }
             }
             for (int p = 0; p < K::P; p++)
-                for (int which = 0; which < keys; which++) {
-                    const cplx *slot = key + ((size_t)key_row_index<K>(p, lev) * keys + which) * 2 * K::P * K::M;
-                    for (int s = 0; s < K::P; s++)
-                        for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
-                            if (keys == 3) {
-                                if (p == s) phase_mac_bmmp<K, true>(R(s, t), t, s, slot, nullptr, tw.Z.data(), ex[which], bmmp_base<K>(tw.Z.data(), t, ex[which]));
-                                else phase_mac_bmmp<K, false>(R(s, t), t, s, slot, b0(p), tw.Z.data(), ex[which], bmmp_base<K>(tw.Z.data(), t, ex[which]));
-                            } else {
-                                if (p == s) phase_mac<K, true>(R(s, t), t, s, slot, nullptr);
-                                else phase_mac<K, false>(R(s, t), t, s, slot, b0(p));
+                for (int which = 0; which < keys; which++)
+                    for (int h = 0; h < K::HALVES; h++) {
+                        const cplx *slot = key + (((size_t)key_row_index<K>(p, lev) * keys + which) * K::HALVES + h) * 2 * K::P * K::MH;
+                        for (int s = 0; s < K::P; s++)
+                            for (uint32_t t = 0; t < (uint32_t)K::T; t++) {
+                                if constexpr (K::HALVES == 1) {
+                                    if (keys == 3) {
+                                        if (p == s) phase_mac_bmmp<K, true>(R(s, t), t, s, slot, nullptr, tw.Z.data(), ex[which], bmmp_base<K>(tw.Z.data(), t, ex[which]));
+                                        else phase_mac_bmmp<K, false>(R(s, t), t, s, slot, b0(p), tw.Z.data(), ex[which], bmmp_base<K>(tw.Z.data(), t, ex[which]));
+                                        continue;
+                                    }
+                                }
+                                if (p == s) phase_mac<K, true>(R(s, t), t, s, slot, nullptr, h);
+                                else phase_mac<K, false>(R(s, t), t, s, slot, b0(p), h);
                             }
-                        }
-                }
+                    }
         }
         for (int s = 0; s < K::P; s++) {
+            if constexpr (K::SINGLE_BUF) {
+                std::vector<uint32_t> lo((size_t)K::T * 2 * K::E);
+                uint32_t *ac = acc.data() + (size_t)s * K::N;
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K1<K, 0>(R(s, t), t, twC(), b0(s));
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K2a<K, 0>(R(s, t), jbase_B<C>(t), twB(t), b0(s));
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K2b<K, 0>(R(s, t), jbase_B<C>(t), b0(s));
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K3_lo<K>(R(s, t), t, tw.A.data(), b0(s), lo.data() + (size_t)t * 2 * K::E, maxfrac);
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K1<K, 1>(R(s, t), t, twC(), b0(s));
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K2a<K, 1>(R(s, t), jbase_B<C>(t), twB(t), b0(s));
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K2b<K, 1>(R(s, t), jbase_B<C>(t), b0(s));
+                for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_K3_hi<K>(R(s, t), t, tw.A.data(), b0(s), lo.data() + (size_t)t * 2 * K::E, ac, maxfrac);
+                continue;
+            }
             for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_J1<K>(R(s, t), t, twC(), b0(s), b1(s));
             for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_J2a<K>(R(s, t), jbase_B<C>(t), twB(t), b0(s), b1(s));
             for (uint32_t t = 0; t < (uint32_t)K::T; t++) phase_J2b<K>(R(s, t), jbase_B<C>(t), b0(s), b1(s));
@@ -94,7 +118,7 @@ struct EmuF {
 
 using F_P0 = FftPbsCfg<9, 3, 2, 6, 4, 4>;
 using F_P1 = FftPbsCfg<10, 3, 1, 3, 8, 3>;
-using F_P2 = FftPbsCfg<11, 4, 1, 3, 8, 3>;
+using F_P2 = FftPbsCfg<11, 4, 1, 3, 8, 2, true, true, 2>;   // single exchange buffer, half-row key slots
 
 template <class K>
 int run_transform(const uint32_t *raw, double *out) {
@@ -147,9 +171,8 @@ int emu_fft_step_bmmp(int cfg, const uint32_t *raw3, uint32_t *glwe, uint32_t a0
     switch (cfg) {
     case 0: return run_bmmp<F_P0>(raw3, glwe, a0, a1, maxfrac);
     case 1: return run_bmmp<F_P1>(raw3, glwe, a0, a1, maxfrac);
-    case 2: return run_bmmp<F_P2>(raw3, glwe, a0, a1, maxfrac);
     }
-    return -1;
+    return -1;   // the BMMP variant is instantiated for whole-row key slots only (P0, P1)
 }
 int emu_fft_transform_ggsw(int cfg, const uint32_t *raw, double *out) {
     switch (cfg) {

@@ -50,7 +50,7 @@ def env(preset, n):
     return _envs[key]
 
 
-CASES = [("P0:ntt", 4), ("P1:ntt", 3), ("P2", 2), ("P1:fft", 3), ("P1:fft", 21), ("P0:fft", 4), ("P0:fft", 7)]
+CASES = [("P0:ntt", 4), ("P1:ntt", 3), ("P2:ntt", 2), ("P1:fft", 3), ("P1:fft", 21), ("P0:fft", 4), ("P0:fft", 7), ("P2:fft", 2), ("P2:fft", 5)]
 
 
 def r32(rng, *shape):
@@ -326,9 +326,9 @@ def test_fft_path_selection_and_limits():
         ctx.set_pbs_path(T.PATH_FFT)
     assert ei.value.code == T.TFHE_E_PARAM
     ctx.close()
-    p2 = T.TfheParams.preset("P2", lwe_dimension=2)      # no FFT instantiation for N = 2048
+    p2 = T.TfheParams.preset("P2", lwe_dimension=2)      # N = 2048: FFT path with half-row key slots, no BMMP variant
     ctx = T.Context(p2, 0)
-    assert ctx.pbs_path == T.PATH_NTT
+    assert ctx.pbs_path == T.PATH_FFT
     with pytest.raises(T.TfheError):
-        ctx.set_pbs_path(T.PATH_FFT)
+        ctx.upload_key_bmmp(np.zeros(3 * p2.ggsw_words, dtype=np.uint32), np.zeros(p2.ksk_words, dtype=np.uint32))
     ctx.close()

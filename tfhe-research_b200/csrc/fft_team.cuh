@@ -192,14 +192,18 @@ struct TwTablesF {
 // against column s of every GGSW row, its two inverse transforms -- low and high key limb -- and the update of acc[s]).
 // Per level the sub-teams exchange their transformed digit rows through shared memory (xbuf), so every forward
 // transform is computed once and every thread carries only 2 x E complex accumulators.
-template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true>
+// SINGLE_BUF: one exchange buffer per sub-team instead of two (N = 2048: 17 KB each), at the price of a barrier between
+// every load and the next store.  HALVES: a key slot holds both limbs of one GGSW row for 1/HALVES of the points, so the
+// two-slot TMA ring stays at 2 x 32 KB when a row is 64 KB.
+template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true, bool SINGLE_BUF_ = false, int HALVES_ = 1>
 struct FftPbsCfg {
     using F = FftCfg<LOGN_ - 1, LOGE_>;
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2;
     static constexpr int K = K_, P = K_ + 1, L = L_, LOGB = LOGB_, ROWS = P * L;
     static constexpr int E = F::E, T = F::T;
     static constexpr int CTS = CTS_;                    // ciphertexts (teams) per CTA, sharing one key stream
-    static constexpr bool CHECK = CHECK_;
+    static constexpr bool CHECK = CHECK_, SINGLE_BUF = SINGLE_BUF_;
+    static constexpr int HALVES = HALVES_, EH = E / HALVES_, MH = M / HALVES_;   // points per thread / per polynomial in one slot
     static constexpr int WARPS_PER_SUB = T / 32, TEAM_THREADS = P * T, THREADS = CTS * TEAM_THREADS;
     static_assert(LOGB * L <= 32 && 32 % LOGB == 0, "decomposer must divide log_q (SURVEY 9-B H2)");
     // digits of the levels after the first wait in a thread-private stash: int8 when they fit ([-B/2, B], B <= 64)
@@ -207,19 +211,25 @@ struct FftPbsCfg {
     static_assert(LOGB <= 14, "digits are stashed as int16 at most");
     // exactness: largest limb convolution * 2^9 (error constant incl. safety) must stay below 2^51
     static_assert((double)ROWS * N * (double)(1 << LOGB) * 32768.0 * 512.0 < 2251799813685248.0, "FP64 exactness bound");
-    // key stream: one SLOT = one GGSW row, both limbs: [2 limbs][P columns][M] complex in slot order; rows are stored
-    // in consumption order (level-major: row index lev*P + p for polynomial p, level lev)
-    static constexpr int POLY_BYTES = M * 16, LIMB_BYTES = P * POLY_BYTES, SLOT_BYTES = 2 * LIMB_BYTES, SLOTS_PER_STEP = ROWS;
+    // key stream: one SLOT = one GGSW row (or 1/HALVES of its points), both limbs: [2 limbs][P columns][MH] complex in slot
+    // order; rows are stored in consumption order (level-major: row index lev*P + p for polynomial p, level lev)
+    static constexpr int POLY_BYTES = MH * 16, LIMB_BYTES = P * POLY_BYTES, SLOT_BYTES = 2 * LIMB_BYTES, SLOTS_PER_STEP = ROWS * HALVES;
     static constexpr int NSLOT = TFHE_FFT_NSLOT;
     static constexpr size_t GGSW_BYTES = (size_t)SLOTS_PER_STEP * SLOT_BYTES;
     // shared memory per team: acc, then per sub-team {stash, buf0, buf1}, then the mod-switched mask
     static constexpr int TM_ACC = 0;                                   // u32 acc[P][N]
     static constexpr int STASH_BYTES = ((L > 1 ? (L - 1) : 1) * 2 * E * T * (int)sizeof(stash_t) + 15) & ~15;  // [(L-1)*2E][T]
-    static constexpr int SUB_BYTES = STASH_BYTES + 2 * F::MPAD * 16;   // + cplx buf[2][MPAD]
+    static constexpr int NBUF = SINGLE_BUF ? 1 : 2;
+    static constexpr int SUB_BYTES = STASH_BYTES + NBUF * F::MPAD * 16;   // + cplx buf[NBUF][MPAD]
     static constexpr int TM_SUB = TM_ACC + P * N * 4;
     static constexpr int TM_AT = TM_SUB + P * SUB_BYTES;               // u16 at[n+1] (size known at launch)
     static constexpr int team_bytes(int n) { return (TM_AT + (n + 1) * 2 + 127) & ~127; }
-    static_assert(CTS >= 2 || CTS == 1, "teams per CTA");  // single-ciphertext modes borrow the accumulators of teams 1 and 2 (need CTS >= 3)
+    // single-ciphertext modes borrow idle shared memory for the polynomial to decompose and a zero subtrahend: the
+    // accumulators of teams 1 and 2, or (two teams) the accumulator and the first exchange buffer of team 1
+    static_assert(CTS >= 3 || (CTS == 2 && F::MPAD * 16 >= P * N * 4), "single-ciphertext modes need two spare accumulator-sized regions");
+    static constexpr int SPARE_DIN = 1 * 0 + TM_ACC;                         // offset inside team 1
+    static constexpr int SPARE_ZERO_TEAM = CTS >= 3 ? 2 : 1;
+    static constexpr int SPARE_ZERO = CTS >= 3 ? TM_ACC : TM_SUB + STASH_BYTES;   // offset inside team SPARE_ZERO_TEAM
 };
 // index of GGSW row (polynomial p, level lev) in the stored key = its position in the consumption order
 template <class K>
@@ -335,6 +345,17 @@ TFHE_HD void phase_F3(FftRegs<K> &r, uint32_t t, const cplx *twC, const cplx *bu
     load_C<C>(r.x, buf1, t);
     fwd_pass<C::LOGE, C::LOGE>(r.x, tw);
 }
+// single-buffer variants: the load half and the store half of a pass are separate phases (a barrier goes between them)
+template <class K>
+TFHE_HD void phase_F2a(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf) {
+    using C = typename K::F;
+    cplx tw[C::NB_TW];
+    load_pass_tw<C::QB>(tw, twB_thread, 1);
+    load_B<C>(r.x, buf, jbB);
+    fwd_pass<C::LOGE, C::QB>(r.x, tw);
+}
+template <class K>
+TFHE_HD void phase_F2b(const FftRegs<K> &r, uint32_t jbB, cplx *buf) { store_B<typename K::F>(r.x, buf, jbB); }
 // X: publish this sub-team's transformed digit row for the other sub-teams (slot order: point (t<<LOGE)|e at e*T + t)
 template <class K>
 TFHE_HD void phase_xstore(const FftRegs<K> &r, uint32_t t, cplx *xbuf) {
@@ -345,17 +366,23 @@ TFHE_HD void phase_xstore(const FftRegs<K> &r, uint32_t t, cplx *xbuf) {
 // slot = [2 limbs][P][M] complex in slot order (consecutive lanes read consecutive 16 bytes); xsrc = this thread's own
 // r.x (OWN) or the publishing sub-team's xbuf.
 template <class K, bool OWN>
-TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot, const cplx *xbuf) {
-    const cplx *g0 = slot + col * K::M + t, *g1 = g0 + K::P * K::M;
+TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot, const cplx *xbuf, uint32_t h = 0) {
+    const cplx *g0 = slot + col * K::MH + t, *g1 = g0 + K::P * K::MH;
+    static_for<0, K::HALVES>([&](auto hi) {      // compile-time register indices: h selects which EH of the E points
+        constexpr int hh = decltype(hi)::value;
+        if (h == (uint32_t)hh) {
 #pragma unroll
-    for (int e = 0; e < K::E; e++) {
-        const cplx xv = OWN ? r.x[e] : xbuf[e * K::T + t];
-        const cplx a = g0[e * K::T], b = g1[e * K::T];
-        r.acc[0][e].re = fma_d(-xv.im, a.im, fma_d(xv.re, a.re, r.acc[0][e].re));
-        r.acc[0][e].im = fma_d(xv.im, a.re, fma_d(xv.re, a.im, r.acc[0][e].im));
-        r.acc[1][e].re = fma_d(-xv.im, b.im, fma_d(xv.re, b.re, r.acc[1][e].re));
-        r.acc[1][e].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e].im));
-    }
+            for (int q = 0; q < K::EH; q++) {
+                constexpr int e0 = hh * K::EH;
+                const cplx xv = OWN ? r.x[e0 + q] : xbuf[(e0 + q) * K::T + t];
+                const cplx a = g0[q * K::T], b = g1[q * K::T];
+                r.acc[0][e0 + q].re = fma_d(-xv.im, a.im, fma_d(xv.re, a.re, r.acc[0][e0 + q].re));
+                r.acc[0][e0 + q].im = fma_d(xv.im, a.re, fma_d(xv.re, a.im, r.acc[0][e0 + q].im));
+                r.acc[1][e0 + q].re = fma_d(-xv.im, b.im, fma_d(xv.re, b.re, r.acc[1][e0 + q].re));
+                r.acc[1][e0 + q].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e0 + q].im));
+            }
+        }
+    });
 }
 // bit reversal of the low `bits` bits
 TFHE_HD uint32_t brv_bits(uint32_t x, int bits) {
@@ -382,6 +409,7 @@ template <class K, bool OWN>
 TFHE_HD void phase_mac_bmmp(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot, const cplx *xbuf, const cplx *ztab, uint32_t ex,
                             const cplx base) {
     using C = typename K::F;
+    static_assert(K::HALVES == 1, "the BMMP variant is instantiated for whole-row key slots only");
     const cplx *g0 = slot + col * K::M + t, *g1 = g0 + K::P * K::M;
     static_for<0, K::E>([&](auto ei) {
         constexpr int e = decltype(ei)::value;
@@ -445,6 +473,51 @@ TFHE_HD void phase_J3(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *bu
         acc_c[j + K::M] += round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
     }
 }
+// single-buffer inverse of ONE limb, in place in its accumulator registers:
+//   K1: pass C, store_C | barrier | K2a: load_B, pass B | barrier | K2b: store_B | barrier | K3: load_A, pass A
+// then (limb 0) keep the rounded words, (limb 1) acc += lo + (hi << 16).
+template <class K, int LIMB>
+TFHE_HD void phase_K1(FftRegs<K> &r, uint32_t t, const cplx *twC, cplx *buf) {
+    using C = typename K::F;
+    cplx tw[C::NC_TW];
+    load_pass_tw<C::LOGE>(tw, twC + t, C::T);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[LIMB], tw);
+    store_C<C>(r.acc[LIMB], buf, t);
+}
+template <class K, int LIMB>
+TFHE_HD void phase_K2a(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf) {
+    using C = typename K::F;
+    cplx tw[C::NB_TW];
+    load_pass_tw<C::QB>(tw, twB_thread, 1);
+    load_B<C>(r.acc[LIMB], buf, jbB);
+    inv_pass<C::LOGE, C::QB>(r.acc[LIMB], tw);
+}
+template <class K, int LIMB>
+TFHE_HD void phase_K2b(const FftRegs<K> &r, uint32_t jbB, cplx *buf) { store_B<typename K::F>(r.acc[LIMB], buf, jbB); }
+template <class K>
+TFHE_HD void phase_K3_lo(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf, uint32_t *lo, double &maxfrac) {
+    using C = typename K::F;
+    load_A<C>(r.acc[0], buf, t);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], twA);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        lo[2 * e] = round_u32<K::CHECK>(r.acc[0][e].re, maxfrac);
+        lo[2 * e + 1] = round_u32<K::CHECK>(r.acc[0][e].im, maxfrac);
+    }
+}
+template <class K>
+TFHE_HD void phase_K3_hi(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf, const uint32_t *lo, uint32_t *acc_c, double &maxfrac) {
+    using C = typename K::F;
+    load_A<C>(r.acc[1], buf, t);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], twA);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+        acc_c[j] += lo[2 * e] + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
+        acc_c[j + K::M] += lo[2 * e + 1] + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
+    }
+}
+
 // ---- one-off key transform: raw GGSW polynomial g[N] (u32) -> limb `limb`, folded, forward FFT, scaled by 1/M,
 // stored in slot order.  T1 -> (barrier) -> F2 -> (barrier) -> T3.
 template <class K>
@@ -463,7 +536,8 @@ TFHE_HD void phase_T3(FftRegs<K> &r, uint32_t t, const cplx *twC, const cplx *bu
     phase_F3<K>(r, t, twC, buf1);
     constexpr double scale = 1.0 / (double)K::M;  // power of two: exact
 #pragma unroll
-    for (int e = 0; e < K::E; e++) out[e * K::T + t] = cplx{mul_d(r.x[e].re, scale), mul_d(r.x[e].im, scale)};
+    for (int e = 0; e < K::E; e++)   // point e of this thread: half e / EH, position (e % EH) * T + t inside the half
+        out[(size_t)(e / K::EH) * (2 * K::P * K::MH) + (e % K::EH) * K::T + t] = cplx{mul_d(r.x[e].re, scale), mul_d(r.x[e].im, scale)};
 }
 
 }  // namespace fft

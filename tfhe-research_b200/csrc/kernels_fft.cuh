@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     uint32_t *acc = reinterpret_cast<uint32_t *>(tm + K::TM_ACC);
     uint8_t *sb = tm + K::TM_SUB + sub * K::SUB_BYTES;
     typename K::stash_t *stash = reinterpret_cast<typename K::stash_t *>(sb);
-    cplx *buf0 = reinterpret_cast<cplx *>(sb + K::STASH_BYTES), *buf1 = buf0 + C::MPAD;
+    cplx *buf0 = reinterpret_cast<cplx *>(sb + K::STASH_BYTES), *buf1 = K::SINGLE_BUF ? buf0 : buf0 + C::MPAD;
     uint16_t *at = reinterpret_cast<uint16_t *>(tm + K::TM_AT);
     // named barriers: one per team, plus one per sub-team unless a sub-team is a single warp (then __syncwarp)
     constexpr bool WARP_SUB = K::T == 32;
@@ -132,10 +132,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             acc[idx] = v;
         }
     } else {
-        // single-ciphertext modes borrow the (idle) accumulators of teams 1 and 2 for the polynomial to decompose
-        // and for a zero subtrahend, so the step below is the same code as the blind rotation with rot = 0
-        uint32_t *din = reinterpret_cast<uint32_t *>(smem + 1 * team_bytes + K::TM_ACC);
-        uint32_t *zero = reinterpret_cast<uint32_t *>(smem + 2 * team_bytes + K::TM_ACC);
+        // single-ciphertext modes borrow idle shared memory of the other teams (FftPbsCfg::SPARE_*) for the polynomial to
+        // decompose and for a zero subtrahend, so the step below is the same code as the blind rotation with rot = 0
+        uint32_t *din = reinterpret_cast<uint32_t *>(smem + 1 * team_bytes + K::SPARE_DIN);
+        uint32_t *zero = reinterpret_cast<uint32_t *>(smem + K::SPARE_ZERO_TEAM * team_bytes + K::SPARE_ZERO);
         const uint32_t *x0 = a.in0 + (size_t)ct * K::P * K::N, *x1 = a.in1 + (size_t)ct * K::P * K::N;
         for (uint32_t idx = tt; idx < (uint32_t)(K::P * K::N); idx += K::TEAM_THREADS) {
             const uint32_t v0 = __ldg(x0 + idx);
@@ -207,14 +207,23 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             else phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
             sub_sync();
-            phase_F2<K>(R, jbB, twB, buf0, buf1);
-            sub_sync();
-            phase_F3<K>(R, t, twC, buf1);
-            phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its pass-B loads
+            if constexpr (K::SINGLE_BUF) {           // one buffer: a barrier between every load and the next store
+                phase_F2a<K>(R, jbB, twB, buf0);
+                sub_sync();
+                phase_F2b<K>(R, jbB, buf0);
+                sub_sync();
+                phase_F3<K>(R, t, twC, buf0);
+                sub_sync();
+            } else {
+                phase_F2<K>(R, jbB, twB, buf0, buf1);
+                sub_sync();
+                phase_F3<K>(R, t, twC, buf1);
+            }
+            phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
             team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
 #pragma unroll 1
-            for (uint32_t pk = 0; pk < (uint32_t)K::P * KEYS; pk++) {
-                const uint32_t p = pk / KEYS, which = pk % KEYS;
+            for (uint32_t pk = 0; pk < (uint32_t)K::P * KEYS * K::HALVES; pk++) {
+                const uint32_t p = pk / (KEYS * K::HALVES), which = (pk / K::HALVES) % KEYS, half = pk % K::HALVES;
                 const uint32_t s = it % K::NSLOT;
                 if (producer) pump(it + 1);
                 mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
@@ -226,8 +235,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                     else phase_mac_bmmp<K, false>(R, t, sub, slot, peer, a.tw.ztab, which == 0 ? ex0 : which == 1 ? rot : rot1, which == 0 ? zb[0] : which == 1 ? zb[1] : zb[2]);
                 } else {
                     (void)which;
-                    if (p == sub) phase_mac<K, true>(R, t, sub, slot, nullptr);
-                    else phase_mac<K, false>(R, t, sub, slot, peer);
+                    if (p == sub) phase_mac<K, true>(R, t, sub, slot, nullptr, half);
+                    else phase_mac<K, false>(R, t, sub, slot, peer, half);
                 }
 #endif
                 __syncwarp();
@@ -238,14 +247,34 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
 #if !(TFHE_FFT_ABLATE & 16)
         // inverse transforms of this sub-team's column: the low- and high-limb products together (fft_team.cuh phase_J*)
-        phase_J1<K>(R, t, twC, buf0, buf1);
-        sub_sync();
-        phase_J2a<K>(R, jbB, twB, buf0, buf1);
-        if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
-        sub_sync();
-        phase_J2b<K>(R, jbB, buf0, buf1);
-        sub_sync();
-        phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
+        if constexpr (K::SINGLE_BUF) {   // one limb after the other through the single buffer
+            uint32_t lo[2 * K::E];
+            phase_K1<K, 0>(R, t, twC, buf0);
+            sub_sync();
+            phase_K2a<K, 0>(R, jbB, twB, buf0);
+            if (producer) pump(0);
+            sub_sync();
+            phase_K2b<K, 0>(R, jbB, buf0);
+            sub_sync();
+            phase_K3_lo<K>(R, t, a.tw.twA, buf0, lo, maxfrac);
+            sub_sync();
+            phase_K1<K, 1>(R, t, twC, buf0);
+            sub_sync();
+            phase_K2a<K, 1>(R, jbB, twB, buf0);
+            sub_sync();
+            phase_K2b<K, 1>(R, jbB, buf0);
+            sub_sync();
+            phase_K3_hi<K>(R, t, a.tw.twA, buf0, lo, acc + sub * K::N, maxfrac);
+        } else {
+            phase_J1<K>(R, t, twC, buf0, buf1);
+            sub_sync();
+            phase_J2a<K>(R, jbB, twB, buf0, buf1);
+            if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
+            sub_sync();
+            phase_J2b<K>(R, jbB, buf0, buf1);
+            sub_sync();
+            phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
+        }
 #endif
         sub_sync();   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
     }
@@ -278,7 +307,7 @@ __global__ void __launch_bounds__(2 * K::T) bsk_fft_transform_kernel(const __gri
     const uint32_t *g = a.raw + poly * K::N;
     const size_t kps = a.keys_per_step, step = i / kps, which = i % kps;
     const size_t row = (step * K::ROWS + key_row_index<K>((uint32_t)(r / K::L), (uint32_t)(r % K::L))) * kps + which;   // consumption order
-    cplx *o = a.out + ((row * 2 + limb) * K::P + c) * K::M;
+    cplx *o = a.out + ((row * K::HALVES * 2 + limb) * K::P + c) * K::MH;   // half 0; phase_T3 adds the half stride
     FftRegs<K> R;
     phase_T1<K>(R, t, (int)limb, g, a.tw.twA, buf0);
     team_bar_id(limb + 1, K::T);

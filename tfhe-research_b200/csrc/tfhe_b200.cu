@@ -174,6 +174,12 @@ using KF1C = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true>;   // + recor
 #endif
 using KF0 = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, false>;    // reference defaults (lib.rs:101-123)
 using KF0C = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, true>;
+#ifndef TFHE_FFT_CTS_P2
+#define TFHE_FFT_CTS_P2 2
+#endif
+// N = 2048: 16 points per thread, one exchange buffer per sub-team, half-row key slots (fft_team.cuh FftPbsCfg)
+using KF2 = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, false, true, 2>;
+using KF2C = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2>;
 template <class K>
 constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8; }
 // the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
@@ -181,6 +187,7 @@ constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_byte
 bool fft_available(int pbs_id, size_t n = 0) {
     if (pbs_id == 0) return fft_smem_bytes<KF0>(n) <= 227 * 1024;
     if (pbs_id == 1) return fft_smem_bytes<KF1>(n) <= 227 * 1024;
+    if (pbs_id == 2) return fft_smem_bytes<KF2>(n) <= 227 * 1024;
     return false;
 }
 
@@ -225,6 +232,7 @@ int launch_fft_transform(tfhe_ctx *ctx, const uint32_t *raw, fft::cplx *out, siz
     switch (ctx->pbs_id) {
     case 0: return launch_fft_transform_t<KF0>(ctx, raw, out, n_ggsw, keys_per_step);
     case 1: return launch_fft_transform_t<KF1>(ctx, raw, out, n_ggsw, keys_per_step);
+    case 2: return launch_fft_transform_t<KF2>(ctx, raw, out, n_ggsw, keys_per_step);
     }
     return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
 }
@@ -245,6 +253,7 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
         switch (ctx->pbs_id) {
         case 0: return ctx->fft_check ? launch_pbs_fft_t<KF0C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0>(ctx, a, bk->d_bsk_fft);
         case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
+        case 2: return ctx->fft_check ? launch_pbs_fft_t<KF2C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF2>(ctx, a, bk->d_bsk_fft);
         }
         return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
     }
@@ -434,7 +443,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         ctx->tw[pr].invC = (const uint2 *)ctx->d_tw[pr][3];
     }
     if (fft_available(ctx->pbs_id, ctx->n())) {
-        const int logm = (int)p->glwe_poly_degree - 1, floge = 3;
+        const int logm = (int)p->glwe_poly_degree - 1, floge = ctx->pbs_id == 2 ? 4 : 3;   // = FftPbsCfg::F::LOGE of the instantiation
         fft::HostFftTw ft;
         fft::build_fft_tables(logm, floge, ft);
         for (size_t i = 0; i < ft.A.size(); i++) ctx->ftw.twA[i] = ft.A[i];
@@ -556,7 +565,8 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
 
 int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk, tfhe_bk **out) {
     if (!ctx || !bsk3 || !ksk || !out) return TFHE_E_PARAM;
-    if (!fft_available(ctx->pbs_id, ctx->n())) return fail(ctx, TFHE_E_PARAM, "the BMMP variant runs on the FFT path, which is not instantiated for this parameter set");
+    if (!fft_available(ctx->pbs_id, ctx->n()) || ctx->pbs_id == 2)
+        return fail(ctx, TFHE_E_PARAM, "the BMMP variant is instantiated for the P0 and P1 shapes only");
     if (ctx->n() & 1) return fail(ctx, TFHE_E_PARAM, "the BMMP variant needs an even lwe_dimension");
     CU(cudaSetDevice(ctx->device));
     const size_t n_ggsw = 3 * (ctx->n() / 2);
