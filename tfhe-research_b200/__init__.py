@@ -19,7 +19,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libtfhe_b200.so")
+LIB_PATH = os.environ.get("TFHE_B200_LIB") or os.path.join(_HERE, "libtfhe_b200.so")   # override: A/B runs of kernel variants
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"]
 _SOURCES = ["tfhe_b200.cu", "host_api.cpp"]

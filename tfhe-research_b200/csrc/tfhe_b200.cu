@@ -167,8 +167,14 @@ int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
 #ifndef TFHE_FFT_CTS_P1
 #define TFHE_FFT_CTS_P1 3
 #endif
-using KF1 = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, false>;   // production: a-priori exactness bound only
-using KF1C = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true>;   // + records the rounding margin (tests, validation)
+#ifndef TFHE_FFT_P1_LOGE
+#define TFHE_FFT_P1_LOGE 3
+#endif
+#ifndef TFHE_FFT_P1_SINGLE
+#define TFHE_FFT_P1_SINGLE 0
+#endif
+using KF1 = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, false, TFHE_FFT_P1_SINGLE != 0>;   // production: a-priori exactness bound only
+using KF1C = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, true, TFHE_FFT_P1_SINGLE != 0>;   // + records the rounding margin (tests, validation)
 #ifndef TFHE_FFT_CTS_P0
 #define TFHE_FFT_CTS_P0 4
 #endif
@@ -443,7 +449,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         ctx->tw[pr].invC = (const uint2 *)ctx->d_tw[pr][3];
     }
     if (fft_available(ctx->pbs_id, ctx->n())) {
-        const int logm = (int)p->glwe_poly_degree - 1, floge = ctx->pbs_id == 2 ? 4 : 3;   // = FftPbsCfg::F::LOGE of the instantiation
+        const int logm = (int)p->glwe_poly_degree - 1, floge = ctx->pbs_id == 2 ? 4 : ctx->pbs_id == 1 ? TFHE_FFT_P1_LOGE : 3;   // = FftPbsCfg::F::LOGE of the instantiation
         fft::HostFftTw ft;
         fft::build_fft_tables(logm, floge, ft);
         for (size_t i = 0; i < ft.A.size(); i++) ctx->ftw.twA[i] = ft.A[i];
