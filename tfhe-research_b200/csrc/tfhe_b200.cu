@@ -214,7 +214,8 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     if (a.mode == 0) {
         // whole waves of one CTA per SM; the kernel spreads the batch evenly over them (<= CTS ciphertexts per CTA)
         const unsigned ctas = (unsigned)((a.batch + K::CTS - 1) / K::CTS), sms = (unsigned)ctx->sm_count;
-        grid = ctas <= sms ? ctas : ((ctas + sms - 1) / sms) * sms;
+        // less than one wave: one CTA per SM with as few ciphertexts each as possible (shortest latency)
+        grid = ctas <= sms ? (a.batch < sms ? (unsigned)a.batch : sms) : ((ctas + sms - 1) / sms) * sms;
         if (grid > a.batch) grid = (unsigned)a.batch;
     }
     kern<<<grid, K::THREADS, smem, ctx->stream>>>(f);
