@@ -43,10 +43,12 @@ def test_oracle_reproduces_golden(case):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path", ["fft", "ntt"])
 @pytest.mark.parametrize("case", GOLD["cases"], ids=[c["name"] for c in GOLD["cases"]])
-def test_gpu_reproduces_golden(case):
+def test_gpu_reproduces_golden(case, path):
+    """Both arithmetic paths (exact FP64 FFT with a limb-split key; 2-prime NTT) reproduce the frozen vectors."""
     p, (lwe_sk, glwe_sk, bsk, ksk) = product_keys(case)
-    ctx = T.Context(p, 0)
+    ctx = T.Context(p, 0, path=T.PATH_FFT if path == "fft" else T.PATH_NTT)
     bk = ctx.upload_key(bsk, ksk)
     tvs = np.stack([T.construct_identity_test_vector(p), T.construct_test_from_lut(p, case["lut"])])
     cts = np.array(case["lwe_in"], dtype=np.uint32)
