@@ -101,6 +101,26 @@ def test_p1_trivial_ciphertexts_closed_form(which):
         assert not acc[b, :p.k].any()
 
 
+def test_p1_skipped_steps_in_shared_ctas():
+    """Steps with a~_i = 0 are skipped per ciphertext while the other ciphertexts of the same CTA (which share the key
+    stream, and on the FFT path relay key rows to each other through TMEM) run them: zero some mask words of some
+    ciphertexts of a batch that fills every CTA with 2-3 ciphertexts; both arithmetic paths must agree bit for bit."""
+    e, en = env("P1:fft"), env("P1:ntt")
+    n = e.p.n
+    tv = T.construct_identity_test_vector(e.p)
+    cts, nu = make_batch(e, 400)
+    rng = np.random.default_rng(11)
+    for b in range(0, 400, 3):                      # every third ciphertext: ~20 % of its steps skipped
+        cts[b, :n][rng.random(n) < 0.2] = 0
+    cts[7, :n] = 0                                  # one trivial ciphertext: all steps skipped
+    cts[8, :n // 2] = 0
+    acc_f = e.ctx.blind_rotate(e.bk, cts, tv)
+    acc_n = en.ctx.blind_rotate(en.bk, cts, tv)
+    assert np.array_equal(acc_f, acc_n)
+    assert np.array_equal(acc_f[:3], e.ctx.blind_rotate(e.bk, cts[:3], tv))   # batch invariance: 1 ciphertext per CTA
+    assert np.array_equal(acc_f[7], e.ctx.blind_rotate(e.bk, cts[7:8], tv)[0])
+
+
 def test_p2_programmable_lut_batch_16k():
     """BASELINE config #3: programmable LUT bootstrap, N=2048, 4-bit messages, batch 16k."""
     e = env("P2")

@@ -259,31 +259,44 @@ TFHE_HD int32_t key_limb(uint32_t g, int limb) {
 // minuend(p, j) - subtrahend(p, j) is coefficient j of polynomial p of the GLWE to decompose (glwe.rs:69-108).  The
 // decomposition (decomposer.rs:27-80) of a thread's 2E coefficients is done once per polynomial, at level 0; the
 // other levels' digits wait in a thread-private stash (no barrier: written and read by the same thread).
+// F1 = F1a (registers only: digits, pass A) followed by store_A into buf0.
 template <class K, class DiffFn>
-TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, typename K::stash_t *stash, const cplx *twA, cplx *buf0, DiffFn diff) {
+TFHE_HD void phase_F1a(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, typename K::stash_t *stash, const cplx *twA, DiffFn diff) {
     using C = typename K::F;
+    // stash word = the two digits (coefficients j and j + M: real and imaginary part of point e) of one level
+    using pair_t = typename std::conditional<sizeof(typename K::stash_t) == 1, uint16_t, uint32_t>::type;
+    constexpr int SB = 8 * (int)sizeof(typename K::stash_t);
+    pair_t *sp = reinterpret_cast<pair_t *>(stash);
     if (lev == 0) {
 #pragma unroll
         for (int e = 0; e < K::E; e++) {
-            int32_t v[2];
+            int32_t d[2][K::L];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t j = (((uint32_t)e << C::LOGT) | t) + (uint32_t)h * K::M;
-                int32_t d[K::L];
-                decompose_signed<K::LOGB, K::L>(diff(p, j), d);
-                v[h] = d[0];
-#pragma unroll
-                for (int l = 1; l < K::L; l++) stash[(((l - 1) * 2 * K::E) + 2 * e + h) * K::T + t] = (typename K::stash_t)d[l];
+                // optional third argument: 2e + h, the position among this thread's coefficients (register-resident operands)
+                if constexpr (std::is_invocable<DiffFn, uint32_t, uint32_t, int>::value) decompose_signed<K::LOGB, K::L>(diff(p, j, 2 * e + h), d[h]);
+                else decompose_signed<K::LOGB, K::L>(diff(p, j), d[h]);
             }
-            r.x[e] = cplx{i2d(v[0]), i2d(v[1])};
+#pragma unroll
+            for (int l = 1; l < K::L; l++)
+                sp[((l - 1) * K::E + e) * K::T + t] = (pair_t)(((uint32_t)d[0][l] & ((1u << SB) - 1u)) | ((uint32_t)d[1][l] << SB));
+            r.x[e] = cplx{i2d(d[0][0]), i2d(d[1][0])};
         }
     } else {
-        const typename K::stash_t *s = stash + (size_t)(lev - 1) * 2 * K::E * K::T + t;
+        const pair_t *s = sp + (size_t)(lev - 1) * K::E * K::T + t;
 #pragma unroll
-        for (int e = 0; e < K::E; e++) r.x[e] = cplx{i2d(s[(2 * e) * K::T]), i2d(s[(2 * e + 1) * K::T])};
+        for (int e = 0; e < K::E; e++) {
+            const uint32_t w = s[e * K::T];
+            r.x[e] = cplx{i2d((int32_t)(typename K::stash_t)(w & ((1u << SB) - 1u))), i2d((int32_t)(typename K::stash_t)(w >> SB))};
+        }
     }
     fwd_pass<C::LOGE, C::LOGE>(r.x, twA);
-    store_A<C>(r.x, buf0, t);
+}
+template <class K, class DiffFn>
+TFHE_HD void phase_F1(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, typename K::stash_t *stash, const cplx *twA, cplx *buf0, DiffFn diff) {
+    phase_F1a<K>(r, t, p, lev, stash, twA, diff);
+    store_A<typename K::F>(r.x, buf0, t);
 }
 // Twiddles of a pass, tw[2^u - 1 + m] for stage u and m in [0, 2^u).  With b0 the thread-dependent block index of the
 // pass and S its first stage, w(S+u, (b0 << u) | m) = base_u * rho_u^brv_u(m), rho_u = exp(2 pi i / 2^(u+1)), and
@@ -300,10 +313,12 @@ TFHE_HD cplx cmul_w8(const cplx a) {
 TFHE_HD cplx cmul_c(const cplx a, double cr, double ci) {
     return cplx{fma_d(-a.im, ci, mul_d(a.re, cr)), fma_d(a.im, cr, mul_d(a.re, ci))};
 }
+// the one table entry a pass of NST stages needs (a thread's entries never change: the kernel keeps them in registers)
 template <int NST>
-TFHE_HD void load_pass_tw(cplx *tw, const cplx *table, uint32_t stride) {
+TFHE_HD cplx pass_tw_base(const cplx *table, uint32_t stride) { return table[(size_t)((1 << (NST - 1)) - 1) * stride]; }
+template <int NST>
+TFHE_HD void derive_pass_tw(cplx *tw, cplx b) {
     static_assert(NST >= 1 && NST <= 4, "derived twiddles are written out for passes of up to 4 stages");
-    cplx b = table[(size_t)((1 << (NST - 1)) - 1) * stride];
     static_for<0, NST>([&](auto vi) {
         constexpr int u = NST - 1 - decltype(vi)::value;
         if constexpr (u < NST - 1) b = csq(b);
@@ -327,23 +342,34 @@ TFHE_HD void load_pass_tw(cplx *tw, const cplx *table, uint32_t stride) {
         }
     });
 }
+template <int NST>
+TFHE_HD void load_pass_tw(cplx *tw, const cplx *table, uint32_t stride) { derive_pass_tw<NST>(tw, pass_tw_base<NST>(table, stride)); }
 // F2: layout B, pass B.   F3: layout C, pass C.
+// (the *v variants take the pass's table entry by value: pass_tw_base<QB>(twB_thread, 1) / pass_tw_base<LOGE>(twC + t, T))
 template <class K>
-TFHE_HD void phase_F2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {
+TFHE_HD void phase_F2v(FftRegs<K> &r, uint32_t jbB, const cplx twB_base, const cplx *buf0, cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NB_TW];
-    load_pass_tw<C::QB>(tw, twB_thread, 1);
+    derive_pass_tw<C::QB>(tw, twB_base);
     load_B<C>(r.x, buf0, jbB);
     fwd_pass<C::LOGE, C::QB>(r.x, tw);
     store_B<C>(r.x, buf1, jbB);
 }
 template <class K>
-TFHE_HD void phase_F3(FftRegs<K> &r, uint32_t t, const cplx *twC, const cplx *buf1) {
+TFHE_HD void phase_F2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {
+    phase_F2v<K>(r, jbB, pass_tw_base<K::F::QB>(twB_thread, 1), buf0, buf1);
+}
+template <class K>
+TFHE_HD void phase_F3v(FftRegs<K> &r, uint32_t t, const cplx twC_base, const cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NC_TW];
-    load_pass_tw<C::LOGE>(tw, twC + t, C::T);
+    derive_pass_tw<C::LOGE>(tw, twC_base);
     load_C<C>(r.x, buf1, t);
     fwd_pass<C::LOGE, C::LOGE>(r.x, tw);
+}
+template <class K>
+TFHE_HD void phase_F3(FftRegs<K> &r, uint32_t t, const cplx *twC, const cplx *buf1) {
+    phase_F3v<K>(r, t, pass_tw_base<K::F::LOGE>(twC + t, K::F::T), buf1);
 }
 // single-buffer variants: the load half and the store half of a pass are separate phases (a barrier goes between them)
 template <class K>
@@ -434,6 +460,26 @@ TFHE_HD void phase_mac_bmmp(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx 
 //   J1: pass C on both, store_C        | barrier |  J2a: load_B both, pass B  | barrier |  J2b: store_B both  | barrier |
 //   J3: load_A both, pass A, round both, acc += lo + (hi << 16)
 template <class K>
+TFHE_HD void phase_J1v(FftRegs<K> &r, uint32_t t, const cplx twC_base, cplx *buf0, cplx *buf1) {
+    using C = typename K::F;
+    cplx tw[C::NC_TW];
+    derive_pass_tw<C::LOGE>(tw, twC_base);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], tw);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], tw);
+    store_C<C>(r.acc[0], buf0, t);
+    store_C<C>(r.acc[1], buf1, t);
+}
+template <class K>
+TFHE_HD void phase_J2av(FftRegs<K> &r, uint32_t jbB, const cplx twB_base, const cplx *buf0, const cplx *buf1) {
+    using C = typename K::F;
+    cplx tw[C::NB_TW];
+    derive_pass_tw<C::QB>(tw, twB_base);
+    load_B<C>(r.acc[0], buf0, jbB);
+    load_B<C>(r.acc[1], buf1, jbB);
+    inv_pass<C::LOGE, C::QB>(r.acc[0], tw);
+    inv_pass<C::LOGE, C::QB>(r.acc[1], tw);
+}
+template <class K>
 TFHE_HD void phase_J1(FftRegs<K> &r, uint32_t t, const cplx *twC, cplx *buf0, cplx *buf1) {
     using C = typename K::F;
     cplx tw[C::NC_TW];
@@ -471,6 +517,24 @@ TFHE_HD void phase_J3(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *bu
         const uint32_t j = ((uint32_t)e << C::LOGT) | t;
         acc_c[j] += round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
         acc_c[j + K::M] += round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
+    }
+}
+// J3 that also hands the thread's 2E updated accumulator words to the next step in registers
+// (accv[2e + h] = acc_c[((e << LOGT) | t) + h M]): they are the subtrahend of the next step's decomposition
+template <class K>
+TFHE_HD void phase_J3r(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf0, const cplx *buf1, uint32_t *acc_c, uint32_t *accv, double &maxfrac) {
+    using C = typename K::F;
+    load_A<C>(r.acc[0], buf0, t);
+    load_A<C>(r.acc[1], buf1, t);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], twA);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], twA);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+        accv[2 * e] = acc_c[j] + round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
+        accv[2 * e + 1] = acc_c[j + K::M] + round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
+        acc_c[j] = accv[2 * e];
+        acc_c[j + K::M] = accv[2 * e + 1];
     }
 }
 // single-buffer inverse of ONE limb, in place in its accumulator registers:
