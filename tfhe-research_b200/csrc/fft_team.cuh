@@ -394,6 +394,38 @@ TFHE_HD void phase_xstore(const FftRegs<K> &r, uint32_t t, cplx *xbuf) {
 template <class K, bool OWN>
 TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot, const cplx *xbuf, uint32_t h = 0) {
     const cplx *g0 = slot + col * K::MH + t, *g1 = g0 + K::P * K::MH;
+#ifndef TFHE_FFT_MAC_CHUNK
+#define TFHE_FFT_MAC_CHUNK 0
+#endif
+#if TFHE_FFT_MAC_CHUNK
+    // all operands of a chunk of points are requested before the first multiply (more loads in flight per warp)
+    static_for<0, K::HALVES>([&](auto hi) {
+        constexpr int hh = decltype(hi)::value, CHK = TFHE_FFT_MAC_CHUNK;
+        if (h == (uint32_t)hh) {
+#pragma unroll
+            for (int q0 = 0; q0 < K::EH; q0 += CHK) {
+                constexpr int e0 = hh * K::EH;
+                cplx av[CHK], bv[CHK], xs[CHK];
+#pragma unroll
+                for (int u = 0; u < CHK; u++) {
+                    av[u] = g0[(q0 + u) * K::T];
+                    bv[u] = g1[(q0 + u) * K::T];
+                    xs[u] = OWN ? r.x[e0 + q0 + u] : xbuf[(e0 + q0 + u) * K::T + t];
+                }
+#pragma unroll
+                for (int u = 0; u < CHK; u++) {
+                    const int q = q0 + u;
+                    const cplx xv = xs[u], a = av[u], b = bv[u];
+                    r.acc[0][e0 + q].re = fma_d(-xv.im, a.im, fma_d(xv.re, a.re, r.acc[0][e0 + q].re));
+                    r.acc[0][e0 + q].im = fma_d(xv.im, a.re, fma_d(xv.re, a.im, r.acc[0][e0 + q].im));
+                    r.acc[1][e0 + q].re = fma_d(-xv.im, b.im, fma_d(xv.re, b.re, r.acc[1][e0 + q].re));
+                    r.acc[1][e0 + q].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e0 + q].im));
+                }
+            }
+        }
+    });
+    return;
+#endif
     static_for<0, K::HALVES>([&](auto hi) {      // compile-time register indices: h selects which EH of the E points
         constexpr int hh = decltype(hi)::value;
         if (h == (uint32_t)hh) {

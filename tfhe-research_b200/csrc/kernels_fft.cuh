@@ -202,6 +202,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     // the TMA copy of the row that reuses it, so a refill starts the moment the slot's last reader is done.
     constexpr bool OWN_FIRST = (TFHE_FFT_OWNFIRST != 0) && !RL::ON && !BMMP && !K::SINGLE_BUF && K::HALVES == 1 && K::NSLOT >= K::P && !(TFHE_FFT_ABLATE);
     constexpr bool SELF_REFILL = OWN_FIRST && (TFHE_FFT_SELFREFILL != 0);
+#ifndef TFHE_FFT_P2PG
+#define TFHE_FFT_P2PG 0
+#endif
+    constexpr bool P2PG = (TFHE_FFT_P2PG != 0) && !OWN_FIRST && !RL::ON && !(TFHE_FFT_ABLATE);
     // point-to-point row barriers of every team (OWN_FIRST / P2P below): pub[P], rd[P]
     uint64_t *p2p_base = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + RL::BYTES);
     uint64_t *pub = p2p_base + team * 2 * K::P, *rd = pub + K::P;
@@ -273,8 +277,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #ifndef TFHE_FFT_TWREG
 #define TFHE_FFT_TWREG 1
 #endif
-    // a thread's two twiddle-table entries (passes B and C) never change: fetched once, not after every barrier
-    const cplx twB_base = pass_tw_base<C::QB>(twB, 1), twC_base = pass_tw_base<C::LOGE>(twC + t, C::T);
+    // a thread's two twiddle-table entries (passes B and C) never change: fetched once, not after every barrier.  Measured
+    // to pay only with the OWN_FIRST level loop (P1: 71.4 -> 69.8 ms); with the ring-order loop the 8 registers cost more
+    // than the loads (P1: 74.8 -> 79.9 ms, and P0 / the BMMP variant alike), so those keep loading the entries per pass.
+    constexpr bool TW_REG = (TFHE_FFT_TWREG != 0) && (TFHE_FFT_OWNFIRST != 0) && !BMMP && !K::SINGLE_BUF && K::HALVES == 1 && K::NSLOT >= K::P && !(TFHE_FFT_ABLATE) && !(TFHE_FFT_TMEM);
+    cplx twB_base = {}, twC_base = {};
+    if constexpr (TW_REG) {
+        twB_base = pass_tw_base<C::QB>(twB, 1);
+        twC_base = pass_tw_base<C::LOGE>(twC + t, C::T);
+    }
     // operands of the decomposed difference  minuend(p, (j - rot)) - subtrahend(p, j)
     const uint32_t *mbase = acc, *sbase = acc;
 
@@ -480,15 +491,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 store_A<C>(R.x, buf0, t);
                 if constexpr (!SELF_REFILL) { if (producer) pump(it + (uint32_t)K::P); }
                 sub_sync();
-#if TFHE_FFT_TWREG
-                phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
-                sub_sync();
-                phase_F3v<K>(R, t, twC_base, buf1);
-#else
-                phase_F2<K>(R, jbB, twB, buf0, buf1);
-                sub_sync();
-                phase_F3<K>(R, t, twC, buf1);
-#endif
+                if constexpr (TW_REG) {
+                    phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
+                    sub_sync();
+                    phase_F3v<K>(R, t, twC_base, buf1);
+                } else {
+                    phase_F2<K>(R, jbB, twB, buf0, buf1);
+                    sub_sync();
+                    phase_F3<K>(R, t, twC, buf1);
+                }
                 phase_xstore<K>(R, t, buf0);
                 if constexpr (P2P) {
                     __syncwarp();
@@ -514,13 +525,17 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) {
             // forward transform of this sub-team's digit row (polynomial `sub`, level `lev`)
 #if (TFHE_FFT_ABLATE & 1)
-            phase_F1<K>(R, t, sub, 1u, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return 0u; });
+            phase_F1a<K>(R, t, sub, 1u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return 0u; });
 #else
-            if constexpr (BMMP && ACC_REG) phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j, int k) { return accv[k]; });
-            else if constexpr (BMMP) phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return acc[pp * K::N + j]; });
-            else if constexpr (ACC_REG) phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j, int k) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - accv[k]; });
-            else phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
+            if constexpr (BMMP && ACC_REG) phase_F1a<K>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t pp, uint32_t j, int k) { return accv[k]; });
+            else if constexpr (BMMP) phase_F1a<K>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return acc[pp * K::N + j]; });
+            else if constexpr (ACC_REG) phase_F1a<K>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t pp, uint32_t j, int k) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - accv[k]; });
+            else phase_F1a<K>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
+            // rows in ring order; P2PG: point-to-point row barriers instead of the two team-wide barriers of a level (a
+            // sub-team waits for the publisher of the row it is about to read, and for its readers only before it overwrites)
+            if constexpr (P2PG) { if (lv > 0u) mbar_wait(rd + sub, (lv - 1u) & 1u, a.err_flag); }
+            store_A<C>(R.x, buf0, t);
             sub_sync();
             if constexpr (K::SINGLE_BUF) {           // one buffer: a barrier between every load and the next store
                 phase_F2a<K>(R, jbB, twB, buf0);
@@ -530,18 +545,17 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 phase_F3<K>(R, t, twC, buf0);
                 sub_sync();
             } else {
-#if TFHE_FFT_TWREG
-                phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
-                sub_sync();
-                phase_F3v<K>(R, t, twC_base, buf1);
-#else
                 phase_F2<K>(R, jbB, twB, buf0, buf1);
                 sub_sync();
                 phase_F3<K>(R, t, twC, buf1);
-#endif
             }
             phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
-            team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
+            if constexpr (P2PG) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(pub + sub);
+            } else {
+                team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
+            }
 #pragma unroll 1
             for (uint32_t pk = 0; pk < (uint32_t)K::P * KEYS * K::HALVES; pk++) {
                 const uint32_t p = pk / (KEYS * K::HALVES), which = (pk / K::HALVES) % KEYS, half = pk % K::HALVES;
@@ -551,6 +565,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 }
                 const uint32_t s = it % K::NSLOT;
                 if (producer) pump(it + 1);
+                if constexpr (P2PG) { if (p != sub && pk % (KEYS * K::HALVES) == 0u) mbar_wait(pub + p, lv & 1u, a.err_flag); }
                 mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
 #if !(TFHE_FFT_ABLATE & 2)
                 const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
@@ -565,10 +580,17 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 }
 #endif
                 __syncwarp();
-                if (lane == 0) mbar_arrive(empty + s);
+                if (lane == 0) {
+                    mbar_arrive(empty + s);
+                    if constexpr (P2PG) { if (p != sub && pk % (KEYS * K::HALVES) == KEYS * K::HALVES - 1u) mbar_arrive(rd + p); }
+                }
                 it++;
             }
-            team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
+            if constexpr (P2PG) lv++;
+            else team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
+        }
+        if constexpr ((OWN_FIRST && (TFHE_FFT_P2P != 0)) || P2PG) {
+            if (lv > 0u) mbar_wait(rd + sub, (lv - 1u) & 1u, a.err_flag);   // the last published row has been read
         }
 #if !(TFHE_FFT_ABLATE & 16)
         // inverse transforms of this sub-team's column: the low- and high-limb products together (fft_team.cuh phase_J*)
@@ -591,18 +613,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             sub_sync();
             phase_K3_hi<K>(R, t, a.tw.twA, buf0, lo, acc + sub * K::N, maxfrac);
         } else {
-            if constexpr (OWN_FIRST && (TFHE_FFT_P2P != 0)) {
-                if (lv > 0u) mbar_wait(rd + sub, (lv - 1u) & 1u, a.err_flag);   // the last published row has been read
+            if constexpr (TW_REG) {
+                phase_J1v<K>(R, t, twC_base, buf0, buf1);
+                sub_sync();
+                phase_J2av<K>(R, jbB, twB_base, buf0, buf1);
+            } else {
+                phase_J1<K>(R, t, twC, buf0, buf1);
+                sub_sync();
+                phase_J2a<K>(R, jbB, twB, buf0, buf1);
             }
-#if TFHE_FFT_TWREG
-            phase_J1v<K>(R, t, twC_base, buf0, buf1);
-            sub_sync();
-            phase_J2av<K>(R, jbB, twB_base, buf0, buf1);
-#else
-            phase_J1<K>(R, t, twC, buf0, buf1);
-            sub_sync();
-            phase_J2a<K>(R, jbB, twB, buf0, buf1);
-#endif
             if constexpr (!SELF_REFILL) { if (producer) pump(0); }   // ring entries freed by slower teams: refill them while this team inverts
             sub_sync();
             phase_J2b<K>(R, jbB, buf0, buf1);
