@@ -274,9 +274,7 @@ TFHE_HD void phase_F1a(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, type
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t j = (((uint32_t)e << C::LOGT) | t) + (uint32_t)h * K::M;
-                // optional third argument: 2e + h, the position among this thread's coefficients (register-resident operands)
-                if constexpr (std::is_invocable<DiffFn, uint32_t, uint32_t, int>::value) decompose_signed<K::LOGB, K::L>(diff(p, j, 2 * e + h), d[h]);
-                else decompose_signed<K::LOGB, K::L>(diff(p, j), d[h]);
+                decompose_signed<K::LOGB, K::L>(diff(p, j), d[h]);
             }
 #pragma unroll
             for (int l = 1; l < K::L; l++)
@@ -394,38 +392,6 @@ TFHE_HD void phase_xstore(const FftRegs<K> &r, uint32_t t, cplx *xbuf) {
 template <class K, bool OWN>
 TFHE_HD void phase_mac(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx *slot, const cplx *xbuf, uint32_t h = 0) {
     const cplx *g0 = slot + col * K::MH + t, *g1 = g0 + K::P * K::MH;
-#ifndef TFHE_FFT_MAC_CHUNK
-#define TFHE_FFT_MAC_CHUNK 0
-#endif
-#if TFHE_FFT_MAC_CHUNK
-    // all operands of a chunk of points are requested before the first multiply (more loads in flight per warp)
-    static_for<0, K::HALVES>([&](auto hi) {
-        constexpr int hh = decltype(hi)::value, CHK = TFHE_FFT_MAC_CHUNK;
-        if (h == (uint32_t)hh) {
-#pragma unroll
-            for (int q0 = 0; q0 < K::EH; q0 += CHK) {
-                constexpr int e0 = hh * K::EH;
-                cplx av[CHK], bv[CHK], xs[CHK];
-#pragma unroll
-                for (int u = 0; u < CHK; u++) {
-                    av[u] = g0[(q0 + u) * K::T];
-                    bv[u] = g1[(q0 + u) * K::T];
-                    xs[u] = OWN ? r.x[e0 + q0 + u] : xbuf[(e0 + q0 + u) * K::T + t];
-                }
-#pragma unroll
-                for (int u = 0; u < CHK; u++) {
-                    const int q = q0 + u;
-                    const cplx xv = xs[u], a = av[u], b = bv[u];
-                    r.acc[0][e0 + q].re = fma_d(-xv.im, a.im, fma_d(xv.re, a.re, r.acc[0][e0 + q].re));
-                    r.acc[0][e0 + q].im = fma_d(xv.im, a.re, fma_d(xv.re, a.im, r.acc[0][e0 + q].im));
-                    r.acc[1][e0 + q].re = fma_d(-xv.im, b.im, fma_d(xv.re, b.re, r.acc[1][e0 + q].re));
-                    r.acc[1][e0 + q].im = fma_d(xv.im, b.re, fma_d(xv.re, b.im, r.acc[1][e0 + q].im));
-                }
-            }
-        }
-    });
-    return;
-#endif
     static_for<0, K::HALVES>([&](auto hi) {      // compile-time register indices: h selects which EH of the E points
         constexpr int hh = decltype(hi)::value;
         if (h == (uint32_t)hh) {
@@ -549,24 +515,6 @@ TFHE_HD void phase_J3(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *bu
         const uint32_t j = ((uint32_t)e << C::LOGT) | t;
         acc_c[j] += round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
         acc_c[j + K::M] += round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
-    }
-}
-// J3 that also hands the thread's 2E updated accumulator words to the next step in registers
-// (accv[2e + h] = acc_c[((e << LOGT) | t) + h M]): they are the subtrahend of the next step's decomposition
-template <class K>
-TFHE_HD void phase_J3r(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf0, const cplx *buf1, uint32_t *acc_c, uint32_t *accv, double &maxfrac) {
-    using C = typename K::F;
-    load_A<C>(r.acc[0], buf0, t);
-    load_A<C>(r.acc[1], buf1, t);
-    inv_pass<C::LOGE, C::LOGE>(r.acc[0], twA);
-    inv_pass<C::LOGE, C::LOGE>(r.acc[1], twA);
-#pragma unroll
-    for (int e = 0; e < K::E; e++) {
-        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
-        accv[2 * e] = acc_c[j] + round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
-        accv[2 * e + 1] = acc_c[j + K::M] + round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
-        acc_c[j] = accv[2 * e];
-        acc_c[j + K::M] = accv[2 * e + 1];
     }
 }
 // single-buffer inverse of ONE limb, in place in its accumulator registers:

@@ -187,7 +187,7 @@ using KF0C = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, true>;
 using KF2 = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, false, true, 2>;
 using KF2C = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2>;
 template <class K>
-constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + fft::KeyRelay<K, false>::BYTES + (size_t)K::CTS * 2 * K::P * 8 + 16; }
+constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 16; }
 // the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
 // resident ciphertext, which bounds the LWE dimension (P1 shape: n <= 1151, P0 shape: n <= 2111; above that the NTT path serves)
 bool fft_available(int pbs_id, size_t n = 0) {
