@@ -17,6 +17,8 @@ cpu_baseline / --impl reference: the C restatement of the reference's Rust path 
          Toeplitz O(N^2) algorithm, one PBS per host thread) -- the Rust crate cannot be built here.
 """
 import argparse
+import contextlib
+import io
 import json
 import os
 import subprocess
@@ -372,5 +374,25 @@ def main():
         dist.destroy_process_group()
 
 
+def _main_with_clean_stdout():
+    """stdout carries exactly ONE JSON line: while the benchmark runs, file descriptor 1 points at stderr, so anything a
+    library writes to stdout from C (NCCL prints its version banner there on some boxes) cannot precede the line."""
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    out = buf.getvalue()
+    if out:
+        sys.stdout.write(out)
+        sys.stdout.flush()
+
+
 if __name__ == "__main__":
-    main()
+    _main_with_clean_stdout()
