@@ -105,6 +105,15 @@ uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx);
 #define TFHE_PATH_FFT 1
 int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path);
 int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx);
+/* Arithmetic of the key-switching product key_switching.rs:88 (out = -D . KSK mod 2^32), batches above 8 ciphertexts
+ * (both give the reference's bits):
+ *   TFHE_KS_IMAD  wrapping 32-bit multiply-adds on the integer pipe, every parameter set;
+ *   TFHE_KS_MMA   integer tensor cores, exact through the four byte planes of the key (s8 x u8 -> s32 sums, recombined
+ *                 mod 2^32); needs k*N*ks_levels % 64 == 0 and k*N*ks_levels * 2^ks_log_base * 255 < 2^31, else IMAD runs.
+ * Default: env TFHE_B200_KS=imad|mma, else MMA where it applies.  May be switched at any time. */
+#define TFHE_KS_IMAD 0
+#define TFHE_KS_MMA 1
+int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path);
 /* FFT path only.  Exactness rests on the a-priori error bound (2^-9 before rounding).  With checking
  * switched on (env TFHE_B200_FFT_CHECK=1 or tfhe_ctx_set_fft_check) the blind rotation runs a kernel variant that also
  * records the largest distance to the nearest integer of every value it rounds (about 5 % slower);

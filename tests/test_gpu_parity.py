@@ -142,6 +142,33 @@ def test_blind_rotate_extract_keyswitch_bootstrap(preset, n):
         assert np.array_equal(e.ctx.bootstrap(e.bk, cts[:nb], tvs, idx[:nb]), out[:nb]), nb
 
 
+@pytest.mark.parametrize("preset,n", [("P1:fft", 21), ("P0:fft", 7), ("P2:fft", 5), ("P1:fft", 630)])
+def test_key_switch_tensor_core_path_vs_imad_vs_oracle(preset, n):
+    """key_switching.rs:63-103 on arbitrary input words: the integer-tensor-core product (byte planes, KS_MMA) and the
+    32-bit multiply-add product (KS_IMAD) give the oracle's bits, for ragged batch sizes and extreme words."""
+    import ctypes as C
+    e = env(preset, n)
+    L = orc.lib()
+    rng = np.random.default_rng(17)
+    kN = e.p.k * e.p.N
+    for B in (9, 130, 301):
+        lwe = r32(rng, B, kN + 1)
+        lwe[0, :] = 0xFFFFFFFF                        # rounding wraps to 0 (decomposer.rs:39)
+        lwe[1, :] = 0x7FFFFFFF
+        lwe[2, :kN:2] = 0x80000000
+        lwe[3, :] = 0xF8F8F8F8                        # windows of B-1 with carries: digit +B (SURVEY 9-B H3)
+        e.ctx.set_ks_path(T.KS_MMA)
+        got_mma = e.ctx.key_switch(e.bk, lwe)
+        e.ctx.set_ks_path(T.KS_IMAD)
+        got_imad = e.ctx.key_switch(e.bk, lwe)
+        e.ctx.set_ks_path(T.KS_MMA)
+        assert np.array_equal(got_mma, got_imad), B
+        for b in (0, 1, 2, 3, B - 1):
+            exp = orc.z(n + 1)
+            L.orc_key_switch_lwe(C.byref(e.o), lwe[b], e.ksk, exp)
+            assert np.array_equal(got_mma[b], exp), (B, b)
+
+
 @pytest.mark.parametrize("preset,n", [("P0:ntt", 4), ("P1:ntt", 3), ("P1:fft", 3), ("P0:fft", 4)])
 def test_gates_boolean_rs(preset, n):
     e = env(preset, n)

@@ -30,6 +30,7 @@ _DEPS = _SOURCES + ["kernels.cuh", "pbs_team.cuh", "tfhe_core.cuh", "host_tables
 TFHE_OK, TFHE_E_PARAM, TFHE_E_CUDA, TFHE_E_OOM, TFHE_E_ASSERT, TFHE_E_NCCL = 0, -1, -2, -3, -4, -5
 AND, OR, XOR, NAND, NOR, XNOR = range(6)
 PATH_NTT, PATH_FFT = 0, 1   # arithmetic path of the external product (include/tfhe_b200.h TFHE_PATH_*)
+KS_IMAD, KS_MMA = 0, 1      # arithmetic of the key-switching product (include/tfhe_b200.h TFHE_KS_*)
 
 
 class TfheError(RuntimeError):
@@ -109,7 +110,7 @@ def lib():
         "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP], "tfhe_keygen_bmmp": [PP, C.c_uint64, VP, VP, VP, VP],
         "tfhe_bk_upload_bmmp": [VP, VP, VP, C.POINTER(VP)],
         "tfhe_ctx_create": [PP, C.c_int, C.POINTER(VP)], "tfhe_ctx_set_stream": [VP, VP],
-        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_fft_check": [VP, C.c_int],
+        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_ks_path": [VP, C.c_int], "tfhe_ctx_set_fft_check": [VP, C.c_int],
         "tfhe_fft_rounding_margin": [VP, C.POINTER(C.c_double)],
         "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)], "tfhe_bk_read_transformed": [VP, VP, SZ],
         "tfhe_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP],
@@ -146,7 +147,7 @@ EXPORTS = [
     "tfhe_ctx_launch_count", "tfhe_bk_upload", "tfhe_bk_free", "tfhe_bootstrap_batch", "tfhe_gate_batch",
     "tfhe_gates_batch", "tfhe_switch_modulus", "tfhe_decompose", "tfhe_glwe_mul_monomial", "tfhe_external_product",
     "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
-    "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
+    "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_ctx_set_ks_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
     "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed", "tfhe_bootstrap_batch_ks_first", "tfhe_gate_k_batch",
     "tfhe_file_write", "tfhe_file_read", "tfhe_keygen_bmmp", "tfhe_bk_upload_bmmp",
 ]
@@ -341,6 +342,10 @@ class Context:
     def set_pbs_path(self, path: int):
         """PATH_NTT (2-prime integer NTT) or PATH_FFT (exact FP64 FFT, limb-split key); call before upload_key."""
         self._ck(lib().tfhe_ctx_set_pbs_path(self._h, int(path)))
+
+    def set_ks_path(self, path: int):
+        """KS_IMAD (32-bit multiply-adds) or KS_MMA (integer tensor cores, exact through byte planes); same bits."""
+        self._ck(lib().tfhe_ctx_set_ks_path(self._h, int(path)))
 
     @property
     def pbs_path(self) -> int:

@@ -375,6 +375,127 @@ __global__ void __launch_bounds__(KS_THREADS) ks_gemm_kernel(const int8_t *__res
     }
 }
 
+// ------------------------------------------------------------------------------------------ K4-MMA
+// The same wrapping-u32 product on the integer tensor cores, exactly.  key_switching.rs:88 is a matrix product
+// (ndarray `dot`): out[b][c] = -sum_r D[b][r] KSK[r][c] mod 2^32 with small signed digits D.  Every key word is the sum
+// of its four bytes, KSK[r][c] = sum_pl 2^(8 pl) byte_pl(r, c), so
+//     sum_r D[b][r] KSK[r][c]  =  sum_pl 2^(8 pl) * ( sum_r D[b][r] byte_pl(r, c) )          (mod 2^32)
+// and each inner sum is an s8 x u8 dot product whose magnitude KD * max|D| * 255 stays below 2^31 (checked on the
+// host), i.e. exactly what mma.sync.m16n8k32.s32.s8.u8 computes with its 32-bit accumulators -- no rounding anywhere,
+// the same bits as the IMAD kernel above.  A = digits [B][KD] (row-major, as ks_digits_kernel writes them); B = the
+// byte-transposed key KSKt[c*4 + pl][KD] (k contiguous per byte column, built once at key upload).
+// CTA: 128 ciphertexts x 128 byte columns (= 32 key columns), 8 warps as 4 x 2, each 32 x 64; BK = 64 digits per stage,
+// 3-stage cp.async ring, operands through ldmatrix (rows padded to 80 B: conflict-free).
+constexpr int KM_BM = 128, KM_BN = 128, KM_BK = 64, KM_STAGES = 3, KM_THREADS = 256, KM_ROW = KM_BK + 16;
+constexpr int KM_SMEM = KM_STAGES * (KM_BM + KM_BN) * KM_ROW;
+__global__ void ksk_byte_transpose_kernel(const uint32_t *__restrict__ ksk, uint8_t *__restrict__ kskt, uint32_t KD, uint32_t stride) {
+    // one thread: key column c, four consecutive rows r..r+3 -> one 32-bit word of each of the four byte-plane rows
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y * 4;
+    if (c >= stride) return;
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) w[i] = ksk[(size_t)(r + i) * stride + c];
+#pragma unroll
+    for (int pl = 0; pl < 4; pl++) {
+        const uint32_t v = ((w[0] >> (8 * pl)) & 255u) | (((w[1] >> (8 * pl)) & 255u) << 8) | (((w[2] >> (8 * pl)) & 255u) << 16) | (((w[3] >> (8 * pl)) & 255u) << 24);
+        *reinterpret_cast<uint32_t *>(kskt + (size_t)(c * 4 + pl) * KD + r) = v;
+    }
+}
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void *p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_s8u8(int32_t (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(KM_THREADS, 2) ks_mma_kernel(const int8_t *__restrict__ digits, const uint8_t *__restrict__ kskt,
+                                                               const uint32_t *__restrict__ body, uint32_t *__restrict__ out,
+                                                               uint32_t KD, uint32_t n, uint32_t batch) {
+    extern __shared__ __align__(128) uint8_t ksm[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t wm = warp & 3, wn = warp >> 2;                 // warp tile: rows wm*32.., byte columns wn*64..
+    const uint32_t b0 = blockIdx.y * KM_BM, n0 = blockIdx.x * KM_BN;
+    auto stageA = [&](int st) { return ksm + (size_t)st * (KM_BM + KM_BN) * KM_ROW; };
+    auto stageB = [&](int st) { return stageA(st) + KM_BM * KM_ROW; };
+    // loader: 2 x (128 rows x 4 chunks of 16 B) per operand and stage; rows beyond the batch re-read its last row (never stored)
+    auto load_stage = [&](int st, uint32_t k0) {
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const uint32_t idx = tid + i * KM_THREADS, row = idx >> 2, ch = idx & 3;
+            const uint32_t br = min(b0 + row, batch - 1u);
+            cp_async16(stageA(st) + row * KM_ROW + ch * 16, digits + (size_t)br * KD + k0 + ch * 16);
+            cp_async16(stageB(st) + row * KM_ROW + ch * 16, kskt + (size_t)(n0 + row) * KD + k0 + ch * 16);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int32_t acc[2][8][4];
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[i][j][q] = 0;
+    const uint32_t nk = KD / KM_BK;
+#pragma unroll
+    for (int st = 0; st < KM_STAGES - 1; st++) {
+        if ((uint32_t)st < nk) load_stage(st, st * KM_BK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ldmatrix row addresses of this lane (see the fragment layouts of mma.m16n8k32 with 8-bit operands):
+    //   A x4 = {rows 0-7 | k 0-15, rows 8-15 | k 0-15, rows 0-7 | k 16-31, rows 8-15 | k 16-31}  = a0..a3
+    //   B x4 = {n-tile j | k 0-15, n-tile j | k 16-31, n-tile j+1 | k 0-15, n-tile j+1 | k 16-31} = b0, b1 of two tiles
+    const uint32_t a_row = wm * 32 + (lane & 7) + ((lane >> 3) & 1) * 8, a_kb = (lane >> 4) * 16;
+    const uint32_t b_row = wn * 64 + (lane >> 4) * 8 + (lane & 7), b_kb = ((lane >> 3) & 1) * 16;
+    for (uint32_t kt = 0; kt < nk; kt++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(KM_STAGES - 2) : "memory");
+        __syncthreads();                                            // stage kt has landed; stage kt-1 is free again
+        if (kt + KM_STAGES - 1 < nk) load_stage((kt + KM_STAGES - 1) % KM_STAGES, (kt + KM_STAGES - 1) * KM_BK);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const uint8_t *sA = stageA(kt % KM_STAGES), *sB = stageB(kt % KM_STAGES);
+#pragma unroll
+        for (int ks = 0; ks < KM_BK / 32; ks++) {
+            uint32_t af[2][4];
+#pragma unroll
+            for (int i = 0; i < 2; i++) ldmatrix_x4(af[i], sA + (a_row + i * 16) * KM_ROW + ks * 32 + a_kb);
+#pragma unroll
+            for (int jp = 0; jp < 4; jp++) {
+                uint32_t bf[4];
+                ldmatrix_x4(bf, sB + (b_row + jp * 16) * KM_ROW + ks * 32 + b_kb);
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    mma_s8u8(acc[i][2 * jp], af[i], bf[0], bf[1]);
+                    mma_s8u8(acc[i][2 * jp + 1], af[i], bf[2], bf[3]);
+                }
+            }
+        }
+    }
+    // epilogue.  c-fragment: rows g / g+8 (g = lane/4), byte columns 2 tg, 2 tg + 1 (tg = lane%4) of each 8-wide tile, i.e.
+    // byte planes {0,1} (tg even) or {2,3} (tg odd) of key column (n0 + wn*64 + 8 j)/4 + tg/2: lanes tg and tg^1 hold the
+    // two halves of one output word.  After the exchange the even lane stores row g, the odd lane row g+8.
+    const uint32_t g = lane >> 2, tg = lane & 3, ncols = n + 1;
+#pragma unroll
+    for (int i = 0; i < 2; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t sh = (tg & 1u) * 16u;
+            const uint32_t lo = ((uint32_t)acc[i][j][0] << sh) + ((uint32_t)acc[i][j][1] << (sh + 8u));   // row g
+            const uint32_t hi = ((uint32_t)acc[i][j][2] << sh) + ((uint32_t)acc[i][j][3] << (sh + 8u));   // row g + 8
+            const uint32_t lo_o = __shfl_xor_sync(0xFFFFFFFFu, lo, 1), hi_o = __shfl_xor_sync(0xFFFFFFFFu, hi, 1);
+            const uint32_t sum = (tg & 1u) ? hi + hi_o : lo + lo_o;
+            const uint32_t b = b0 + wm * 32 + i * 16 + g + (tg & 1u) * 8u;
+            const uint32_t c = (n0 + wn * 64 + j * 8) / 4 + (tg >> 1);
+            if (b < batch && c < ncols) {
+                uint32_t v = 0u - sum;                    // key_switching.rs:96 negate
+                if (c == n) v += body[b];                 // key_switching.rs:98-100
+                out[(size_t)b * ncols + c] = v;
+            }
+        }
+}
+
 // Small-batch key switch (latency path): the KSK (tens of MB) is the only traffic that matters, so the rows are
 // split over many CTAs and partial sums are combined with u32 atomics (addition mod 2^32 is associative, so the
 // result is bit-identical to the sequential reference sum).  out must be pre-initialised by ks_init_kernel.

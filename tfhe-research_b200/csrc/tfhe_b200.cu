@@ -43,6 +43,7 @@ struct tfhe_ctx {
     int pbs_id = -1, ks_id = -1;
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
+    bool ks_mma = true;                     // key switch on the integer tensor cores where the key has a byte-plane copy
     fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
@@ -71,6 +72,7 @@ struct tfhe_bk {
     uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]                      (TFHE_PATH_NTT)
     fft::cplx *d_bsk_fft = nullptr; // [n][ROWS][2 limbs][P][N/2], scaled 2/N  (TFHE_PATH_FFT)
     uint32_t *d_ksk = nullptr;      // [kN*l_ks][ksk_stride], ksk_stride = n+1 rounded up to 128 words, zero padded
+    uint8_t *d_ksk_t = nullptr;     // [ksk_stride*4][kN*l_ks] byte planes, k contiguous (ks_mma_kernel); null if not applicable
     size_t ksk_stride = 0;
 };
 
@@ -320,6 +322,14 @@ int run_key_switch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *src, int fr
         ctx->launches += 3;
         return TFHE_OK;
     }
+    if (bk->d_ksk_t && ctx->ks_mma) {
+        // integer tensor cores, exact through byte planes (kernels.cuh K4-MMA)
+        dim3 grid((unsigned)(bk->ksk_stride * 4 / KM_BN), (unsigned)((batch + KM_BM - 1) / KM_BM));
+        ks_mma_kernel<<<grid, KM_THREADS, KM_SMEM, ctx->stream>>>(dg, bk->d_ksk_t, bd, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch);
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        return TFHE_OK;
+    }
     dim3 grid((unsigned)((ctx->n() + 1 + KS_BN - 1) / KS_BN), (unsigned)((batch + KS_BM - 1) / KS_BM));
     if (KD % KS_BK) return fail(ctx, TFHE_E_PARAM, "k*N*ks_levels must be a multiple of 32");
     ks_gemm_kernel<<<grid, KS_THREADS, 0, ctx->stream>>>(dg, bk->d_ksk, bd, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch, (uint32_t)bk->ksk_stride);
@@ -336,9 +346,21 @@ cudaError_t alloc_ksk(tfhe_ctx *ctx, tfhe_bk *bk) {
     return e;
 }
 cudaError_t copy_ksk(tfhe_ctx *ctx, tfhe_bk *bk, const uint32_t *ksk) {
-    const size_t row = (ctx->n() + 1) * 4;
-    return cudaMemcpy2DAsync(bk->d_ksk, bk->ksk_stride * 4, ksk, row, row, ctx->kd(),
-                             is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    const size_t row = (ctx->n() + 1) * 4, KD = ctx->kd();
+    cudaError_t e = cudaMemcpy2DAsync(bk->d_ksk, bk->ksk_stride * 4, ksk, row, row, KD,
+                                      is_device_ptr(ksk) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) return e;
+    // byte-plane copy for the tensor-core key switch: needs whole 64-digit stages and s8 x u8 sums that fit 32 bits
+    const double bound = (double)KD * (double)(1u << ctx->p.ks_log_base) * 255.0;
+    if (KD % KM_BK == 0 && ctx->p.ks_log_base <= 6 && bound < 2147483648.0) {
+        if ((e = cudaMalloc(&bk->d_ksk_t, bk->ksk_stride * 4 * KD)) != cudaSuccess) return e;
+        dim3 grid((unsigned)((bk->ksk_stride + 127) / 128), (unsigned)(KD / 4));
+        ksk_byte_transpose_kernel<<<grid, 128, 0, ctx->stream>>>(bk->d_ksk, bk->d_ksk_t, (uint32_t)KD, (uint32_t)bk->ksk_stride);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM)) != cudaSuccess) return e;
+        ctx->launches++;
+    }
+    return cudaSuccess;
 }
 
 int check_bk(tfhe_ctx *ctx, const tfhe_bk *bk) {
@@ -467,6 +489,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         ctx->path = TFHE_DEFAULT_PATH;
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
+    if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_mma = strcmp(e, "imad") != 0;
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
         if (!strcmp(e, "fft") && fft_available(ctx->pbs_id, ctx->n())) ctx->path = TFHE_PATH_FFT;
         if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
@@ -514,6 +537,12 @@ int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path) {
     return fail(ctx, TFHE_E_PARAM, "arithmetic path not instantiated for this parameter set");
 }
 int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx) { return ctx ? ctx->path : TFHE_E_PARAM; }
+int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path) {
+    if (!ctx) return TFHE_E_PARAM;
+    if (path != TFHE_KS_IMAD && path != TFHE_KS_MMA) return fail(ctx, TFHE_E_PARAM, "unknown key-switch path");
+    ctx->ks_mma = path == TFHE_KS_MMA;
+    return TFHE_OK;
+}
 int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on) {
     if (!ctx) return TFHE_E_PARAM;
     ctx->fft_check = on != 0;
@@ -614,6 +643,7 @@ void tfhe_bk_free(tfhe_bk *bk) {
     if (bk->d_bsk_ntt) cudaFree(bk->d_bsk_ntt);
     if (bk->d_bsk_fft) cudaFree(bk->d_bsk_fft);
     if (bk->d_ksk) cudaFree(bk->d_ksk);
+    if (bk->d_ksk_t) cudaFree(bk->d_ksk_t);
     delete bk;
 }
 
