@@ -260,21 +260,25 @@ TFHE_HD int32_t key_limb(uint32_t g, int limb) {
 // decomposition (decomposer.rs:27-80) of a thread's 2E coefficients is done once per polynomial, at level 0; the
 // other levels' digits wait in a thread-private stash (no barrier: written and read by the same thread).
 // F1 = F1a (registers only: digits, pass A) followed by store_A into buf0.
-template <class K, class DiffFn>
+// WHICH: 0 = any level (run-time test), 1 = the caller knows lev == 0, 2 = the caller knows lev > 0 (then diff is not used:
+// a level loop peeled this way does not keep the operands of diff alive across the later levels)
+template <class K, int WHICH = 0, class DiffFn>
 TFHE_HD void phase_F1a(FftRegs<K> &r, uint32_t t, uint32_t p, uint32_t lev, typename K::stash_t *stash, const cplx *twA, DiffFn diff) {
     using C = typename K::F;
     // stash word = the two digits (coefficients j and j + M: real and imaginary part of point e) of one level
     using pair_t = typename std::conditional<sizeof(typename K::stash_t) == 1, uint16_t, uint32_t>::type;
     constexpr int SB = 8 * (int)sizeof(typename K::stash_t);
     pair_t *sp = reinterpret_cast<pair_t *>(stash);
-    if (lev == 0) {
+    if (WHICH == 1 || (WHICH == 0 && lev == 0)) {
 #pragma unroll
         for (int e = 0; e < K::E; e++) {
             int32_t d[2][K::L];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const uint32_t j = (((uint32_t)e << C::LOGT) | t) + (uint32_t)h * K::M;
-                decompose_signed<K::LOGB, K::L>(diff(p, j), d[h]);
+                // optional third argument: 2e + h, the position among this thread's coefficients (register-resident operands)
+                if constexpr (std::is_invocable<DiffFn, uint32_t, uint32_t, int>::value) decompose_signed<K::LOGB, K::L>(diff(p, j, 2 * e + h), d[h]);
+                else decompose_signed<K::LOGB, K::L>(diff(p, j), d[h]);
             }
 #pragma unroll
             for (int l = 1; l < K::L; l++)
@@ -515,6 +519,24 @@ TFHE_HD void phase_J3(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *bu
         const uint32_t j = ((uint32_t)e << C::LOGT) | t;
         acc_c[j] += round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
         acc_c[j + K::M] += round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
+    }
+}
+// J3 that also hands the thread's 2E updated accumulator words to the next step in registers
+// (accv[2e + h] = acc_c[((e << LOGT) | t) + h M]): they are the subtrahend of the next step's decomposition
+template <class K>
+TFHE_HD void phase_J3r(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf0, const cplx *buf1, uint32_t *acc_c, uint32_t *accv, double &maxfrac) {
+    using C = typename K::F;
+    load_A<C>(r.acc[0], buf0, t);
+    load_A<C>(r.acc[1], buf1, t);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], twA);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], twA);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+        accv[2 * e] = acc_c[j] + round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
+        accv[2 * e + 1] = acc_c[j + K::M] + round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
+        acc_c[j] = accv[2 * e];
+        acc_c[j + K::M] = accv[2 * e + 1];
     }
 }
 // single-buffer inverse of ONE limb, in place in its accumulator registers:

@@ -185,6 +185,16 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     FftRegs<K> R;
     double maxfrac = 0.0;
     uint32_t it = 0;   // position in the key stream (the same sequence in every warp)
+    // OWN_FIRST: the 2E words of acc[sub] this thread decomposes are the ones it updates; they cross the step boundary in registers
+    uint32_t accv[2 * K::E];
+    if constexpr (OWN_FIRST) {
+#pragma unroll
+        for (int e = 0; e < K::E; e++) {
+            const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+            accv[2 * e] = sbase[sub * K::N + j];
+            accv[2 * e + 1] = sbase[sub * K::N + j + K::M];
+        }
+    }
 
     // ---- key stream.  Ring-order loop: thread 0 issues the TMA bulk copies (SASS UBLKCP) in consumption order, up to
     // NSLOT slots ahead of its own position; pump(need) returns with slots [0, need) issued (blocking on the ring's
@@ -260,10 +270,20 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) release_slot(ir);
             };
-#pragma unroll 1
-            for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) {
+#ifndef TFHE_FFT_ACCREG
+#define TFHE_FFT_ACCREG 1
+#endif
+            auto level = [&](auto first_c, uint32_t lev) {
+                constexpr bool FIRST = decltype(first_c)::value;
+#if TFHE_FFT_ACCREG
+                // level 0 is peeled off the loop: the subtrahend of the decomposition comes from accv (registers, handed over
+                // by the previous step's J3), and accv is dead from here to the end of the step
+                if constexpr (FIRST) phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j, int k) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - accv[k]; });
+                else phase_F1a<K, 2>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t, uint32_t) { return 0u; });
+#else
                 phase_F1a<K>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
-                if (lev > 0) team_bar_id(team_bar, K::TEAM_THREADS);   // the row published at the previous level has been read
+#endif
+                if (!FIRST) team_bar_id(team_bar, K::TEAM_THREADS);   // the row published at the previous level has been read
                 store_A<C>(R.x, buf0, t);
                 sub_sync();
                 phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
@@ -276,7 +296,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 for (uint32_t p = 0; p < (uint32_t)K::P; p++)
                     if (p != sub) mac_slot(p);
                 it += (uint32_t)K::P;
-            }
+            };
+#if TFHE_FFT_ACCREG
+            level(std::true_type{}, 0u);
+#pragma unroll 1
+            for (uint32_t lev = 1; lev < (uint32_t)K::L; lev++) level(std::false_type{}, lev);
+#else
+#pragma unroll 1
+            for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) level(std::false_type{}, lev);
+#endif
             team_bar_id(team_bar, K::TEAM_THREADS);      // the last published rows have been read: buf0 may be overwritten
         } else {
 #pragma unroll 1
@@ -362,7 +390,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             sub_sync();
             phase_J2b<K>(R, jbB, buf0, buf1);
             sub_sync();
+#if TFHE_FFT_ACCREG
+            if constexpr (OWN_FIRST) phase_J3r<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, accv, maxfrac);
+            else phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
+#else
             phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
+#endif
         }
 #endif
         sub_sync();   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
