@@ -82,6 +82,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 #ifndef TFHE_FFT_OWNFIRST
 #define TFHE_FFT_OWNFIRST 1
 #endif
+#ifndef TFHE_FFT_ACCREG
+#define TFHE_FFT_ACCREG 1
+#endif
 template <class K, bool BMMP = false>
 __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_constant__ FftArgs a) {
     using C = typename K::F;
@@ -185,9 +188,14 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     FftRegs<K> R;
     double maxfrac = 0.0;
     uint32_t it = 0;   // position in the key stream (the same sequence in every warp)
-    // OWN_FIRST: the 2E words of acc[sub] this thread decomposes are the ones it updates; they cross the step boundary in registers
+    // the 2E words of acc[sub] this thread decomposes are the ones it updates: they cross the step boundary in registers
+    // (not with the single exchange buffer of N = 2048, which is out of registers)
+#ifndef TFHE_FFT_ACCREG_G
+#define TFHE_FFT_ACCREG_G 1
+#endif
+    constexpr bool ACC_REG = (TFHE_FFT_ACCREG != 0) && (OWN_FIRST || ((TFHE_FFT_ACCREG_G != 0) && !K::SINGLE_BUF && !(TFHE_FFT_ABLATE)));
     uint32_t accv[2 * K::E];
-    if constexpr (OWN_FIRST) {
+    if constexpr (ACC_REG) {
 #pragma unroll
         for (int e = 0; e < K::E; e++) {
             const uint32_t j = ((uint32_t)e << C::LOGT) | t;
@@ -260,19 +268,16 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
         zero_acc<K>(R);
         if constexpr (OWN_FIRST) {
-            auto mac_slot = [&](uint32_t p) {   // ring row it + p = GGSW row (polynomial p, this level)
+            auto mac_slot = [&](auto own_c, uint32_t p) {   // ring row it + p = GGSW row (polynomial p, this level)
+                constexpr bool OWN = decltype(own_c)::value;
                 const uint32_t ir = it + p, s = ir % K::NSLOT;
                 mbar_wait(full + s, (ir / K::NSLOT) & 1u, a.err_flag);
                 const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
                 const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
-                if (p == sub) phase_mac<K, true>(R, t, sub, slot, nullptr, 0u);
-                else phase_mac<K, false>(R, t, sub, slot, peer, 0u);
+                phase_mac<K, OWN>(R, t, sub, slot, peer, 0u);
                 __syncwarp();
                 if (lane == 0) release_slot(ir);
             };
-#ifndef TFHE_FFT_ACCREG
-#define TFHE_FFT_ACCREG 1
-#endif
             auto level = [&](auto first_c, uint32_t lev) {
                 constexpr bool FIRST = decltype(first_c)::value;
 #if TFHE_FFT_ACCREG
@@ -290,11 +295,11 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 sub_sync();
                 phase_F3v<K>(R, t, twC_base, buf1);
                 phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
-                mac_slot(sub);
+                mac_slot(std::true_type{}, sub);
                 team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
 #pragma unroll 1
                 for (uint32_t p = 0; p < (uint32_t)K::P; p++)
-                    if (p != sub) mac_slot(p);
+                    if (p != sub) mac_slot(std::false_type{}, p);
                 it += (uint32_t)K::P;
             };
 #if TFHE_FFT_ACCREG
@@ -307,15 +312,20 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #endif
             team_bar_id(team_bar, K::TEAM_THREADS);      // the last published rows have been read: buf0 may be overwritten
         } else {
-#pragma unroll 1
-            for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) {
-                // forward transform of this sub-team's digit row (polynomial `sub`, level `lev`)
+            auto level = [&](auto first_c, uint32_t lev) {
+                constexpr bool FIRST = decltype(first_c)::value;
+                // forward transform of this sub-team's digit row (polynomial `sub`, level `lev`); level 0 is peeled off the
+                // loop so that its operands (accv, with ACC_REG) are dead during the later levels
 #if (TFHE_FFT_ABLATE & 1)
-                phase_F1<K>(R, t, sub, 1u, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return 0u; });
+                phase_F1a<K, 2>(R, t, sub, 1u, stash, a.tw.twA, [&](uint32_t, uint32_t) { return 0u; });
 #else
-                if constexpr (BMMP) phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return acc[pp * K::N + j]; });
-                else phase_F1<K>(R, t, sub, lev, stash, a.tw.twA, buf0, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
+                if constexpr (!FIRST) phase_F1a<K, 2>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t, uint32_t) { return 0u; });
+                else if constexpr (BMMP && ACC_REG) phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t, uint32_t, int k) { return accv[k]; });
+                else if constexpr (BMMP) phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return acc[pp * K::N + j]; });
+                else if constexpr (ACC_REG) phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j, int k) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - accv[k]; });
+                else phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
+                store_A<C>(R.x, buf0, t);
                 sub_sync();
                 if constexpr (K::SINGLE_BUF) {           // one buffer: a barrier between every load and the next store
                     phase_F2a<K>(R, jbB, twB, buf0);
@@ -331,30 +341,44 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 }
                 phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
                 team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
-#pragma unroll 1
-                for (uint32_t pk = 0; pk < (uint32_t)K::P * KEYS * K::HALVES; pk++) {
-                    const uint32_t p = pk / (KEYS * K::HALVES), which = (pk / K::HALVES) % KEYS, half = pk % K::HALVES;
-                    const uint32_t s = it % K::NSLOT;
-                    if (producer) pump(it + 1);
-                    mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
-#if !(TFHE_FFT_ABLATE & 2)
-                    const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
+                // the slots of GGSW row (polynomial p, this level), in ring order; OWN: the transformed digit row is this thread's R.x
+                auto row_slots = [&](auto own_c, uint32_t p) {
+                    constexpr bool OWN = decltype(own_c)::value;
                     const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
-                    if constexpr (BMMP) {
-                        if (p == sub) phase_mac_bmmp<K, true>(R, t, sub, slot, nullptr, a.tw.ztab, which == 0 ? ex0 : which == 1 ? rot : rot1, which == 0 ? zb[0] : which == 1 ? zb[1] : zb[2]);
-                        else phase_mac_bmmp<K, false>(R, t, sub, slot, peer, a.tw.ztab, which == 0 ? ex0 : which == 1 ? rot : rot1, which == 0 ? zb[0] : which == 1 ? zb[1] : zb[2]);
-                    } else {
-                        (void)which;
-                        if (p == sub) phase_mac<K, true>(R, t, sub, slot, nullptr, half);
-                        else phase_mac<K, false>(R, t, sub, slot, peer, half);
-                    }
+#pragma unroll 1
+                    for (uint32_t kh = 0; kh < KEYS * K::HALVES; kh++, it++) {
+                        const uint32_t which = kh / K::HALVES, half = kh % K::HALVES, s = it % K::NSLOT;
+                        if (producer) pump(it + 1);
+                        mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
+#if !(TFHE_FFT_ABLATE & 2)
+                        const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
+                        if constexpr (BMMP) phase_mac_bmmp<K, OWN>(R, t, sub, slot, peer, a.tw.ztab, which == 0 ? ex0 : which == 1 ? rot : rot1, which == 0 ? zb[0] : which == 1 ? zb[1] : zb[2]);
+                        else phase_mac<K, OWN>(R, t, sub, slot, peer, half);
 #endif
-                    __syncwarp();
-                    if (lane == 0) release_slot(it);
-                    it++;
+                        __syncwarp();
+                        if (lane == 0) release_slot(it);
+                    }
+                };
+                // rows before the own one, the own one, rows after it: three specialised copies of the loop body.  Measured: the
+                // BMMP variant gains 7.6 % (76.6 -> 70.8 ms at P1), P = 2 is neutral, P0 (P = 3) loses 4 % and keeps one loop.
+                if constexpr (BMMP || K::P == 2) {
+#pragma unroll 1
+                    for (uint32_t p = 0; p < sub; p++) row_slots(std::false_type{}, p);
+                    row_slots(std::true_type{}, sub);
+#pragma unroll 1
+                    for (uint32_t p = sub + 1; p < (uint32_t)K::P; p++) row_slots(std::false_type{}, p);
+                } else {
+#pragma unroll 1
+                    for (uint32_t p = 0; p < (uint32_t)K::P; p++) {
+                        if (p == sub) row_slots(std::true_type{}, p);
+                        else row_slots(std::false_type{}, p);
+                    }
                 }
                 team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
-            }
+            };
+            level(std::true_type{}, 0u);
+#pragma unroll 1
+            for (uint32_t lev = 1; lev < (uint32_t)K::L; lev++) level(std::false_type{}, lev);
         }
 #if !(TFHE_FFT_ABLATE & 16)
         // inverse transforms of this sub-team's column: the low- and high-limb products together (fft_team.cuh phase_J*)
@@ -390,12 +414,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             sub_sync();
             phase_J2b<K>(R, jbB, buf0, buf1);
             sub_sync();
-#if TFHE_FFT_ACCREG
-            if constexpr (OWN_FIRST) phase_J3r<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, accv, maxfrac);
+            if constexpr (ACC_REG) phase_J3r<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, accv, maxfrac);
             else phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
-#else
-            phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
-#endif
         }
 #endif
         sub_sync();   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
