@@ -32,6 +32,7 @@ extern "C" {
     fn tfhe_ctx_destroy(ctx: *mut RawCtx);
     fn tfhe_last_error(ctx: *const RawCtx) -> *const c_char;
     fn tfhe_ctx_set_pbs_path(ctx: *mut RawCtx, path: c_int) -> c_int;
+    fn tfhe_ctx_set_ks_path(ctx: *mut RawCtx, path: c_int) -> c_int;
     fn tfhe_bk_upload(ctx: *mut RawCtx, bsk: *const u32, ksk: *const u32, out: *mut *mut RawBk) -> c_int;
     fn tfhe_bk_free(bk: *mut RawBk);
     fn tfhe_bootstrap_batch(ctx: *mut RawCtx, bk: *const RawBk, lwe_in: *const u32, luts: *const u32, n_luts: usize,
@@ -168,6 +169,8 @@ impl B200 {
     /// 0 = 2-prime NTT path, 1 = exact FP64-FFT path; call before uploading a key (i.e. before `new` returns -- see
     /// tfhe_ctx_set_pbs_path; exposed here for completeness).
     pub fn set_pbs_path(&self, path: i32) -> Result<(), Error> { let rc = unsafe { tfhe_ctx_set_pbs_path(self.ctx, path) }; self.check(rc) }
+    /// Arithmetic of the key-switching product: 0 = 32-bit multiply-adds, 1 = integer tensor cores (same bits).
+    pub fn set_ks_path(&self, path: i32) -> Result<(), Error> { let rc = unsafe { tfhe_ctx_set_ks_path(self.ctx, path) }; self.check(rc) }
 }
 impl Drop for B200 {
     fn drop(&mut self) { unsafe { if !self.bk.is_null() { tfhe_bk_free(self.bk); } tfhe_ctx_destroy(self.ctx); } }
