@@ -77,7 +77,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 //    instead of barrier waits (P1: 74.8 -> 70.8 ms per batch of 4096).  Rows are consumed out of ring order, so there is
 //    no producer thread: the warp whose arrival frees a ring slot issues the TMA copy of the row that reuses it
 //    (release_slot), i.e. a refill starts the moment the slot's last reader is done (-> 69.4 ms).
-//  * ring order (P0, P2, the BMMP variant) -- thread 0 is the producer, rows are consumed in the order they are stored.
+//  * ring order (P0, P2, the BMMP variant) -- rows are consumed in the order they are stored; thread 0 is the producer
+//    (P0, BMMP) or, with half-row slots (P2), the last reader of a slot refills it as above.
 // Variants measured and dropped are listed in profiles/r01_fft_v8_variants.README.
 #ifndef TFHE_FFT_OWNFIRST
 #define TFHE_FFT_OWNFIRST 1
@@ -96,6 +97,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
     uint32_t *claimed = reinterpret_cast<uint32_t *>(empty + K::NSLOT);   // [NSLOT] refills issued per ring slot (OWN_FIRST)
     constexpr bool OWN_FIRST = (TFHE_FFT_OWNFIRST != 0) && !BMMP && !K::SINGLE_BUF && K::HALVES == 1 && K::NSLOT >= K::P && !(TFHE_FFT_ABLATE);
+    // ring slots are refilled by their last reader (release_slot) instead of by thread 0.  In the ring-order loop this was
+    // measured per configuration: N = 2048 (half-row slots) 201.8 -> 185.5 ms; P0 neutral (119.8 / 120.6 ms) and the BMMP
+    // variant slower (70.7 -> 72.6 ms), so those keep the producer thread.
+    constexpr bool SELF_REFILL = OWN_FIRST || (K::HALVES > 1 && !BMMP);
 
     const bool single = a.mode != 0;   // sub-operation entry points: one ciphertext (team 0) per CTA, its own GGSW
     // blind rotation: the batch is split over the grid as evenly as possible (CTA b gets base or base+1 ciphertexts,
@@ -234,14 +239,14 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     auto release_slot = [&](uint32_t r) {
         const uint32_t s = r % K::NSLOT;
         mbar_arrive(empty + s);
-        if constexpr (OWN_FIRST) {
+        if constexpr (SELF_REFILL) {
             const uint32_t k = r + (uint32_t)K::NSLOT, u = r / K::NSLOT;
             if (k < total_slots && mbar_test(empty + s, u & 1u)) {
                 if (atomicCAS(claimed + s, u, u + 1u) == u) issue_row(k);   // one issuer per use
             }
         }
     };
-    if constexpr (OWN_FIRST) { if (producer) pump(0); }
+    if constexpr (SELF_REFILL) { if (producer) pump(0); }
     auto diff = [&](uint32_t pp, uint32_t j, uint32_t rot) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - sbase[pp * K::N + j]; };
 #pragma unroll 1
     for (uint32_t i = 0; i < n_steps; i++) {
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             // diff == 0 (bundle == 0) => external product == 0 exactly: consume this step's slots without using them
 #pragma unroll 1
             for (uint32_t s = 0; s < STEP_SLOTS; s++, it++) {
-                if constexpr (!OWN_FIRST) { if (producer) pump(it + 1); }
+                if constexpr (!SELF_REFILL) { if (producer) pump(it + 1); }
                 mbar_wait(full + (it % K::NSLOT), (it / K::NSLOT) & 1u, a.err_flag);
                 __syncwarp();
                 if (lane == 0) release_slot(it);
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #pragma unroll 1
                     for (uint32_t kh = 0; kh < KEYS * K::HALVES; kh++, it++) {
                         const uint32_t which = kh / K::HALVES, half = kh % K::HALVES, s = it % K::NSLOT;
-                        if (producer) pump(it + 1);
+                        if constexpr (!SELF_REFILL) { if (producer) pump(it + 1); }
                         mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
 #if !(TFHE_FFT_ABLATE & 2)
                         const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             phase_K1<K, 0>(R, t, twC, buf0);
             sub_sync();
             phase_K2a<K, 0>(R, jbB, twB, buf0);
-            if (producer) pump(0);
+            if constexpr (!SELF_REFILL) { if (producer) pump(0); }
             sub_sync();
             phase_K2b<K, 0>(R, jbB, buf0);
             sub_sync();
@@ -409,7 +414,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 phase_J1<K>(R, t, twC, buf0, buf1);
                 sub_sync();
                 phase_J2a<K>(R, jbB, twB, buf0, buf1);
-                if (producer) pump(0);   // ring entries freed by slower teams: refill them while this team inverts
+                if constexpr (!SELF_REFILL) { if (producer) pump(0); }   // ring entries freed by slower teams: refill them while this team inverts
             }
             sub_sync();
             phase_J2b<K>(R, jbB, buf0, buf1);
