@@ -275,3 +275,34 @@ def test_bmmp_unrolled_blind_rotation_decrypts():
             assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, out)) == m, (preset, m)
             # same ciphertext through the standard chain decrypts to the same message (different key material, different bits)
             assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, orc.bootstrap(o, ct, bsk, ksk, tv))) == m
+
+
+def test_key_switch_byte_plane_identity():
+    """The tensor-core key switch (kernels.cuh K4-MMA) rests on: sum_r d_r * w_r = sum_pl 2^(8 pl) * (sum_r d_r * byte_pl(w_r))
+    mod 2^32, with every inner sum an exact 32-bit integer.  Checked here in plain integers against the oracle's
+    key_switching.rs:63-103 restatement, digits from the oracle's decomposer (incl. the +B digit), extreme key words."""
+    import ctypes as C
+    o = orc.params(True)                       # k=2, N=512, n=4, ks (4, 5)
+    L = orc.lib()
+    rng = np.random.default_rng(23)
+    kN, n, lev, logb = 2 * 512, 4, 5, 4
+    ksk = rng.integers(0, 1 << 32, (kN * lev, n + 1), dtype=np.uint64).astype(np.uint32)
+    ksk[:7] = 0xFFFFFFFF
+    ksk[7:9] = 0x80000000
+    lwe = rng.integers(0, 1 << 32, kN + 1, dtype=np.uint64).astype(np.uint32)
+    lwe[:16] = 0xF8F8F8F8                      # windows of B-1 plus carry: digit +B
+    exp = orc.z(n + 1)
+    L.orc_key_switch_lwe(C.byref(o), lwe, ksk, exp)
+    digits = np.zeros(kN * lev, dtype=np.int64)                                                   # signed, MSB first
+    d = orc.z(lev)
+    for i in range(kN):
+        L.orc_decompose(int(lwe[i]), logb, lev, d)
+        digits[i * lev:(i + 1) * lev] = d.view(np.int32)
+    assert digits.max() == 16 and digits.min() >= -8
+    planes = [((ksk.astype(np.int64) >> (8 * pl)) & 255) for pl in range(4)]
+    inner = [digits @ pb for pb in planes]                                                        # exact integers
+    assert max(int(np.abs(x).max()) for x in inner) < 2 ** 31                                     # fit the s32 accumulators
+    total = sum(int(1 << (8 * pl)) * inner[pl] for pl in range(4))
+    got = (-total) % (1 << 32)
+    got[n] = (got[n] + int(lwe[kN])) % (1 << 32)
+    assert np.array_equal(got.astype(np.uint32), exp)
