@@ -65,6 +65,8 @@ def test_p1_batch_4096_identity(which):
     assert np.array_equal(out[:nu], out[nu:2 * nu])
     small = e.ctx.bootstrap(e.bk, cts[5:8], tv)
     assert np.array_equal(small, out[5:8])
+    # 445 ciphertexts spread over two waves of CTAs holding 1 or 2 each (4096: 2 or 3 each): same bits per ciphertext
+    assert np.array_equal(e.ctx.bootstrap(e.bk, cts[:445], tv), out[:445])
     # oracle spot check at full n (reference algorithm, ~1 s each)
     for i in (0, 77):
         assert np.array_equal(out[i], orc.bootstrap(e.o, cts[i], e.bsk, e.ksk, tv))
