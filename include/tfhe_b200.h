@@ -136,7 +136,9 @@ int tfhe_keygen_bmmp(const tfhe_params *p, uint64_t seed, uint32_t *lwe_sk /* n 
 int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk, tfhe_bk **out);
 void tfhe_bk_free(tfhe_bk *bk);
 /* Inspection (parity tests of the one-off key transform): size in bytes of the transformed BSK held on the device,
- * and a copy of it to host memory.  NTT path: u32[n][2][(k+1)l][k+1][N]; FFT path: f64 pairs[n][(k+1)l][2][k+1][N/2]. */
+ * and a copy of it to host memory.  NTT path: u32[n][2][(k+1)l][k+1][N]; FFT path: f64 pairs[n][l][k+1 (slot d)][2][k+1 (c)][N/2],
+ * diagonal-major: slot d of a level holds at column position c the polynomial (GGSW row of polynomial (c + d) mod (k+1),
+ * column c) -- the order in which the blind rotation consumes it. */
 size_t tfhe_bk_transformed_bytes(const tfhe_bk *bk);
 int tfhe_bk_read_transformed(const tfhe_bk *bk, void *out, size_t bytes);
 

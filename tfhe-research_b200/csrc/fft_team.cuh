@@ -234,6 +234,13 @@ struct FftPbsCfg {
 // index of GGSW row (polynomial p, level lev) in the stored key = its position in the consumption order
 template <class K>
 TFHE_HD constexpr uint32_t key_row_index(uint32_t p, uint32_t lev) { return lev * K::P + p; }
+// Device layout ("diagonal-major"): the P x P polynomials (GGSW row of polynomial p, column c) of a level are regrouped so
+// that slot d of the level holds, at column position c, the polynomial of row p = (c + d) mod P.  Sub-team s always reads
+// column position s; at slot d it multiplies the transformed digits of polynomial (s + d) mod P -- its OWN row at d = 0,
+// whatever s is.  So every sub-team can start a level on the row it still holds in registers while the slots stream in one
+// fixed order through a two-slot ring.
+template <class K>
+TFHE_HD constexpr uint32_t key_slot_index(uint32_t p, uint32_t c, uint32_t lev) { return lev * K::P + (p + K::P - c) % K::P; }
 
 template <class K>
 struct FftRegs {

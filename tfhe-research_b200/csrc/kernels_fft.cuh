@@ -20,7 +20,7 @@ namespace fft {
 
 struct FftArgs {
     TwTablesF tw;
-    const cplx *bsk_fft;       // [n][ROWS][2 limbs][P][M] slot order, pre-scaled by 1/M
+    const cplx *bsk_fft;       // [n][L][P slots][2 limbs][P][M], diagonal-major (fft_team.cuh key_slot_index), slot order, pre-scaled by 1/M
     const uint32_t *lwe_in;    // mode 0: [B][n+1]
     const uint32_t *luts;      // [T][N] unencoded
     const uint32_t *lut_idx;   // [B] or nullptr
@@ -70,15 +70,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // BMMP = true: blind rotation unrolled by two (notes/BMMP Bootstrapping.md): n/2 steps, each consumes the three GGSWs of
 // a key triple (3 slots per row), decomposes acc itself and adds ExtProd(bundle, acc); blind rotation mode only.
 //
+// Key stream.  The key is stored diagonal-major (fft_team.cuh key_slot_index): slot d of a level holds, at column position c,
+// the polynomial (row of polynomial (c + d) mod P, column c).  Sub-team s always reads column position s and multiplies, at
+// slot d, the transformed digits of polynomial (s + d) mod P: its OWN row (still in its registers) at d = 0 -- for every s --
+// and the published rows of the other sub-teams after that.  So the slots stream in one fixed order through a two-slot ring,
+// and every sub-team starts a level without waiting for anyone.
 // Two level loops (what they compute is the same):
-//  * OWN_FIRST (the ring holds all P rows of a level: P1) -- a sub-team multiplies its OWN transformed row, still in its
-//    registers, before the team barrier that publishes the rows, and runs the register part of the next level's F1
-//    before the barrier that lets it overwrite its published row: skew between sub-teams is absorbed by useful work
-//    instead of barrier waits (P1: 74.8 -> 70.8 ms per batch of 4096).  Rows are consumed out of ring order, so there is
-//    no producer thread: the warp whose arrival frees a ring slot issues the TMA copy of the row that reuses it
-//    (release_slot), i.e. a refill starts the moment the slot's last reader is done (-> 69.4 ms).
-//  * ring order (P0, P2, the BMMP variant) -- rows are consumed in the order they are stored; thread 0 is the producer
-//    (P0, BMMP) or, with half-row slots (P2), the last reader of a slot refills it as above.
+//  * OWN_FIRST (P0, P1) -- the own row is multiplied before the team barrier that publishes the rows, and the register part
+//    of the next level's F1 runs before the barrier that lets a sub-team overwrite its published row: skew between sub-teams
+//    is absorbed by useful work instead of barrier waits (P1: 74.8 -> 70.8 ms per batch of 4096).  There is no producer
+//    thread: the warp whose arrival frees a ring slot issues the TMA copy of the row that reuses it (release_slot), i.e. a
+//    refill starts the moment the slot's last reader is done (P1: -> 69.4 ms; with thread 0 as producer 68.5 vs 65.2 ms in v11).
+//  * general (P2: one exchange buffer, half-row slots; the BMMP variant: three keys per row) -- same order, own row before
+//    the publish barrier; thread 0 is the producer (BMMP) or the last reader of a slot refills it (P2: 196.6 -> 183.5 ms).
 // Variants measured and dropped are listed in profiles/r01_fft_v8_variants.README.
 #ifndef TFHE_FFT_OWNFIRST
 #define TFHE_FFT_OWNFIRST 1
@@ -96,11 +100,14 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     uint8_t *ring = smem + K::CTS * team_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
     uint32_t *claimed = reinterpret_cast<uint32_t *>(empty + K::NSLOT);   // [NSLOT] refills issued per ring slot (OWN_FIRST)
-    constexpr bool OWN_FIRST = (TFHE_FFT_OWNFIRST != 0) && !BMMP && !K::SINGLE_BUF && K::HALVES == 1 && K::NSLOT >= K::P && !(TFHE_FFT_ABLATE);
+    constexpr bool OWN_FIRST = (TFHE_FFT_OWNFIRST != 0) && !BMMP && !K::SINGLE_BUF && K::HALVES == 1 && !(TFHE_FFT_ABLATE);
     // ring slots are refilled by their last reader (release_slot) instead of by thread 0.  In the ring-order loop this was
     // measured per configuration: N = 2048 (half-row slots) 201.8 -> 185.5 ms; P0 neutral (119.8 / 120.6 ms) and the BMMP
     // variant slower (70.7 -> 72.6 ms), so those keep the producer thread.
-    constexpr bool SELF_REFILL = OWN_FIRST || (K::HALVES > 1 && !BMMP);
+#ifndef TFHE_FFT_SELFREFILL
+#define TFHE_FFT_SELFREFILL 1
+#endif
+    constexpr bool SELF_REFILL = (TFHE_FFT_SELFREFILL != 0) && (OWN_FIRST || (K::HALVES > 1 && !BMMP));
 
     const bool single = a.mode != 0;   // sub-operation entry points: one ciphertext (team 0) per CTA, its own GGSW
     // blind rotation: the batch is split over the grid as evenly as possible (CTA b gets base or base+1 ciphertexts,
@@ -222,8 +229,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         bulk_g2s(ring + s * K::SLOT_BYTES + K::LIMB_BYTES, ksrc + (size_t)row * K::SLOT_BYTES + K::LIMB_BYTES, K::LIMB_BYTES, full + s);
     };
     uint32_t issued = 0;
-    auto pump = [&](uint32_t need) {
-        while (issued < total_slots && issued < it + (uint32_t)K::NSLOT) {
+    auto pump = [&](uint32_t need, uint32_t pos) {   // pos = the caller's position in the key stream
+        while (issued < total_slots && issued < pos + (uint32_t)K::NSLOT) {
             const uint32_t s = issued % K::NSLOT;
             if (issued >= (uint32_t)K::NSLOT) {
                 const uint32_t par = ((issued / K::NSLOT) - 1u) & 1u;
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             }
         }
     };
-    if constexpr (SELF_REFILL) { if (producer) pump(0); }
+    if constexpr (SELF_REFILL) { if (producer) pump(0, it); }
     auto diff = [&](uint32_t pp, uint32_t j, uint32_t rot) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - sbase[pp * K::N + j]; };
 #pragma unroll 1
     for (uint32_t i = 0; i < n_steps; i++) {
@@ -264,7 +271,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             // diff == 0 (bundle == 0) => external product == 0 exactly: consume this step's slots without using them
 #pragma unroll 1
             for (uint32_t s = 0; s < STEP_SLOTS; s++, it++) {
-                if constexpr (!SELF_REFILL) { if (producer) pump(it + 1); }
+                if constexpr (!SELF_REFILL) { if (producer) pump(it + 1, it); }
                 mbar_wait(full + (it % K::NSLOT), (it / K::NSLOT) & 1u, a.err_flag);
                 __syncwarp();
                 if (lane == 0) release_slot(it);
@@ -273,9 +280,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
         zero_acc<K>(R);
         if constexpr (OWN_FIRST) {
-            auto mac_slot = [&](auto own_c, uint32_t p) {   // ring row it + p = GGSW row (polynomial p, this level)
+            auto mac_slot = [&](auto own_c, uint32_t d) {   // ring row it + d: slot d of this level = row of polynomial (sub + d) mod P
                 constexpr bool OWN = decltype(own_c)::value;
-                const uint32_t ir = it + p, s = ir % K::NSLOT;
+                const uint32_t ir = it + d, s = ir % K::NSLOT, p = (sub + d) % (uint32_t)K::P;
+                if constexpr (!SELF_REFILL) { if (producer) pump(ir + 1, ir); }
                 mbar_wait(full + s, (ir / K::NSLOT) & 1u, a.err_flag);
                 const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
                 const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
@@ -300,11 +308,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 sub_sync();
                 phase_F3v<K>(R, t, twC_base, buf1);
                 phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
-                mac_slot(std::true_type{}, sub);
+                mac_slot(std::true_type{}, 0u);
                 team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
 #pragma unroll 1
-                for (uint32_t p = 0; p < (uint32_t)K::P; p++)
-                    if (p != sub) mac_slot(std::false_type{}, p);
+                for (uint32_t d = 1; d < (uint32_t)K::P; d++) mac_slot(std::false_type{}, d);
                 it += (uint32_t)K::P;
             };
 #if TFHE_FFT_ACCREG
@@ -345,15 +352,16 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                     phase_F3<K>(R, t, twC, buf1);
                 }
                 phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
-                team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
-                // the slots of GGSW row (polynomial p, this level), in ring order; OWN: the transformed digit row is this thread's R.x
-                auto row_slots = [&](auto own_c, uint32_t p) {
+                // slot group d of this level (KEYS * HALVES ring slots) = row of polynomial (sub + d) mod P at this sub-team's
+                // column position; OWN (d = 0): the transformed digit row is this thread's R.x
+                auto row_slots = [&](auto own_c, uint32_t d) {
                     constexpr bool OWN = decltype(own_c)::value;
+                    const uint32_t p = (sub + d) % (uint32_t)K::P;
                     const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
 #pragma unroll 1
                     for (uint32_t kh = 0; kh < KEYS * K::HALVES; kh++, it++) {
                         const uint32_t which = kh / K::HALVES, half = kh % K::HALVES, s = it % K::NSLOT;
-                        if constexpr (!SELF_REFILL) { if (producer) pump(it + 1); }
+                        if constexpr (!SELF_REFILL) { if (producer) pump(it + 1, it); }
                         mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
 #if !(TFHE_FFT_ABLATE & 2)
                         const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
@@ -364,21 +372,18 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                         if (lane == 0) release_slot(it);
                     }
                 };
-                // rows before the own one, the own one, rows after it: three specialised copies of the loop body.  Measured: the
-                // BMMP variant gains 7.6 % (76.6 -> 70.8 ms at P1), P = 2 is neutral, P0 (P = 3) loses 4 % and keeps one loop.
-                if constexpr (BMMP || K::P == 2) {
+#ifndef TFHE_FFT_GEN_OWNFIRST
+#define TFHE_FFT_GEN_OWNFIRST 1
+#endif
+#if TFHE_FFT_GEN_OWNFIRST
+                row_slots(std::true_type{}, 0u);         // the own row needs no barrier
+                team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
+#else
+                team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
+                row_slots(std::true_type{}, 0u);
+#endif
 #pragma unroll 1
-                    for (uint32_t p = 0; p < sub; p++) row_slots(std::false_type{}, p);
-                    row_slots(std::true_type{}, sub);
-#pragma unroll 1
-                    for (uint32_t p = sub + 1; p < (uint32_t)K::P; p++) row_slots(std::false_type{}, p);
-                } else {
-#pragma unroll 1
-                    for (uint32_t p = 0; p < (uint32_t)K::P; p++) {
-                        if (p == sub) row_slots(std::true_type{}, p);
-                        else row_slots(std::false_type{}, p);
-                    }
-                }
+                for (uint32_t d = 1; d < (uint32_t)K::P; d++) row_slots(std::false_type{}, d);
                 team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
             };
             level(std::true_type{}, 0u);
@@ -392,7 +397,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             phase_K1<K, 0>(R, t, twC, buf0);
             sub_sync();
             phase_K2a<K, 0>(R, jbB, twB, buf0);
-            if constexpr (!SELF_REFILL) { if (producer) pump(0); }
+            if constexpr (!SELF_REFILL) { if (producer) pump(0, it); }
             sub_sync();
             phase_K2b<K, 0>(R, jbB, buf0);
             sub_sync();
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 phase_J1<K>(R, t, twC, buf0, buf1);
                 sub_sync();
                 phase_J2a<K>(R, jbB, twB, buf0, buf1);
-                if constexpr (!SELF_REFILL) { if (producer) pump(0); }   // ring entries freed by slower teams: refill them while this team inverts
+                if constexpr (!SELF_REFILL) { if (producer) pump(0, it); }   // ring entries freed by slower teams: refill them while this team inverts
             }
             sub_sync();
             phase_J2b<K>(R, jbB, buf0, buf1);
@@ -453,7 +458,7 @@ __global__ void __launch_bounds__(2 * K::T) bsk_fft_transform_kernel(const __gri
     const size_t ir = poly / K::P, c = poly % K::P, i = ir / K::ROWS, r = ir % K::ROWS;
     const uint32_t *g = a.raw + poly * K::N;
     const size_t kps = a.keys_per_step, step = i / kps, which = i % kps;
-    const size_t row = (step * K::ROWS + key_row_index<K>((uint32_t)(r / K::L), (uint32_t)(r % K::L))) * kps + which;   // consumption order
+    const size_t row = (step * K::ROWS + key_slot_index<K>((uint32_t)(r / K::L), (uint32_t)c, (uint32_t)(r % K::L))) * kps + which;   // consumption order, diagonal-major
     cplx *o = a.out + ((row * K::HALVES * 2 + limb) * K::P + c) * K::MH;   // half 0; phase_T3 adds the half stride
     FftRegs<K> R;
     phase_T1<K>(R, t, (int)limb, g, a.tw.twA, buf0);

@@ -29,6 +29,14 @@ for i in range(p.n):
     emu_key = np.zeros(per)
     E.emu_fft_transform_ggsw(1, bsk[i * gg:(i + 1) * gg], emu_key)
     g = gpu_key[i * per:(i + 1) * per]
+    # the emulation stores rows (level, polynomial p); the device stores slots (level, d) with p = (c + d) mod P at column c
+    Pn, Ln = p.k + 1, p.pbs_levels
+    ek = emu_key.reshape(Ln, Pn, 2, Pn, -1)
+    dk = np.empty_like(ek)
+    for d in range(Pn):
+        for c in range(Pn):
+            dk[:, d, :, c] = ek[:, (c + d) % Pn, :, c]
+    emu_key = dk.reshape(-1)
     bad = np.nonzero(g != emu_key)[0]
     print(f"ggsw {i}: transformed key mismatches: {bad.size} of {per}", bad[:8], g[bad[:4]], emu_key[bad[:4]])
 rng = np.random.default_rng(2)
