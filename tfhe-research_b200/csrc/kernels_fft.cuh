@@ -99,11 +99,11 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     const uint32_t team_bytes = (uint32_t)K::team_bytes((int)a.n);
     uint8_t *ring = smem + K::CTS * team_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
-    uint32_t *claimed = reinterpret_cast<uint32_t *>(empty + K::NSLOT);   // [NSLOT] refills issued per ring slot (OWN_FIRST)
+    uint32_t *claimed = reinterpret_cast<uint32_t *>(empty + K::NSLOT);   // [NSLOT] refills issued per ring slot (SELF_REFILL)
     constexpr bool OWN_FIRST = (TFHE_FFT_OWNFIRST != 0) && !BMMP && !K::SINGLE_BUF && K::HALVES == 1 && !(TFHE_FFT_ABLATE);
-    // ring slots are refilled by their last reader (release_slot) instead of by thread 0.  In the ring-order loop this was
-    // measured per configuration: N = 2048 (half-row slots) 201.8 -> 185.5 ms; P0 neutral (119.8 / 120.6 ms) and the BMMP
-    // variant slower (70.7 -> 72.6 ms), so those keep the producer thread.
+    // ring slots are refilled by their last reader (release_slot) instead of by thread 0: measured per configuration -- P1 68.5 ->
+    // 65.2 ms, N = 2048 (half-row slots) 196.6 -> 183.5 ms, P0 neutral (116.7 / 117.2 ms); the BMMP variant was slower with it
+    // (70.7 -> 72.6 ms) and keeps the producer thread.
 #ifndef TFHE_FFT_SELFREFILL
 #define TFHE_FFT_SELFREFILL 1
 #endif
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     // ---- key stream.  Ring-order loop: thread 0 issues the TMA bulk copies (SASS UBLKCP) in consumption order, up to
     // NSLOT slots ahead of its own position; pump(need) returns with slots [0, need) issued (blocking on the ring's
     // `empty` barriers if it must) and opportunistically issues further slots whose ring entry is already free.
-    // OWN_FIRST loop: thread 0 only issues the first NSLOT rows; every later row is issued by release_slot.
+    // SELF_REFILL: thread 0 only issues the first NSLOT rows; every later row is issued by release_slot.
     const bool producer = tid == 0;
     const uint8_t *ksrc = reinterpret_cast<const uint8_t *>(a.bsk_fft) + (single ? (size_t)__ldg(a.ggsw_index + ct0) * K::GGSW_BYTES : 0);
     auto issue_row = [&](uint32_t row) {
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             issued++;
         }
     };
-    // lane 0 of a warp that is done with ring row r.  OWN_FIRST: the slot's use u = r / NSLOT is complete once every warp
+    // lane 0 of a warp that is done with ring row r.  SELF_REFILL: the slot's use u = r / NSLOT is complete once every warp
     // has arrived; whoever sees that first (at the latest the last arriver, right after its own arrival) claims the refill.
     auto release_slot = [&](uint32_t r) {
         const uint32_t s = r % K::NSLOT;
