@@ -241,6 +241,15 @@ TFHE_HD constexpr uint32_t key_row_index(uint32_t p, uint32_t lev) { return lev 
 // fixed order through a two-slot ring.
 template <class K>
 TFHE_HD constexpr uint32_t key_slot_index(uint32_t p, uint32_t c, uint32_t lev) { return lev * K::P + (p + K::P - c) % K::P; }
+// every (slot d, column position c) of a level is hit exactly once, by the row p = (c + d) mod P the kernels multiply there
+template <class K>
+constexpr bool key_slot_layout_ok() {
+    for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++)
+        for (uint32_t d = 0; d < (uint32_t)K::P; d++)
+            for (uint32_t c = 0; c < (uint32_t)K::P; c++)
+                if (key_slot_index<K>((c + d) % K::P, c, lev) != lev * K::P + d) return false;
+    return true;
+}
 
 template <class K>
 struct FftRegs {

@@ -188,6 +188,7 @@ using KF0C = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, true>;
 // N = 2048: 16 points per thread, one exchange buffer per sub-team, half-row key slots (fft_team.cuh FftPbsCfg)
 using KF2 = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, false, true, 2>;
 using KF2C = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2>;
+static_assert(fft::key_slot_layout_ok<KF0>() && fft::key_slot_layout_ok<KF1>() && fft::key_slot_layout_ok<KF2>(), "diagonal-major key layout");
 template <class K>
 constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 16; }
 // the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
