@@ -11,9 +11,11 @@
  *  - every function returns 0 on success or a negative tfhe_status; nothing unwinds across the ABI
  *    (the reference panics via assert!/unwrap -- those sites map to TFHE_E_ASSERT);
  *  - a tfhe_ctx is bound to ONE CUDA device and is single-caller, like the reference's synchronous
- *    single-threaded calls; multi-GPU = one process (one ctx) per GPU, batches sharded by the caller;
+ *    single-threaded calls; multi-GPU = either one process (one ctx) per GPU with the batch sharded by the
+ *    caller, or ONE process driving all GPUs of the box through a tfhe_mgpu (section "multi-GPU" below);
  *  - pointer arguments of the batched device entry points may be host OR device pointers (queried
- *    with cudaPointerGetAttributes); host buffers are staged through the ctx's pinned buffers;
+ *    with cudaPointerGetAttributes); host buffers are copied with cudaMemcpyAsync into device staging
+ *    buffers owned by the ctx (pass pinned host memory for full-speed, truly asynchronous copies);
  *  - there is NO CPU fallback: device entry points fail with TFHE_E_CUDA when no GPU is present.
  *
  * Layouts:  N = 2^log_poly_degree, k = glwe_dimension, n = lwe_dimension,
@@ -92,6 +94,8 @@ void tfhe_ctx_destroy(tfhe_ctx *ctx);
 const char *tfhe_last_error(const tfhe_ctx *ctx);
 /* Run all subsequent work of this ctx on an existing CUDA stream (cudaStream_t as void*); NULL = own stream. */
 int tfhe_ctx_set_stream(tfhe_ctx *ctx, void *cuda_stream);
+/* The stream this ctx launches on (cudaStream_t as void*). */
+void *tfhe_ctx_get_stream(const tfhe_ctx *ctx);
 /* Kernels launched by this ctx since creation (the bench's gpu_launches claim). */
 uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx);
 
@@ -134,7 +138,11 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
 int tfhe_keygen_bmmp(const tfhe_params *p, uint64_t seed, uint32_t *lwe_sk /* n */, uint32_t *glwe_sk /* k*N */,
                      uint32_t *bsk3, uint32_t *ksk);
 int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk, tfhe_bk **out);
+/* Keys may be freed before or after their context: tfhe_ctx_destroy orphans the ctx's live keys (they can then only be
+ * freed; every other use returns TFHE_E_PARAM). */
 void tfhe_bk_free(tfhe_bk *bk);
+/* Arithmetic path the key was transformed for (TFHE_PATH_*; BMMP keys: TFHE_PATH_FFT). */
+int tfhe_bk_get_path(const tfhe_bk *bk);
 /* Inspection (parity tests of the one-off key transform): size in bytes of the transformed BSK held on the device,
  * and a copy of it to host memory.  NTT path: u32[n][2][(k+1)l][k+1][N]; FFT path: f64 pairs[n][l][k+1 (slot d)][2][k+1 (c)][N/2],
  * diagonal-major: slot d of a level holds at column position c the polynomial (GGSW row of polynomial (c + d) mod (k+1),
@@ -144,7 +152,9 @@ int tfhe_bk_read_transformed(const tfhe_bk *bk, void *out, size_t bytes);
 
 /* ------------------------------------------------------------------ the hot path */
 /* bootstrapping.rs:58-120 `bootstrap`, batched.  luts = T unencoded test vectors [T][N] (values < 2^log_p,
- * else TFHE_E_ASSERT like glwe.rs:144); lut_idx[b] selects the test vector of ciphertext b (NULL: all 0). */
+ * else TFHE_E_ASSERT like glwe.rs:144); lut_idx[b] selects the test vector of ciphertext b (NULL: all 0);
+ * an entry >= n_luts is never dereferenced: the call returns TFHE_E_PARAM (checked on the device, so lut_idx may be
+ * a device pointer). */
 int tfhe_bootstrap_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in /* [B][n+1] */,
                          const uint32_t *luts /* [T][N] */, size_t n_luts, const uint32_t *lut_idx /* [B] or NULL */,
                          size_t batch, uint32_t *lwe_out /* [B][n+1] */);
@@ -154,6 +164,37 @@ int tfhe_gate_batch(tfhe_ctx *ctx, const tfhe_bk *bk, int gate, const uint32_t *
 /* Same with one opcode per ciphertext (mixed-gate circuit level). gates[b] in tfhe_gate. */
 int tfhe_gates_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint8_t *gates /* [B], host */, const uint32_t *ct0,
                      const uint32_t *ct1, size_t batch, uint32_t *out);
+
+/* ------------------------------------------------------------------ multi-GPU: one process, all GPUs of the box */
+/* Every ciphertext's bootstrap is independent (bootstrapping.rs:58-65), so a batch is split into contiguous, balanced index
+ * ranges, one per GPU, with the keys REPLICATED on every GPU.  A tfhe_mgpu owns one tfhe_ctx per device and, for
+ * device-resident batches, an NCCL communicator over them (libnccl.so.2 is opened at run time; without it the
+ * device-pointer form returns TFHE_E_NCCL, the host-pointer form needs no NCCL):
+ *   host pointers    each GPU copies its own shard in and out (cudaMemcpyAsync on its stream), all GPUs concurrently;
+ *   device pointers  (memory of one of the tfhe_mgpu's devices, the "root") grouped ncclSend/ncclRecv scatter over NVLink,
+ *                    local bootstraps, grouped ncclSend/ncclRecv gather into the root's output buffer.
+ * There is no collective inside the data path.  Results are bit-identical to the single-GPU entry points. */
+typedef struct tfhe_mgpu tfhe_mgpu;
+typedef struct tfhe_mgpu_bk tfhe_mgpu_bk;
+/* devices == NULL: devices 0..n_gpus-1. */
+int tfhe_mgpu_create(const tfhe_params *p, int n_gpus, const int *devices, tfhe_mgpu **out);
+void tfhe_mgpu_destroy(tfhe_mgpu *m);
+int tfhe_mgpu_n_gpus(const tfhe_mgpu *m);
+tfhe_ctx *tfhe_mgpu_ctx(tfhe_mgpu *m, int i);   /* the i-th device's context (path selection, timing, launch counts) */
+const char *tfhe_mgpu_last_error(const tfhe_mgpu *m);
+/* Replicates the key: uploaded and transformed on every device concurrently (bsk/ksk: host pointers). */
+int tfhe_mgpu_bk_upload(tfhe_mgpu *m, const uint32_t *bsk, const uint32_t *ksk, tfhe_mgpu_bk **out);
+int tfhe_mgpu_bk_upload_bmmp(tfhe_mgpu *m, const uint32_t *bsk3, const uint32_t *ksk, tfhe_mgpu_bk **out);
+void tfhe_mgpu_bk_free(tfhe_mgpu_bk *bk);
+/* tfhe_bootstrap_batch / tfhe_gates_batch over all GPUs.  lwe_in, lwe_out (ct0, ct1, out): all host or all on ONE
+ * device of the tfhe_mgpu; luts, lut_idx, gates: host pointers. */
+int tfhe_mgpu_bootstrap_batch(tfhe_mgpu *m, const tfhe_mgpu_bk *bk, const uint32_t *lwe_in, const uint32_t *luts, size_t n_luts,
+                              const uint32_t *lut_idx, size_t batch, uint32_t *lwe_out);
+int tfhe_mgpu_gates_batch(tfhe_mgpu *m, const tfhe_mgpu_bk *bk, const uint8_t *gates, const uint32_t *ct0, const uint32_t *ct1,
+                          size_t batch, uint32_t *out);
+/* Wall-clock split (ms) of the last tfhe_mgpu_* batch call: out[0] scatter, out[1] compute (slowest GPU), out[2] gather,
+ * out[3] whole call. */
+int tfhe_mgpu_last_timing(const tfhe_mgpu *m, double out[4]);
 
 /* ------------------------------------------------------------------ compositions of the same kernels */
 /* Key-switch-FIRST ordering (notes/TFHE.md:365-400): input and output live under the GLWE-derived LWE key

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "tfhe_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|void|uint64_t|size_t|const char \*)\s*(tfhe_[a-z0-9_]+)\(", hdr, re.M))
+    declared = set(re.findall(r"^(?:int|void \*|void|uint64_t|size_t|const char \*|tfhe_ctx \*)\s*(tfhe_[a-z0-9_]+)\(", hdr, re.M))
     assert declared == set(T.EXPORTS), declared ^ set(T.EXPORTS)
     L = C.CDLL(T.LIB_PATH)
     for name in declared:

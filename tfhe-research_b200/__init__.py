@@ -14,6 +14,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import weakref
 
 import numpy as np
 
@@ -21,8 +22,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("TFHE_B200_LIB") or os.path.join(_HERE, "libtfhe_b200.so")   # override: A/B runs of kernel variants
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++"]
-_SOURCES = ["tfhe_b200.cu", "host_api.cpp"]
+              "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-ldl"]
+_SOURCES = ["tfhe_b200.cu", "host_api.cpp", "tfhe_mgpu.cpp"]
 _DEPS = _SOURCES + ["kernels.cuh", "pbs_team.cuh", "tfhe_core.cuh", "host_tables.hpp", "api_internal.hpp",
                     "kernels_fft.cuh", "fft_team.cuh", "host_tables_fft.hpp",
                     os.path.join("..", "..", "include", "tfhe_b200.h")]
@@ -125,6 +126,11 @@ def lib():
         "tfhe_blind_rotate": [VP, VP, VP, VP, SZ, VP, SZ, VP],
         "tfhe_sample_extract": [VP, VP, SZ, VP], "tfhe_key_switch": [VP, VP, VP, SZ, VP],
         "tfhe_gate_linear": [VP, VP, VP, SZ, VP],
+        "tfhe_bk_get_path": [VP],
+        "tfhe_mgpu_create": [PP, C.c_int, VP, C.POINTER(VP)], "tfhe_mgpu_n_gpus": [VP],
+        "tfhe_mgpu_bk_upload": [VP, VP, VP, C.POINTER(VP)], "tfhe_mgpu_bk_upload_bmmp": [VP, VP, VP, C.POINTER(VP)],
+        "tfhe_mgpu_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP], "tfhe_mgpu_gates_batch": [VP, VP, VP, VP, VP, SZ, VP],
+        "tfhe_mgpu_last_timing": [VP, C.POINTER(C.c_double * 4)],
         "tfhe_measure_int_peak": [VP, C.POINTER(C.c_double * 8)], "tfhe_measure_fp64_peak": [VP, C.POINTER(C.c_double * 4)], "tfhe_last_timing": [VP, C.POINTER(C.c_double * 3)],
     }
     for name, args in sig.items():
@@ -136,6 +142,11 @@ def lib():
     L.tfhe_last_error.argtypes = [VP]; L.tfhe_last_error.restype = C.c_char_p
     L.tfhe_ctx_launch_count.argtypes = [VP]; L.tfhe_ctx_launch_count.restype = C.c_uint64
     L.tfhe_bk_transformed_bytes.argtypes = [VP]; L.tfhe_bk_transformed_bytes.restype = C.c_size_t
+    L.tfhe_ctx_get_stream.argtypes = [VP]; L.tfhe_ctx_get_stream.restype = C.c_void_p
+    L.tfhe_mgpu_destroy.argtypes = [VP]; L.tfhe_mgpu_destroy.restype = None
+    L.tfhe_mgpu_bk_free.argtypes = [VP]; L.tfhe_mgpu_bk_free.restype = None
+    L.tfhe_mgpu_ctx.argtypes = [VP, C.c_int]; L.tfhe_mgpu_ctx.restype = C.c_void_p
+    L.tfhe_mgpu_last_error.argtypes = [VP]; L.tfhe_mgpu_last_error.restype = C.c_char_p
     _LIB = L
     return L
 
@@ -149,7 +160,9 @@ EXPORTS = [
     "tfhe_negacyclic_mul", "tfhe_cmux", "tfhe_blind_rotate", "tfhe_sample_extract", "tfhe_key_switch", "tfhe_gate_linear",
     "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_ctx_set_ks_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
     "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed", "tfhe_bootstrap_batch_ks_first", "tfhe_gate_k_batch",
-    "tfhe_file_write", "tfhe_file_read", "tfhe_keygen_bmmp", "tfhe_bk_upload_bmmp",
+    "tfhe_file_write", "tfhe_file_read", "tfhe_keygen_bmmp", "tfhe_bk_upload_bmmp", "tfhe_bk_get_path", "tfhe_ctx_get_stream",
+    "tfhe_mgpu_create", "tfhe_mgpu_destroy", "tfhe_mgpu_n_gpus", "tfhe_mgpu_ctx", "tfhe_mgpu_last_error", "tfhe_mgpu_bk_upload",
+    "tfhe_mgpu_bk_upload_bmmp", "tfhe_mgpu_bk_free", "tfhe_mgpu_bootstrap_batch", "tfhe_mgpu_gates_batch", "tfhe_mgpu_last_timing",
 ]
 
 
@@ -167,10 +180,36 @@ def _ptr(x):
     if x is None:
         return None
     if _is_torch(x):
-        assert x.is_contiguous() and x.element_size() == 4
+        import torch
+        if x.dtype not in (torch.int32, torch.uint32) or not x.is_contiguous():
+            raise TypeError(f"expected a contiguous int32/uint32 tensor, got {x.dtype}, contiguous={x.is_contiguous()}")
         return x.data_ptr()
-    assert x.dtype == np.uint32 and x.flags["C_CONTIGUOUS"]
+    if x.dtype != np.uint32 or not x.flags["C_CONTIGUOUS"]:
+        raise TypeError(f"expected a C-contiguous uint32 array, got {x.dtype}")
     return x.ctypes.data
+
+
+def _shape(x):
+    return tuple(x.shape)
+
+
+def _rows(x, width, what):
+    """Batch size of x = [B, width] (or a single row [width]); anything else would be an out-of-bounds device access."""
+    sh = _shape(x)
+    if len(sh) == 1 and sh[0] == width:
+        return 1
+    if len(sh) == 2 and sh[1] == width:
+        return sh[0]
+    raise ValueError(f"{what}: expected shape [B, {width}] (or [{width}]), got {list(sh)}")
+
+
+def _check_out(out, shape, like, what="out"):
+    if _shape(out) != tuple(shape):
+        raise ValueError(f"{what}: expected shape {list(shape)}, got {list(_shape(out))}")
+    if _is_torch(out) != _is_torch(like):
+        raise ValueError(f"{what}: must live where the input lives (both numpy or both CUDA tensors)")
+    if _is_torch(out) and out.device != like.device:
+        raise ValueError(f"{what}: on {out.device}, input on {like.device}")
 
 
 def _u32(x):
@@ -305,16 +344,23 @@ class BootstrappingKey:
 
     def __init__(self, ctx, handle):
         self.ctx, self._h = ctx, handle
+        ctx._keys.add(self)
 
     def free(self):
         if self._h:
             lib().tfhe_bk_free(self._h)
             self._h = None
+            self.ctx._keys.discard(self)
+
+    @property
+    def path(self) -> int:
+        """Arithmetic path the key was transformed for (fixed at upload; independent of later Context.set_pbs_path calls)."""
+        return int(lib().tfhe_bk_get_path(self._h))
 
     def transformed(self) -> np.ndarray:
         """Host copy of the transformed BSK (u32 residues on the NTT path, float64 re/im pairs on the FFT path)."""
         nbytes = lib().tfhe_bk_transformed_bytes(self._h)
-        out = np.empty(nbytes // 8, dtype=np.float64) if self.ctx.pbs_path == PATH_FFT else np.empty(nbytes // 4, dtype=np.uint32)
+        out = np.empty(nbytes // 8, dtype=np.float64) if self.path == PATH_FFT else np.empty(nbytes // 4, dtype=np.uint32)
         self.ctx._ck(lib().tfhe_bk_read_transformed(self._h, out.ctypes.data, nbytes))
         return out
 
@@ -336,6 +382,8 @@ class Context:
             raise TfheError(rc, "no usable CUDA device: the PBS path has no CPU fallback")
         _check(rc, "tfhe_ctx_create")
         self._h = h
+        self.device = device
+        self._keys = weakref.WeakSet()   # live keys of this context: freed by close() before the context goes
         if path is not None:
             self.set_pbs_path(path)
 
@@ -367,8 +415,15 @@ class Context:
 
     def close(self):
         if self._h:
+            for k in list(self._keys):
+                k.free()
             lib().tfhe_ctx_destroy(self._h)
             self._h = None
+
+    def _on_device(self, *xs):
+        for x in xs:
+            if x is not None and _is_torch(x) and (not x.is_cuda or x.device.index != self.device):
+                raise ValueError(f"tensor on {x.device}: this context drives cuda:{self.device} (pass numpy arrays for host data)")
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(lib().tfhe_ctx_set_stream(self._h, cuda_stream_ptr))
@@ -394,10 +449,15 @@ class Context:
     def bootstrap(self, bk: BootstrappingKey, lwe_in, test_vectors, lut_idx=None, out=None):
         p = self.params
         lwe_in, tvs = _u32(lwe_in), _u32(test_vectors)
-        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
-        T = tvs.shape[0] if tvs.ndim == 2 else 1
+        B, T = _rows(lwe_in, p.n + 1, "lwe_in"), _rows(tvs, p.N, "test_vectors")
         idx = None if lut_idx is None else _u32(lut_idx)
-        out = _like(lwe_in, (B, p.n + 1)) if out is None else out
+        if idx is not None and _shape(idx) != (B,):
+            raise ValueError(f"lut_idx: expected shape [{B}], got {list(_shape(idx))}")
+        self._on_device(lwe_in, tvs, idx, out)
+        if out is None:
+            out = _like(lwe_in, (B, p.n + 1))
+        else:
+            _check_out(out, (B, p.n + 1), lwe_in)
         self._ck(lib().tfhe_bootstrap_batch(self._h, bk._h, _ptr(lwe_in), _ptr(tvs), T, _ptr(idx), B, _ptr(out)))
         return out
 
@@ -405,8 +465,14 @@ class Context:
     def gate(self, bk: BootstrappingKey, op, ct0, ct1, out=None):
         p = self.params
         ct0, ct1 = _u32(ct0), _u32(ct1)
-        B = ct0.shape[0] if ct0.ndim == 2 else 1
-        out = _like(ct0, (B, p.n + 1)) if out is None else out
+        B = _rows(ct0, p.n + 1, "ct0")
+        if _rows(ct1, p.n + 1, "ct1") != B:
+            raise ValueError("ct0 and ct1 must hold the same number of ciphertexts")
+        self._on_device(ct0, ct1, out)
+        if out is None:
+            out = _like(ct0, (B, p.n + 1))
+        else:
+            _check_out(out, (B, p.n + 1), ct0)
         if isinstance(op, (int, np.integer)):
             self._ck(lib().tfhe_gate_batch(self._h, bk._h, int(op), _ptr(ct0), _ptr(ct1), B, _ptr(out)))
         else:
@@ -419,10 +485,15 @@ class Context:
     def bootstrap_ks_first(self, bk: BootstrappingKey, lwe_in, test_vectors, lut_idx=None, out=None):
         p = self.params
         lwe_in, tvs = _u32(lwe_in), _u32(test_vectors)
-        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
-        T = tvs.shape[0] if tvs.ndim == 2 else 1
+        B, T = _rows(lwe_in, p.k * p.N + 1, "lwe_in"), _rows(tvs, p.N, "test_vectors")
         idx = None if lut_idx is None else _u32(lut_idx)
-        out = _like(lwe_in, (B, p.k * p.N + 1)) if out is None else out
+        if idx is not None and _shape(idx) != (B,):
+            raise ValueError(f"lut_idx: expected shape [{B}], got {list(_shape(idx))}")
+        self._on_device(lwe_in, tvs, idx, out)
+        if out is None:
+            out = _like(lwe_in, (B, p.k * p.N + 1))
+        else:
+            _check_out(out, (B, p.k * p.N + 1), lwe_in)
         self._ck(lib().tfhe_bootstrap_batch_ks_first(self._h, bk._h, _ptr(lwe_in), _ptr(tvs), T, _ptr(idx), B, _ptr(out)))
         return out
 
@@ -430,8 +501,14 @@ class Context:
     def gate_k(self, bk: BootstrappingKey, truth_table: int, cts, out=None):
         p = self.params
         cts = [_u32(c) for c in cts]
-        B = cts[0].shape[0] if cts[0].ndim == 2 else 1
-        out = _like(cts[0], (B, p.n + 1)) if out is None else out
+        B = _rows(cts[0], p.n + 1, "cts[0]")
+        if any(_rows(c, p.n + 1, "cts") != B for c in cts):
+            raise ValueError("all inputs of a k-input gate must hold the same number of ciphertexts")
+        self._on_device(*cts, out)
+        if out is None:
+            out = _like(cts[0], (B, p.n + 1))
+        else:
+            _check_out(out, (B, p.n + 1), cts[0])
         ptrs = (C.c_void_p * len(cts))(*[_ptr(c) for c in cts])
         self._ck(lib().tfhe_gate_k_batch(self._h, bk._h, len(cts), truth_table, ptrs, B, _ptr(out)))
         return out
@@ -462,6 +539,9 @@ class Context:
     def glwe_mul_monomial(self, glwe, index):
         glwe = _u32(glwe)
         index = np.ascontiguousarray(index, dtype=np.int64)
+        if _shape(glwe) != (len(index), self.params.k + 1, self.params.N):
+            raise ValueError(f"glwe: expected shape [{len(index)}, {self.params.k + 1}, {self.params.N}], got {list(_shape(glwe))}")
+        self._on_device(glwe)
         out = _like(glwe, glwe.shape)
         self._ck(lib().tfhe_glwe_mul_monomial(self._h, _ptr(glwe), index.ctypes.data, len(index), _ptr(out)))
         return out
@@ -469,7 +549,9 @@ class Context:
     def negacyclic_mul(self, a_small, g):
         """utils.rs:155-160 poly_mul: a_small int32 [B, N] with |a| <= 1024, g uint32 [B, N]."""
         a_small = np.ascontiguousarray(a_small, dtype=np.int32)
-        g = _u32(g)
+        g = np.ascontiguousarray(g, dtype=np.uint32)
+        if g.ndim != 2 or g.shape[1] != self.params.N or a_small.shape != g.shape:
+            raise ValueError(f"a_small, g: expected two [B, {self.params.N}] arrays, got {list(a_small.shape)} and {list(g.shape)}")
         out = np.empty(g.shape, dtype=np.uint32)
         self._ck(lib().tfhe_negacyclic_mul(self._h, a_small.ctypes.data, _ptr(g), g.shape[0], out.ctypes.data))
         return out
@@ -477,6 +559,9 @@ class Context:
     def external_product(self, bk, ggsw_index, glwe):
         glwe = _u32(glwe)
         gi = np.ascontiguousarray(ggsw_index, dtype=np.uint32)
+        if _shape(glwe) != (len(gi), self.params.k + 1, self.params.N):
+            raise ValueError(f"glwe: expected shape [{len(gi)}, {self.params.k + 1}, {self.params.N}], got {list(_shape(glwe))}")
+        self._on_device(glwe)
         out = _like(glwe, glwe.shape)
         self._ck(lib().tfhe_external_product(self._h, bk._h, gi.ctypes.data, _ptr(glwe), len(gi), _ptr(out)))
         return out
@@ -484,6 +569,10 @@ class Context:
     def cmux(self, bk, ggsw_index, ct0, ct1):
         ct0, ct1 = _u32(ct0), _u32(ct1)
         gi = np.ascontiguousarray(ggsw_index, dtype=np.uint32)
+        want = (len(gi), self.params.k + 1, self.params.N)
+        if _shape(ct0) != want or _shape(ct1) != want:
+            raise ValueError(f"ct0, ct1: expected shape {list(want)}, got {list(_shape(ct0))} and {list(_shape(ct1))}")
+        self._on_device(ct0, ct1)
         out = _like(ct0, ct0.shape)
         self._ck(lib().tfhe_cmux(self._h, bk._h, gi.ctypes.data, _ptr(ct0), _ptr(ct1), len(gi), _ptr(out)))
         return out
@@ -491,9 +580,11 @@ class Context:
     def blind_rotate(self, bk, lwe_in, test_vectors, lut_idx=None):
         p = self.params
         lwe_in, tvs = _u32(lwe_in), _u32(test_vectors)
-        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
-        T = tvs.shape[0] if tvs.ndim == 2 else 1
+        B, T = _rows(lwe_in, p.n + 1, "lwe_in"), _rows(tvs, p.N, "test_vectors")
         idx = None if lut_idx is None else _u32(lut_idx)
+        if idx is not None and _shape(idx) != (B,):
+            raise ValueError(f"lut_idx: expected shape [{B}], got {list(_shape(idx))}")
+        self._on_device(lwe_in, tvs, idx)
         out = _like(lwe_in, (B, p.k + 1, p.N))
         self._ck(lib().tfhe_blind_rotate(self._h, bk._h, _ptr(lwe_in), _ptr(tvs), T, _ptr(idx), B, _ptr(out)))
         return out
@@ -501,7 +592,10 @@ class Context:
     def sample_extract(self, glwe):
         p = self.params
         glwe = _u32(glwe)
+        if _shape(glwe)[-2:] != (p.k + 1, p.N):
+            raise ValueError(f"glwe: expected shape [B, {p.k + 1}, {p.N}], got {list(_shape(glwe))}")
         B = glwe.shape[0] if glwe.ndim == 3 else 1
+        self._on_device(glwe)
         out = _like(glwe, (B, p.k * p.N + 1))
         self._ck(lib().tfhe_sample_extract(self._h, _ptr(glwe), B, _ptr(out)))
         return out
@@ -509,14 +603,18 @@ class Context:
     def key_switch(self, bk, lwe_in):
         p = self.params
         lwe_in = _u32(lwe_in)
-        B = lwe_in.shape[0] if lwe_in.ndim == 2 else 1
+        B = _rows(lwe_in, p.k * p.N + 1, "lwe_in")
+        self._on_device(lwe_in)
         out = _like(lwe_in, (B, p.n + 1))
         self._ck(lib().tfhe_key_switch(self._h, bk._h, _ptr(lwe_in), B, _ptr(out)))
         return out
 
     def gate_linear(self, ct0, ct1):
         ct0, ct1 = _u32(ct0), _u32(ct1)
-        B = ct0.shape[0] if ct0.ndim == 2 else 1
+        B = _rows(ct0, self.params.n + 1, "ct0")
+        if _shape(ct1) != _shape(ct0):
+            raise ValueError("ct0 and ct1 must have the same shape")
+        self._on_device(ct0, ct1)
         out = _like(ct0, ct0.shape)
         self._ck(lib().tfhe_gate_linear(self._h, _ptr(ct0), _ptr(ct1), B, _ptr(out)))
         return out
@@ -537,3 +635,117 @@ class Context:
         out = (C.c_double * 3)()
         self._ck(lib().tfhe_last_timing(self._h, C.byref(out)))
         return {"blind_rotate_ms": out[0], "key_switch_ms": out[1], "total_ms": out[2]}
+
+
+# ------------------------------------------------------------------ one process, all GPUs of the box (include/tfhe_b200.h "multi-GPU")
+class MultiGpuKey:
+    """BootstrappingKey replicated on every device of a MultiGpuContext."""
+
+    def __init__(self, m, handle):
+        self.m, self._h = m, handle
+        m._keys.add(self)
+
+    def free(self):
+        if self._h:
+            lib().tfhe_mgpu_bk_free(self._h)
+            self._h = None
+            self.m._keys.discard(self)
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MultiGpuContext:
+    """tfhe_mgpu: batches are split into contiguous balanced ranges, one per GPU, keys replicated.
+
+    numpy inputs: every GPU copies its own shard in and out; CUDA tensors (all on ONE of the devices): NCCL
+    send/recv scatter, local bootstraps, NCCL gather into the output tensor on that device.  Same bits as Context.
+    """
+
+    def __init__(self, params: TfheParams, n_gpus: int, devices=None):
+        self.params = params
+        h = C.c_void_p()
+        dev = None if devices is None else (C.c_int * n_gpus)(*devices)
+        rc = lib().tfhe_mgpu_create(C.byref(params), n_gpus, dev, C.byref(h))
+        if rc == TFHE_E_CUDA:
+            raise TfheError(rc, "no usable CUDA device: the PBS path has no CPU fallback")
+        _check(rc, "tfhe_mgpu_create")
+        self._h = h
+        self.n_gpus = n_gpus
+        self.devices = list(range(n_gpus)) if devices is None else list(devices)
+        self._keys = weakref.WeakSet()
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise TfheError(rc, (lib().tfhe_mgpu_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if self._h:
+            for k in list(self._keys):
+                k.free()
+            lib().tfhe_mgpu_destroy(self._h)
+            self._h = None
+
+    def launch_count(self) -> int:
+        return sum(int(lib().tfhe_ctx_launch_count(lib().tfhe_mgpu_ctx(self._h, i))) for i in range(self.n_gpus))
+
+    def upload_key(self, bsk, ksk) -> MultiGpuKey:
+        bsk, ksk = np.ascontiguousarray(bsk, dtype=np.uint32), np.ascontiguousarray(ksk, dtype=np.uint32)
+        h = C.c_void_p()
+        self._ck(lib().tfhe_mgpu_bk_upload(self._h, bsk.ctypes.data, ksk.ctypes.data, C.byref(h)))
+        return MultiGpuKey(self, h)
+
+    def upload_key_bmmp(self, bsk3, ksk) -> MultiGpuKey:
+        bsk3, ksk = np.ascontiguousarray(bsk3, dtype=np.uint32), np.ascontiguousarray(ksk, dtype=np.uint32)
+        h = C.c_void_p()
+        self._ck(lib().tfhe_mgpu_bk_upload_bmmp(self._h, bsk3.ctypes.data, ksk.ctypes.data, C.byref(h)))
+        return MultiGpuKey(self, h)
+
+    def _same_place(self, *xs):
+        dev = {(x.device.index if _is_torch(x) else None) for x in xs if x is not None}
+        if len(dev) != 1:
+            raise ValueError("inputs and output must be all numpy arrays or all CUDA tensors on one device")
+        d = dev.pop()
+        if d is not None and d not in self.devices:
+            raise ValueError(f"tensors on cuda:{d}, which is not one of this context's devices {self.devices}")
+
+    def bootstrap(self, bk: MultiGpuKey, lwe_in, test_vectors, lut_idx=None, out=None):
+        p = self.params
+        lwe_in = _u32(lwe_in)
+        tvs = np.ascontiguousarray(test_vectors, dtype=np.uint32)
+        B, T = _rows(lwe_in, p.n + 1, "lwe_in"), _rows(tvs, p.N, "test_vectors")
+        idx = None if lut_idx is None else np.ascontiguousarray(lut_idx, dtype=np.uint32)
+        if idx is not None and idx.shape != (B,):
+            raise ValueError(f"lut_idx: expected shape [{B}], got {list(idx.shape)}")
+        if out is None:
+            out = _like(lwe_in, (B, p.n + 1))
+        else:
+            _check_out(out, (B, p.n + 1), lwe_in)
+        self._same_place(lwe_in, out)
+        self._ck(lib().tfhe_mgpu_bootstrap_batch(self._h, bk._h, _ptr(lwe_in), tvs.ctypes.data, T, None if idx is None else idx.ctypes.data, B, _ptr(out)))
+        return out
+
+    def gate(self, bk: MultiGpuKey, ops, ct0, ct1, out=None):
+        p = self.params
+        ct0, ct1 = _u32(ct0), _u32(ct1)
+        B = _rows(ct0, p.n + 1, "ct0")
+        if _rows(ct1, p.n + 1, "ct1") != B:
+            raise ValueError("ct0 and ct1 must hold the same number of ciphertexts")
+        ops = np.full(B, int(ops), dtype=np.uint8) if isinstance(ops, (int, np.integer)) else np.ascontiguousarray(ops, dtype=np.uint8)
+        if ops.shape != (B,):
+            raise ValueError(f"ops: expected shape [{B}]")
+        if out is None:
+            out = _like(ct0, (B, p.n + 1))
+        else:
+            _check_out(out, (B, p.n + 1), ct0)
+        self._same_place(ct0, ct1, out)
+        self._ck(lib().tfhe_mgpu_gates_batch(self._h, bk._h, ops.ctypes.data, _ptr(ct0), _ptr(ct1), B, _ptr(out)))
+        return out
+
+    def last_timing(self):
+        out = (C.c_double * 4)()
+        self._ck(lib().tfhe_mgpu_last_timing(self._h, C.byref(out)))
+        return {"scatter_ms": out[0], "compute_ms": out[1], "gather_ms": out[2], "total_ms": out[3]}

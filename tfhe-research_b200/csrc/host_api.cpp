@@ -16,7 +16,9 @@
 namespace tfhe_host {
 
 // ---- seeded RNG: xoshiro256** seeded by splitmix64(seed ^ domain*0x9E3779B97F4A7C15 ^ index*0xD1B54A32D192ED03);
-// domains: 1 GGSW i, 2 KSK block s_index, 3 lwe_sk, 4 glwe_sk, 5 client encryption index ----
+// domains: 1 GGSW i, 2 KSK block s_index, 3 lwe_sk, 4 glwe_sk, 5 client encryption index, 6 GGSW g of a BMMP key triple.
+// This seeded generator is a TEST HARNESS (reproducible keys and inputs for parity tests and benchmarks; the reference
+// itself uses thread_rng), NOT a CSPRNG: do not generate production keys with it. ----
 struct Rng {
     uint64_t s[4];
     static uint64_t splitmix(uint64_t &x) {
@@ -201,6 +203,7 @@ int tfhe_params_validate(const tfhe_params *p) {
 // test_vector.rs:38-67
 int tfhe_test_vector_from_lut(const tfhe_params *p, const uint32_t *lut, size_t lut_len, uint32_t *tv) {
     if (!p || !lut || !tv) return TFHE_E_PARAM;
+    if (p->glwe_poly_degree > 31 || p->log_p > p->glwe_poly_degree) return TFHE_E_PARAM;   // 2^log_p must divide N (rep = N / 2^log_p >= 1)
     const uint32_t pm = 1u << p->log_p;
     if (lut_len != pm) return TFHE_E_ASSERT;  // assert! test_vector.rs:41
     const size_t N = (size_t)1 << p->glwe_poly_degree;
@@ -217,7 +220,7 @@ int tfhe_test_vector_from_lut(const tfhe_params *p, const uint32_t *lut, size_t 
 }
 
 int tfhe_test_vector_identity(const tfhe_params *p, uint32_t *tv) {
-    if (!p) return TFHE_E_PARAM;
+    if (!p || p->glwe_poly_degree > 31 || p->log_p > p->glwe_poly_degree) return TFHE_E_PARAM;
     std::vector<uint32_t> lut(1u << p->log_p);
     for (uint32_t i = 0; i < lut.size(); i++) lut[i] = i;
     return tfhe_test_vector_from_lut(p, lut.data(), lut.size(), tv);
@@ -225,6 +228,7 @@ int tfhe_test_vector_identity(const tfhe_params *p, uint32_t *tv) {
 
 int tfhe_test_vector_boolean(const tfhe_params *p, int gate, uint32_t *tv) {
     if (!p || gate < TFHE_AND || gate > TFHE_XOR) return TFHE_E_PARAM;
+    if (p->glwe_poly_degree > 31 || p->log_p > p->glwe_poly_degree) return TFHE_E_PARAM;
     std::vector<uint32_t> lut(1u << p->log_p);
     for (uint32_t i = 0; i < lut.size(); i++) {  // test_vector.rs:14-17: left = bit 1, right = bit 0
         const uint32_t l = (i >> 1) & 1u, r = i & 1u;
@@ -234,7 +238,7 @@ int tfhe_test_vector_boolean(const tfhe_params *p, int gate, uint32_t *tv) {
 }
 
 int tfhe_lwe_encode(const tfhe_params *p, uint32_t m, uint32_t *out) {
-    if (!p || !out) return TFHE_E_PARAM;
+    if (!p || !out || p->log_p + p->padding_bits > p->log_q || p->log_q > 32 || p->log_p > 31) return TFHE_E_PARAM;
     if (!(m < (1u << p->log_p))) return TFHE_E_ASSERT;  // lwe.rs:84
     *out = m << (p->log_q - (p->log_p + p->padding_bits));
     return TFHE_OK;
@@ -290,7 +294,7 @@ int tfhe_keygen_bmmp(const tfhe_params *pp, uint64_t seed, uint32_t *lwe_sk, uin
         const size_t i = g / 3, which = g % 3;
         const uint32_t s0 = lwe_sk[2 * i], s1 = lwe_sk[2 * i + 1];
         const uint32_t m = which == 0 ? s0 * s1 : which == 1 ? s0 * (1u - s1) : s1 * (1u - s0);
-        Rng r(seed, 5, g);
+        Rng r(seed, 6, g);   // own domain: domain 5 is the client-encryption stream (a shared stream would leak the noise)
         encrypt_ggsw(p, glwe_sk, m, r, bsk3 + g * ggsw_sz);
     });
     gen_ksk(p, seed, lwe_sk, glwe_sk, ksk);

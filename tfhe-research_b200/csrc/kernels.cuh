@@ -1,13 +1,15 @@
-// kernels.cuh -- sm_100a kernels of the PBS path.  No tensor cores: this is modular integer
-// arithmetic (IMAD / IMAD.WIDE on the FMA pipe, IADD3/LOP3/VIADDMNMX on the ALU pipe).
+// kernels.cuh -- sm_100a kernels of the PBS path.  The blind rotation is modular integer arithmetic on the CUDA cores
+// (IMAD / IMAD.WIDE on the FMA pipe, IADD3/LOP3/VIADDMNMX on the ALU pipe; the FP64-FFT form is in kernels_fft.cuh);
+// the key-switching product -- a genuine integer matrix product -- also has an exact integer-tensor-core form.
 //
 //   K2 pbs_kernel           blind rotation = n fused CMUX steps per ciphertext, accumulator resident
 //                           in shared memory (bootstrapping.rs:58-105, ggsw.rs:132-178); GGSW rows are
 //                           streamed global -> shared with cp.async.bulk (TMA) + mbarrier; also runs a
 //                           single external product / CMUX for the sub-operation entry points
 //   K0 bsk_transform_kernel raw BSK -> 2-prime NTT domain, pre-scaled by N^-1 (one-off at upload)
-//   K3+K4 ks_digits_kernel / ks_gemm_kernel   sample extract + KS decomposition, then the wrapping
-//                           u32 accumulation against the KSK (bootstrapping.rs:122-156,
+//   K3+K4 ks_digits_kernel, then ks_mma_kernel (default; s8 x u8 IMMA over the key's byte planes, exact) /
+//                           ks_gemm_kernel (IMAD) / ks_gemv_kernel (batches <= 8): sample extract + KS decomposition,
+//                           then the wrapping u32 accumulation against the KSK (bootstrapping.rs:122-156,
 //                           key_switching.rs:63-103)
 //   K5 small element-wise kernels (gate linear part lwe.rs:9-23, NAND-style negation, sub-ops)
 #pragma once
@@ -34,8 +36,9 @@ struct PbsArgs {
     const uint32_t *in0, *in1; // [B][P][N]
     const uint32_t *ggsw_index;  // [B]
     uint32_t *glwe_out;        // [B][P][N]
-    uint32_t *err_flag;        // bit 0: a test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out
+    uint32_t *err_flag;        // bit 0: a test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out; bit 2: lut_idx out of range
     uint32_t n, batch, mode, log_p, enc_shift;
+    uint32_t n_luts;           // lut_idx[b] >= n_luts sets err_flag bit 2 and selects test vector 0
     uint32_t skew_ns, skew_div, skew_mod;  // start-up stagger of co-resident CTAs (see pbs_kernel)
 };
 
@@ -57,18 +60,33 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// bounded wait (a hung kernel would cost a GPU strike): ~seconds of polling, then flag + trap
+// Bounded wait (a hung kernel would cost a GPU strike).  The bound is wall-clock (%globaltimer, 10 s), not a spin count, so a
+// debugger or heavy time-slicing cannot trip it.  On expiry the waiter sets bit 1 of err_flag and RETURNS: every other
+// waiter of the grid sees the bit at its next poll and returns too, so the kernel runs to completion with invalid data
+// (all addresses are data independent) and the host reports TFHE_E_CUDA -- no trap, no sticky context error.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool mbar_try_once(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t *err_flag) {
-    uint32_t done = 0;
-    for (uint32_t spin = 0; !done; spin++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-        if (!done && spin > (1u << 26)) {
-            atomicOr(err_flag, 2u);
-            __trap();
+    if (mbar_try_once(bar, parity)) return;   // the common case
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 1; !mbar_try_once(bar, parity); spin++) {
+        if ((spin & 255u) == 0u) {
+            if (*(volatile uint32_t *)err_flag & 2u) return;                      // another waiter timed out: abandon
+            const unsigned long long now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 10000000000ull) { atomicOr(err_flag, 2u); return; }
         }
     }
 }
@@ -193,7 +211,12 @@ __global__ void __launch_bounds__(K::THREADS, MINB) pbs_kernel(const __grid_cons
         __syncthreads();
         // acc = trivial GLWE of the encoded test vector times X^{-b~}  (bootstrapping.rs:79-86)
         const uint32_t b = at[a.n];
-        const uint32_t *lut = a.luts + (size_t)(a.lut_idx ? __ldg(a.lut_idx + ct) : 0u) * K::N;
+        uint32_t li = a.lut_idx ? __ldg(a.lut_idx + ct) : 0u;
+        if (li >= a.n_luts) {   // never read a test vector out of bounds: flag it (host returns TFHE_E_PARAM) and fall back to 0
+            atomicOr(a.err_flag, 4u);
+            li = 0u;
+        }
+        const uint32_t *lut = a.luts + (size_t)li * K::N;
         for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += K::THREADS) {
             const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
             uint32_t v = 0;

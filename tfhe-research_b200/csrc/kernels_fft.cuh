@@ -27,9 +27,10 @@ struct FftArgs {
     const uint32_t *in0, *in1; // mode 1 (out = ExtProd(G, in0)) / mode 2 (out = ExtProd(G, in1-in0)+in0): [B][P][N]
     const uint32_t *ggsw_index;
     uint32_t *glwe_out;        // [B][P][N]
-    uint32_t *err_flag;        // bit 0: test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out
+    uint32_t *err_flag;        // bit 0: test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out; bit 2: lut_idx out of range
     unsigned long long *margin;  // largest |x - rint(x)| before rounding (bits of a non-negative double), CHECK only
     uint32_t n, batch, mode, log_p, enc_shift;
+    uint32_t n_luts;           // lut_idx[b] >= n_luts sets err_flag bit 2 and selects test vector 0
 };
 
 // TFHE_FFT_ABLATE (bit mask, measurement only -- results are WRONG when set): 1 = constant digits instead of the
@@ -167,7 +168,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         team_bar_id(team_bar, K::TEAM_THREADS);
         // acc = trivial GLWE of the encoded test vector times X^{-b~}  (bootstrapping.rs:79-86)
         const uint32_t b = at[a.n];
-        const uint32_t *lut = a.luts + (size_t)(a.lut_idx ? __ldg(a.lut_idx + ct) : 0u) * K::N;
+        uint32_t li = a.lut_idx ? __ldg(a.lut_idx + ct) : 0u;
+        if (li >= a.n_luts) {   // never read a test vector out of bounds: flag it (host returns TFHE_E_PARAM) and fall back to 0
+            atomicOr(a.err_flag, 4u);
+            li = 0u;
+        }
+        const uint32_t *lut = a.luts + (size_t)li * K::N;
         for (uint32_t idx = tt; idx < (uint32_t)(K::P * K::N); idx += K::TEAM_THREADS) {
             const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
             uint32_t v = 0;

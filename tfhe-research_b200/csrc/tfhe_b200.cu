@@ -57,6 +57,7 @@ struct tfhe_ctx {
     int sm_count = 148;
     cudaEvent_t ev[5] = {};
     double last_ms[3] = {0, 0, 0};
+    std::vector<tfhe_bk *> keys;             // keys uploaded through this ctx and not yet freed (orphaned by tfhe_ctx_destroy)
     size_t N() const { return (size_t)1 << p.glwe_poly_degree; }
     size_t k() const { return p.glwe_dimension; }
     size_t n() const { return p.lwe_dimension; }
@@ -66,7 +67,8 @@ struct tfhe_ctx {
 };
 
 struct tfhe_bk {
-    tfhe_ctx *ctx = nullptr;
+    tfhe_ctx *ctx = nullptr;        // null once the context is gone: the key can then only be freed
+    int device = 0;                 // where the allocations below live (tfhe_bk_free does not touch ctx)
     int path = TFHE_PATH_NTT;
     bool bmmp = false;              // key triples of the unrolled-by-two blind rotation (FFT path only)
     uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]                      (TFHE_PATH_NTT)
@@ -208,7 +210,7 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     f.lwe_in = a.lwe_in; f.luts = a.luts; f.lut_idx = a.lut_idx;
     f.in0 = a.in0; f.in1 = a.in1; f.ggsw_index = a.ggsw_index;
     f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
-    f.n = a.n; f.batch = a.batch; f.mode = a.mode; f.log_p = a.log_p; f.enc_shift = a.enc_shift;
+    f.n = a.n; f.batch = a.batch; f.mode = a.mode; f.log_p = a.log_p; f.enc_shift = a.enc_shift; f.n_luts = a.n_luts;
     const size_t smem = fft_smem_bytes<K>(a.n);
     if (smem > 227 * 1024) return fail(ctx, TFHE_E_PARAM, "lwe_dimension too large for the FFT path's shared-memory layout");
     auto kern = fft::pbs_fft_kernel<K, BMMP>;
@@ -366,12 +368,12 @@ cudaError_t copy_ksk(tfhe_ctx *ctx, tfhe_bk *bk, const uint32_t *ksk) {
 
 int check_bk(tfhe_ctx *ctx, const tfhe_bk *bk) {
     if (!ctx) return TFHE_E_PARAM;
-    if (!bk || bk->ctx != ctx) return fail(ctx, TFHE_E_PARAM, "bootstrapping key does not belong to this context");
+    if (!bk || bk->ctx != ctx) return fail(ctx, TFHE_E_PARAM, "bootstrapping key does not belong to this context (or its context was destroyed)");
     return TFHE_OK;
 }
 
 // core of bootstrap: d_in [B][n+1] device, luts/lut_idx device (lut_idx may be null) -> d_out [B][n+1]
-int run_bootstrap(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *d_in, const uint32_t *d_luts, const uint32_t *d_lut_idx,
+int run_bootstrap(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *d_in, const uint32_t *d_luts, size_t n_luts, const uint32_t *d_lut_idx,
                   size_t batch, uint32_t *d_out) {
     CU(ctx->glwe.ensure(batch * ctx->glwe_words() * 4));
     CU(cudaMemsetAsync(ctx->d_err, 0, 4, ctx->stream));
@@ -385,6 +387,7 @@ int run_bootstrap(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *d_in, const 
     a.n = (uint32_t)ctx->n(); a.batch = (uint32_t)batch; a.mode = 0;
     a.log_p = ctx->p.log_p;
     a.enc_shift = ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits);
+    a.n_luts = (uint32_t)n_luts;
     if (const char *e = getenv("TFHE_B200_SKEW_NS")) {
         a.skew_ns = (uint32_t)atoi(e);
         a.skew_div = (uint32_t)ctx->sm_count;
@@ -400,6 +403,13 @@ int run_bootstrap(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *d_in, const 
     CU(cudaEventRecord(ctx->ev[3], ctx->stream));
     return TFHE_OK;
 }
+// err_flag written by the blind-rotation kernels (kernels.cuh PbsArgs::err_flag)
+int decode_err_flag(tfhe_ctx *ctx, uint32_t flag) {
+    if (flag & 2u) return fail(ctx, TFHE_E_CUDA, "TMA bulk copy wait timed out in the blind-rotation kernel (results are invalid)");
+    if (flag & 4u) return fail(ctx, TFHE_E_PARAM, "lut_idx entry >= n_luts");
+    if (flag & 1u) return fail(ctx, TFHE_E_ASSERT, "test vector entry >= 2^log_p (reference assert! glwe.rs:144)");
+    return TFHE_OK;
+}
 int finish_timed(tfhe_ctx *ctx) {
     CU(cudaEventRecord(ctx->ev[4], ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -409,9 +419,7 @@ int finish_timed(tfhe_ctx *ctx) {
     CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4])); ctx->last_ms[2] = t;
     uint32_t flag = 0;
     CU(cudaMemcpy(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost));
-    if (flag & 2u) return fail(ctx, TFHE_E_CUDA, "TMA bulk copy wait timed out in pbs_kernel");
-    if (flag) return fail(ctx, TFHE_E_ASSERT, "test vector entry >= 2^log_p (reference assert! glwe.rs:144)");
-    return TFHE_OK;
+    return decode_err_flag(ctx, flag);
 }
 
 template <class K>
@@ -445,7 +453,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     ctx->ks_id = tfhe_host::ks_config_id(*p);
     auto bail = [&](const char *what) {
         fprintf(stderr, "tfhe_ctx_create: %s failed: %s\n", what, cudaGetErrorString(cudaGetLastError()));
-        delete ctx;
+        tfhe_ctx_destroy(ctx);   // releases whatever was created so far (stream, events, device tables)
         return (int)TFHE_E_CUDA;
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
@@ -502,6 +510,8 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
 void tfhe_ctx_destroy(tfhe_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    for (tfhe_bk *k : ctx->keys) k->ctx = nullptr;   // keys outlive the ctx as plain allocations: tfhe_bk_free still works
+    ctx->keys.clear();
     for (DevBuf *b : {&ctx->in0, &ctx->in1, &ctx->in2, &ctx->out, &ctx->glwe, &ctx->digits, &ctx->body, &ctx->luts, &ctx->lutidx, &ctx->misc})
         b->release();
     for (int pr = 0; pr < 2; pr++)
@@ -530,6 +540,7 @@ int tfhe_ctx_set_stream(tfhe_ctx *ctx, void *s) {
     return TFHE_OK;
 }
 uint64_t tfhe_ctx_launch_count(const tfhe_ctx *ctx) { return ctx ? ctx->launches : 0; }
+void *tfhe_ctx_get_stream(const tfhe_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path) {
     if (!ctx) return TFHE_E_PARAM;
@@ -569,6 +580,7 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     const size_t ksk_words = ctx->kd() * (ctx->n() + 1);
     tfhe_bk *bk = new tfhe_bk();
     bk->ctx = ctx;
+    bk->device = ctx->device;
     bk->path = ctx->path;
     auto cleanup = [&]() { tfhe_bk_free(bk); };
     cudaError_t e;
@@ -596,6 +608,7 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     if (d_raw) cudaFree(d_raw);
     if (rc == TFHE_OK && es != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(es));
     if (rc != TFHE_OK) { cleanup(); return rc; }
+    ctx->keys.push_back(bk);
     *out = bk;
     return TFHE_OK;
 }
@@ -610,6 +623,7 @@ int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk
     const size_t bsk_words = n_ggsw * ctx->ggsw_words(), ksk_words = ctx->kd() * (ctx->n() + 1);
     tfhe_bk *bk = new tfhe_bk();
     bk->ctx = ctx;
+    bk->device = ctx->device;
     bk->path = TFHE_PATH_FFT;
     bk->bmmp = true;
     auto cleanup = [&]() { tfhe_bk_free(bk); };
@@ -634,13 +648,19 @@ int tfhe_bk_upload_bmmp(tfhe_ctx *ctx, const uint32_t *bsk3, const uint32_t *ksk
     if (d_raw) cudaFree(d_raw);
     if (rc == TFHE_OK && es != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(es));
     if (rc != TFHE_OK) { cleanup(); return rc; }
+    ctx->keys.push_back(bk);
     *out = bk;
     return TFHE_OK;
 }
 
 void tfhe_bk_free(tfhe_bk *bk) {
     if (!bk) return;
-    if (bk->ctx) cudaSetDevice(bk->ctx->device);
+    if (bk->ctx) {
+        auto &ks = bk->ctx->keys;
+        for (size_t i = 0; i < ks.size(); i++)
+            if (ks[i] == bk) { ks.erase(ks.begin() + i); break; }
+    }
+    cudaSetDevice(bk->device);
     if (bk->d_bsk_ntt) cudaFree(bk->d_bsk_ntt);
     if (bk->d_bsk_fft) cudaFree(bk->d_bsk_fft);
     if (bk->d_ksk) cudaFree(bk->d_ksk);
@@ -653,6 +673,7 @@ size_t tfhe_bk_transformed_bytes(const tfhe_bk *bk) {
     if (bk->bmmp) return fft_key_bytes(bk->ctx) / bk->ctx->n() * (3 * (bk->ctx->n() / 2));
     return bk->path == TFHE_PATH_FFT ? fft_key_bytes(bk->ctx) : bk->ctx->n() * bk->ctx->ggsw_words() * 2 * 4;
 }
+int tfhe_bk_get_path(const tfhe_bk *bk) { return bk ? bk->path : TFHE_E_PARAM; }
 int tfhe_bk_read_transformed(const tfhe_bk *bk, void *out, size_t bytes) {
     if (!bk || !bk->ctx || !out || bytes != tfhe_bk_transformed_bytes(bk)) return TFHE_E_PARAM;
     tfhe_ctx *ctx = bk->ctx;
@@ -677,7 +698,7 @@ int tfhe_bootstrap_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_i
     if ((rc = stage_in(ctx, luts, n_luts * ctx->N() * 4, ctx->luts, &d_luts))) return rc;
     if (lut_idx && (rc = stage_in(ctx, lut_idx, batch * 4, ctx->lutidx, &d_idx))) return rc;
     if ((rc = stage_out(ctx, lwe_out, io_bytes, ctx->out, &d_out))) return rc;
-    if ((rc = run_bootstrap(ctx, bk, (const uint32_t *)d_in, (const uint32_t *)d_luts, (const uint32_t *)d_idx, batch, (uint32_t *)d_out))) return rc;
+    if ((rc = run_bootstrap(ctx, bk, (const uint32_t *)d_in, (const uint32_t *)d_luts, n_luts, (const uint32_t *)d_idx, batch, (uint32_t *)d_out))) return rc;
     if ((rc = finish_out(ctx, lwe_out, io_bytes, d_out))) return rc;
     return finish_timed(ctx);
 }
@@ -718,7 +739,7 @@ int tfhe_gates_batch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint8_t *gates, con
     gate_linear_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)d0, (const uint32_t *)d1, (uint32_t *)ctx->in2.p, len);
     CU(cudaGetLastError());
     ctx->launches++;
-    if ((rc = run_bootstrap(ctx, bk, (const uint32_t *)ctx->in2.p, (const uint32_t *)ctx->luts.p, (const uint32_t *)ctx->lutidx.p, batch, (uint32_t *)d_out))) return rc;
+    if ((rc = run_bootstrap(ctx, bk, (const uint32_t *)ctx->in2.p, (const uint32_t *)ctx->luts.p, 3, (const uint32_t *)ctx->lutidx.p, batch, (uint32_t *)d_out))) return rc;
     if (any_neg) {
         uint32_t one = 1u << (ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits));
         gate_negate_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>((uint32_t *)d_out, (const uint8_t *)ctx->misc.p, 0, (uint32_t)ctx->n(), (uint32_t)batch, one);
@@ -770,6 +791,7 @@ int tfhe_bootstrap_batch_ks_first(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32
     a.n = (uint32_t)ctx->n(); a.batch = (uint32_t)batch; a.mode = 0;
     a.log_p = ctx->p.log_p;
     a.enc_shift = ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits);
+    a.n_luts = (uint32_t)n_luts;
     if ((rc = launch_pbs(ctx, a, bk))) return rc;
     const size_t total = batch * kN1;
     sample_extract_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>((const uint32_t *)ctx->glwe.p, (uint32_t *)d_out, (uint32_t)ctx->k(),
@@ -787,9 +809,7 @@ int tfhe_bootstrap_batch_ks_first(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32
     CU(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[4])); ctx->last_ms[2] = t;
     uint32_t flag = 0;
     CU(cudaMemcpy(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost));
-    if (flag & 2u) return fail(ctx, TFHE_E_CUDA, "TMA bulk copy wait timed out in the blind-rotation kernel");
-    if (flag) return fail(ctx, TFHE_E_ASSERT, "test vector entry >= 2^log_p (reference assert! glwe.rs:144)");
-    return TFHE_OK;
+    return decode_err_flag(ctx, flag);
 }
 
 int tfhe_gate_k_batch(tfhe_ctx *ctx, const tfhe_bk *bk, uint32_t k_inputs, uint32_t truth_table, const uint32_t *const *cts, size_t batch,
@@ -827,7 +847,7 @@ int tfhe_gate_k_batch(tfhe_ctx *ctx, const tfhe_bk *bk, uint32_t k_inputs, uint3
         ctx->launches++;
         d_acc = ctx->in2.p;   // in place from the second step on: element-wise, each thread reads before it writes
     }
-    if ((rc = run_bootstrap(ctx, bk, (const uint32_t *)d_acc, (const uint32_t *)ctx->luts.p, nullptr, batch, (uint32_t *)d_out))) return rc;
+    if ((rc = run_bootstrap(ctx, bk, (const uint32_t *)d_acc, (const uint32_t *)ctx->luts.p, 1, nullptr, batch, (uint32_t *)d_out))) return rc;
     if (negate) {
         const uint32_t one = 1u << (ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits));
         gate_negate_kernel<<<(unsigned)((len + 255) / 256), 256, 0, ctx->stream>>>((uint32_t *)d_out, nullptr, 1, (uint32_t)ctx->n(), (uint32_t)batch, one);
@@ -959,13 +979,13 @@ int tfhe_blind_rotate(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *lwe_in, 
     a.n = (uint32_t)ctx->n(); a.batch = (uint32_t)batch; a.mode = 0;
     a.log_p = ctx->p.log_p;
     a.enc_shift = ctx->p.log_q - (ctx->p.log_p + ctx->p.padding_bits);
+    a.n_luts = (uint32_t)n_luts;
     if ((rc = launch_pbs(ctx, a, bk))) return rc;
     if ((rc = finish_out(ctx, glwe_out, out_bytes, d_out))) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     uint32_t flag = 0;
     CU(cudaMemcpy(&flag, ctx->d_err, 4, cudaMemcpyDeviceToHost));
-    if (flag) return fail(ctx, TFHE_E_ASSERT, "test vector entry >= 2^log_p (reference assert! glwe.rs:144)");
-    return TFHE_OK;
+    return decode_err_flag(ctx, flag);
 }
 
 int tfhe_sample_extract(tfhe_ctx *ctx, const uint32_t *glwe, size_t batch, uint32_t *lwe_out) {
