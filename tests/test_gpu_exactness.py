@@ -1,0 +1,183 @@
+"""Exactness of the FP64-FFT path on the GPU (-m gpu): the kernel variant that records the rounding margin (CHECK) on
+adversarial inputs, whole-batch agreement of the FFT path with the all-integer 2-prime NTT path for every preset, and
+the BMMP instantiation of the reference's own parameter set (P0).
+
+The FFT path rounds floating-point values to integers; DESIGN.md section 3b bounds the distance to the integer a priori
+(<= 2^-9 incl. derived twiddles).  These tests measure it: every value the kernel rounds must be closer than 2^-6 to an
+integer, and the results must equal exact integer arithmetic (the oracle's O(N^2) products, or the NTT path).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import tfhe_research_b200 as T
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+FIELDS = [f for f, _ in T.TfheParams._fields_]
+MARGIN = 2.0 ** -6
+
+
+def oparams(p):
+    return orc.params(**{f: getattr(p, f) for f in FIELDS})
+
+
+def adversarial_words(rng, shape, kind):
+    """kind 'key': every centred 16-bit limb at an extreme (0x7FFF7FFF -> lo = hi = +32767; 0x80008000 -> lo = -32768,
+    hi = -32767), random signs; kind 'glwe': words whose digits sit at the extremes of the reference's digit set
+    (windows of B-1 plus a carry give +B -- the H3 quirk --, windows of B/2 give -B/2)."""
+    pick = rng.integers(0, 2, shape) == 1
+    if kind == "key":
+        return np.where(pick, np.uint32(0x7FFF7FFF), np.uint32(0x80008000)).astype(np.uint32)
+    return np.where(pick, np.uint32(0xFFFFFF80), np.uint32(0x80808080)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("preset", ["P0", "P1", "P2"])
+def test_adversarial_external_product_margin(preset):
+    """One external product / CMUX with every digit and every key limb at an extreme, against the oracle."""
+    n = 4
+    p = T.TfheParams.preset(preset, lwe_dimension=n)
+    o = oparams(p)
+    L = orc.lib()
+    rng = np.random.default_rng(31)
+    bsk = adversarial_words(rng, p.bsk_words, "key")
+    bsk[:p.ggsw_words] = np.uint32(0x7FFF7FFF)                      # GGSW 0: every limb +32767, no sign cancellation at all
+    ksk = rng.integers(0, 1 << 32, p.ksk_words, dtype=np.uint64).astype(np.uint32)
+    ctx = T.Context(p, 0, path=T.PATH_FFT)
+    ctx.set_fft_check(True)
+    bk = ctx.upload_key(bsk, ksk)
+    B = 2 * n
+    glwe = adversarial_words(rng, (B, p.k + 1, p.N), "glwe")
+    glwe[0] = np.uint32(0xFFFFFF80)                                   # all digits equal: the largest possible sums
+    glwe[1] = np.uint32(0x80808080)
+    gi = (np.arange(B) % n).astype(np.uint32)
+    got = ctx.external_product(bk, gi, glwe)
+    gg = p.ggsw_words
+    for b in range(B):
+        exp = orc.z(p.glwe_words)
+        L.orc_external_product(C.byref(o), bsk[int(gi[b]) * gg:(int(gi[b]) + 1) * gg], glwe[b].reshape(-1), exp)
+        assert np.array_equal(got[b].reshape(-1), exp), b
+    m1 = ctx.fft_rounding_margin()
+    other = adversarial_words(rng, (B, p.k + 1, p.N), "glwe")
+    got = ctx.cmux(bk, gi, glwe, other)
+    for b in range(0, B, 3):
+        exp = orc.z(p.glwe_words)
+        L.orc_cmux(C.byref(o), bsk[int(gi[b]) * gg:(int(gi[b]) + 1) * gg], glwe[b].reshape(-1), other[b].copy().reshape(-1), exp)
+        assert np.array_equal(got[b].reshape(-1), exp), b
+    m2 = ctx.fft_rounding_margin()
+    print(f"{preset}: adversarial rounding margins: external product 2^{np.log2(m1):.1f}, cmux 2^{np.log2(max(m2, 1e-300)):.1f}")
+    assert 0.0 < m1 < MARGIN and m2 < MARGIN, (m1, m2)
+    bk.free(); ctx.close()
+
+
+@pytest.mark.parametrize("preset,batch", [("P0", 296), ("P1", 444), ("P2", 296)])
+def test_adversarial_key_full_n_blind_rotation(preset, batch):
+    """Full LWE dimension, one full wave of CTAs, a bootstrapping key whose every limb is at +-2^15: the FFT path (margin
+    recorded) must agree bit for bit with the all-integer NTT path, and one ciphertext with the oracle."""
+    p = T.TfheParams.preset(preset)
+    rng = np.random.default_rng(41)
+    bsk = adversarial_words(rng, p.bsk_words, "key")
+    ksk = rng.integers(0, 1 << 32, p.ksk_words, dtype=np.uint64).astype(np.uint32)
+    cts = rng.integers(0, 1 << 32, (batch, p.n + 1), dtype=np.uint64).astype(np.uint32)
+    tv = rng.integers(0, 1 << p.log_p, p.N).astype(np.uint32)
+    accs = {}
+    for path in (T.PATH_FFT, T.PATH_NTT):
+        ctx = T.Context(p, 0, path=path)
+        ctx.set_fft_check(True)
+        bk = ctx.upload_key(bsk, ksk)
+        accs[path] = ctx.blind_rotate(bk, cts, tv)
+        if path == T.PATH_FFT:
+            m = ctx.fft_rounding_margin()
+            print(f"{preset}: adversarial key, full n, batch {batch}: rounding margin 2^{np.log2(m):.1f}")
+            assert 0.0 < m < MARGIN, m
+            ctx.set_fft_check(False)                                # the production kernel: same bits
+            assert np.array_equal(ctx.blind_rotate(bk, cts[:7], tv), accs[path][:7])
+        bk.free(); ctx.close()
+    assert np.array_equal(accs[T.PATH_FFT], accs[T.PATH_NTT])
+    if preset != "P2":                                              # P2 at full n costs the oracle ~10 s; P0/P1 1-2 s
+        assert np.array_equal(accs[T.PATH_FFT][3], orc.blind_rotate(oparams(p), cts[3], bsk, tv))
+
+
+@pytest.mark.parametrize("preset,batch", [("P0", 1024), ("P2", 1024)])
+def test_fft_equals_ntt_whole_batch(preset, batch):
+    """The two arithmetic paths agree bit for bit on a whole batch of real ciphertexts (P1: test_gpu_fullsize.py)."""
+    p = T.TfheParams.preset(preset)
+    lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 0xB200)
+    pm = 1 << p.log_p
+    nu = 64
+    uniq = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(nu)])
+    cts = np.tile(uniq, (batch // nu, 1))
+    cts[nu:, 0] += (np.arange(batch - nu, dtype=np.uint32) + 1) * np.uint32(0x9E3779B1)   # distinct inputs beyond the first 64
+    tv = T.construct_identity_test_vector(p)
+    outs = {}
+    for path in (T.PATH_FFT, T.PATH_NTT):
+        ctx = T.Context(p, 0, path=path)
+        ctx.set_fft_check(True)
+        bk = ctx.upload_key(bsk, ksk)
+        outs[path] = ctx.bootstrap(bk, cts, tv)
+        if path == T.PATH_FFT:
+            m = ctx.fft_rounding_margin()
+            assert 0.0 < m < MARGIN, m
+        bk.free(); ctx.close()
+    assert np.array_equal(outs[T.PATH_FFT], outs[T.PATH_NTT])
+    for i in range(nu):
+        assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, outs[T.PATH_FFT][i])) == i % pm
+
+
+@pytest.mark.parametrize("preset,n", [("P0", 6), ("P1", 6)])
+def test_bmmp_bit_exact_vs_oracle_incl_adversarial_key(preset, n):
+    """BMMP instantiations (P0 = the reference's own parameter set, and P1): real key triples and an adversarial key, bit
+    for bit against orc_blind_rotate_bmmp (the reference holds prose only for this variant: parity with the Rust crate is
+    unpinned; this pins the kernel against the note's restatement), margin recorded."""
+    p = T.TfheParams.preset(preset, lwe_dimension=n)
+    o = oparams(p)
+    lwe_sk, glwe_sk, bsk3, ksk = T.bootstrapping_key_gen_bmmp(p, 0xB200)
+    rng = np.random.default_rng(51)
+    pm = 1 << p.log_p
+    B = 2 * 4 + 3                                                  # two full CTAs of either shape + a partial one
+    cts = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(B)])
+    cts[5] = rng.integers(0, 1 << 32, n + 1, dtype=np.uint64).astype(np.uint32)
+    cts[6, :n] = 0
+    cts[4, 0] = 0
+    tvs = np.stack([T.construct_identity_test_vector(p), rng.integers(0, pm, p.N).astype(np.uint32)])
+    idx = (np.arange(B) % 2).astype(np.uint32)
+    for key3, real in ((bsk3, True), (adversarial_words(rng, bsk3.shape, "key"), False)):
+        ctx = T.Context(p, 0, path=T.PATH_FFT)
+        ctx.set_fft_check(True)
+        bk = ctx.upload_key_bmmp(key3, ksk)
+        acc = ctx.blind_rotate(bk, cts, tvs, idx)
+        out = ctx.bootstrap(bk, cts, tvs, idx)
+        for b in range(B):
+            assert np.array_equal(acc[b], orc.blind_rotate_bmmp(o, cts[b], key3, tvs[idx[b]])), (real, b)
+            assert np.array_equal(out[b], orc.bootstrap_bmmp(o, cts[b], key3, ksk, tvs[idx[b]])), (real, b)
+        if real:
+            for b in (0, 2):
+                assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, out[b])) == b % pm
+        m = ctx.fft_rounding_margin()
+        print(f"{preset} BMMP ({'real' if real else 'adversarial'} key): rounding margin 2^{np.log2(m):.1f}")
+        assert 0.0 < m < MARGIN, m
+        ctx.set_fft_check(False)
+        assert np.array_equal(ctx.blind_rotate(bk, cts, tvs, idx), acc)
+        bk.free(); ctx.close()
+
+
+def test_bmmp_p0_full_n_decrypts_and_matches_oracle():
+    """The reference's own parameter set (lib.rs:101-123, n = 722) through the unrolled-by-two blind rotation."""
+    p = T.TfheParams.preset("P0")
+    lwe_sk, glwe_sk, bsk3, ksk = T.bootstrapping_key_gen_bmmp(p, 0xB200)
+    ctx = T.Context(p, 0, path=T.PATH_FFT)
+    ctx.set_fft_check(True)
+    bk = ctx.upload_key_bmmp(bsk3, ksk)
+    pm = 1 << p.log_p
+    nu, B = 32, 600
+    uniq = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(nu)])
+    cts = np.tile(uniq, ((B + nu - 1) // nu, 1))[:B]
+    tv = T.construct_identity_test_vector(p)
+    out = ctx.bootstrap(bk, cts, tv)
+    for i in range(0, B, 7):
+        assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, out[i])) == (i % nu) % pm, i
+    assert np.array_equal(out[:nu], out[nu:2 * nu])
+    assert 0.0 < ctx.fft_rounding_margin() < MARGIN
+    assert np.array_equal(out[5], orc.bootstrap_bmmp(oparams(p), cts[5], bsk3, ksk, tv))
+    bk.free(); ctx.close()

@@ -1,17 +1,20 @@
-"""Batch sharding of independent PBS / gate evaluations across the GPUs of one box.
+"""Batch sharding of independent PBS / gate evaluations across the GPUs of one box (one process per GPU).
 
 Every ciphertext's bootstrap is independent (bootstrapping.rs:58-65 reads only its own ciphertext, the
 shared read-only BootstrappingKey and a LUT), so the batch is split into contiguous index ranges, one per
-rank (one process per GPU), with the keys REPLICATED on every GPU.  The only collectives are the input
-scatter and the result gather (and one all-gather per level of a layered circuit); there is no
-collective inside the data path.  Works with any torch.distributed backend: NCCL with CUDA tensors on
-the GPU box, gloo with CPU tensors in the CPU-only test-suite (the compute function is injected).
+rank, with the keys REPLICATED on every GPU.  The only communication is the input scatter and the result
+gather (and one all-gather per level of a layered circuit); there is no collective inside the data path.
+Works with any torch.distributed backend: NCCL with CUDA tensors on the GPU box, gloo with CPU tensors in
+the CPU-only test-suite (the compute function is injected).
+
+Scatter and gather are batched point-to-point transfers of exactly the shard's rows (`batch_isend_irecv`:
+one NCCL group): the root sends row slices of its tensor and receives straight into row slices of the
+result -- no padding, no staging copies, no concatenation.  (The one-process form of the same thing, for a
+host that is not Python, is `tfhe_mgpu_*` in include/tfhe_b200.h.)
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Sequence
-
-import numpy as np
+from typing import Callable, List, Sequence
 
 
 def shard_range(total: int, rank: int, world: int):
@@ -37,47 +40,56 @@ def world_info(group=None):
     return 0, 1
 
 
-def scatter_rows(root_tensor, row_shape: Sequence[int], total: int, device, dtype, src: int = 0, group=None):
-    """Rank `src` holds [total, *row_shape]; every rank receives its shard [n_r, *row_shape].
+def _run(ops):
+    if ops:
+        for req in _dist().batch_isend_irecv(ops):
+            req.wait()
 
-    Shards are padded to the largest shard so that the collective uses equal-size buffers (NCCL scatter
-    requirement); the padding rows are dropped on receipt.
-    """
+
+def scatter_rows(root_tensor, row_shape: Sequence[int], total: int, device, dtype, src: int = 0, group=None):
+    """Rank `src` holds [total, *row_shape]; every rank receives its shard [n_r, *row_shape] (the root: a view)."""
     import torch
     dist = _dist()
     rank, world = world_info(group)
     lo, hi = shard_range(total, rank, world)
     if world == 1:
         return root_tensor[lo:hi]
-    pad = max(shard_sizes(total, world))
-    recv = torch.empty((pad, *row_shape), dtype=dtype, device=device)
-    chunks = None
     if rank == src:
-        chunks = []
+        ops = []
         for r in range(world):
             a, b = shard_range(total, r, world)
-            c = torch.zeros((pad, *row_shape), dtype=dtype, device=device)
-            c[: b - a] = root_tensor[a:b]
-            chunks.append(c)
-    dist.scatter(recv, chunks, src=src, group=group)
-    return recv[: hi - lo]
+            if r != src and b > a:
+                ops.append(dist.P2POp(dist.isend, root_tensor[a:b], r, group))
+        _run(ops)
+        return root_tensor[lo:hi]
+    recv = torch.empty((hi - lo, *row_shape), dtype=dtype, device=device)
+    if hi > lo:
+        _run([dist.P2POp(dist.irecv, recv, src, group)])
+    return recv
 
 
-def gather_rows(local, total: int, dst: int = 0, group=None):
-    """Inverse of scatter_rows: rank `dst` returns [total, ...], the others None."""
+def gather_rows(local, total: int, dst: int = 0, group=None, out=None):
+    """Inverse of scatter_rows: rank `dst` returns [total, ...] (`out` if given), the others None."""
     import torch
     dist = _dist()
     rank, world = world_info(group)
     if world == 1:
         return local
-    pad = max(shard_sizes(total, world))
-    send = torch.zeros((pad, *local.shape[1:]), dtype=local.dtype, device=local.device)
-    send[: local.shape[0]] = local
-    bufs = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
-    dist.gather(send, bufs, dst=dst, group=group)
     if rank != dst:
+        if local.shape[0]:
+            _run([dist.P2POp(dist.isend, local.contiguous(), dst, group)])
         return None
-    return torch.cat([bufs[r][: n] for r, n in enumerate(shard_sizes(total, world))], dim=0)
+    if out is None:
+        out = torch.empty((total, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    ops = []
+    for r in range(world):
+        a, b = shard_range(total, r, world)
+        if r == dst:
+            out[a:b] = local
+        elif b > a:
+            ops.append(dist.P2POp(dist.irecv, out[a:b], r, group))
+    _run(ops)
+    return out
 
 
 def all_gather_rows(local, total: int, group=None):
@@ -87,16 +99,24 @@ def all_gather_rows(local, total: int, group=None):
     rank, world = world_info(group)
     if world == 1:
         return local
-    pad = max(shard_sizes(total, world))
+    out = torch.empty((total, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    if total % world == 0:
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)   # equal shards: one collective, straight into `out`
+        return out
+    sizes = shard_sizes(total, world)
+    pad = max(sizes)
     send = torch.zeros((pad, *local.shape[1:]), dtype=local.dtype, device=local.device)
     send[: local.shape[0]] = local
-    bufs = [torch.empty_like(send) for _ in range(world)]
-    dist.all_gather(bufs, send, group=group)
-    return torch.cat([bufs[r][: n] for r, n in enumerate(shard_sizes(total, world))], dim=0)
+    buf = torch.empty((world * pad, *local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, send, group=group)
+    for r, n in enumerate(sizes):
+        a, _ = shard_range(total, r, world)
+        out[a:a + n] = buf[r * pad:r * pad + n]
+    return out
 
 
-def bootstrap_sharded(compute: Callable, lwe_in_root, total: int, row_len: int, device, dtype, src: int = 0, group=None):
+def bootstrap_sharded(compute: Callable, lwe_in_root, total: int, row_len: int, device, dtype, src: int = 0, group=None, out=None):
     """scatter -> compute(local_shard) -> gather.  `compute` maps [b, row_len] -> [b, row_len]."""
     local = scatter_rows(lwe_in_root, (row_len,), total, device, dtype, src, group)
-    out = compute(local) if local.shape[0] else local
-    return gather_rows(out, total, src, group)
+    res = compute(local) if local.shape[0] else local
+    return gather_rows(res, total, src, group, out)

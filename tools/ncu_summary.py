@@ -20,6 +20,10 @@ keep = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__inst_executed.sum', 'lts__t_bytes.sum', 'lts__t_sectors_srcunit_tex_op_read.sum', 'sm__cycles_elapsed.max', 'smsp__cycles_active.avg',
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed']
 keep += [h for h in hdr if h.startswith('smsp__average_warps_issue_stalled')]
+# the pipe the FFT kernel computes on (FP64), the pipes around it, and the L2 side of the key stream
+keep += [h for h in hdr if h.startswith(('sm__pipe_fp64', 'sm__inst_executed_pipe_fp64', 'smsp__inst_executed_pipe_fp64', 'sm__inst_executed_pipe_fma', 'sm__inst_executed_pipe_alu',
+                                         'sm__inst_executed_pipe_uniform', 'sm__inst_executed_pipe_tensor', 'lts__t_bytes', 'lts__t_sectors_op_read.sum', 'l1tex__data_pipe_lsu_wavefronts.sum',
+                                         'smsp__inst_executed_op_shared', 'sm__sass_inst_executed_op_shared'))]
 print("kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?", file=out)
 for h, u, v in zip(hdr, units, vals):
     if h in keep:
