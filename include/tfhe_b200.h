@@ -123,6 +123,12 @@ int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path);
  * records the largest distance to the nearest integer of every value it rounds (about 5 % slower);
  * tfhe_fft_rounding_margin returns that maximum since the last call and resets it (0 when nothing was recorded). */
 int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on);
+/* FFT path, blind rotations of at most one ciphertext per SM (small batches, single-PBS latency).  on (default; env
+ * TFHE_B200_LATENCY_CFG=0|1): such a batch runs a kernel configuration with ONE ciphertext per CTA whose otherwise idle
+ * shared memory holds a deep key ring (5-7 GGSW rows in flight instead of 2) -- a lone ciphertext is bound by the round trip
+ * of each ring refill, not by arithmetic.  off: always the throughput configuration (2-4 ciphertexts per CTA, two-slot ring).
+ * Same bits either way. */
+int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on);
 int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out);
 
 /* Copies BSK+KSK (host or device pointers) to the ctx's device and transforms the BSK into the domain of the ctx's

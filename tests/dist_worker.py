@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--backend", default="nccl")
     ap.add_argument("--preset", default="P1")
-    ap.add_argument("--n", type=int, default=12)
+    ap.add_argument("--lwe-dim", dest="n", type=int, default=12)
     ap.add_argument("--batch", type=int, default=1001)
     a = ap.parse_args()
     import torch

@@ -181,3 +181,33 @@ def test_bmmp_p0_full_n_decrypts_and_matches_oracle():
     assert 0.0 < ctx.fft_rounding_margin() < MARGIN
     assert np.array_equal(out[5], orc.bootstrap_bmmp(oparams(p), cts[5], bsk3, ksk, tv))
     bk.free(); ctx.close()
+
+
+@pytest.mark.parametrize("preset", ["P0", "P1", "P2"])
+def test_latency_configuration_same_bits_as_throughput_configuration(preset):
+    """Small batches (at most one ciphertext per SM) run the one-ciphertext-per-CTA, deep-ring configuration of the blind
+    rotation; it must give the bits of the throughput configuration (several ciphertexts per CTA, two-slot ring) and of the
+    oracle, at full n, for batch sizes around the switch-over."""
+    p = T.TfheParams.preset(preset)
+    lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 0xB200)
+    pm = 1 << p.log_p
+    ctx = T.Context(p, 0, path=T.PATH_FFT)
+    bk = ctx.upload_key(bsk, ksk)
+    tv = T.construct_identity_test_vector(p)
+    cts = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(150)])
+    cts[7, :p.n] = 0                                               # every step skipped
+    cts[8, :p.n // 2] = 0
+    ref = None
+    for B in (150, 148, 37, 1):                                    # 150: throughput configuration either way
+        ctx.set_latency_config(True)
+        lat = ctx.bootstrap(bk, cts[:B], tv)
+        ctx.set_latency_config(False)
+        thr = ctx.bootstrap(bk, cts[:B], tv)
+        assert np.array_equal(lat, thr), B
+        ref = thr if ref is None else ref
+        assert np.array_equal(lat, ref[:B]), B                     # batch invariance across configurations
+    for i in (0, 5):
+        assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, ref[i])) == i % pm
+    if preset != "P2":
+        assert np.array_equal(ref[1], orc.bootstrap(oparams(p), cts[1], bsk, ksk, tv))
+    bk.free(); ctx.close()

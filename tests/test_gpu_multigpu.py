@@ -38,14 +38,14 @@ def _torchrun(nproc, *args):
 
 
 def test_two_ranks_on_one_gpu_gloo_equal_single_gpu():
-    out = _torchrun(2, "--backend", "gloo", "--preset", "P1", "--n", "12", "--batch", "1001")
+    out = _torchrun(2, "--backend", "gloo", "--preset", "P1", "--lwe-dim", "12", "--batch", "1001")
     assert "layered circuit over 2 ranks == single GPU: True; decrypts to the plain evaluation: True" in out
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_nccl_ranks_equal_single_gpu():
     n = min(torch.cuda.device_count(), 8)
-    out = _torchrun(n, "--backend", "nccl", "--preset", "P0", "--n", "10", "--batch", "2051")
+    out = _torchrun(n, "--backend", "nccl", "--preset", "P0", "--lwe-dim", "10", "--batch", "2051")
     assert f"layered circuit over {n} ranks == single GPU: True; decrypts to the plain evaluation: True" in out
 
 

@@ -111,7 +111,7 @@ def lib():
         "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP], "tfhe_keygen_bmmp": [PP, C.c_uint64, VP, VP, VP, VP],
         "tfhe_bk_upload_bmmp": [VP, VP, VP, C.POINTER(VP)],
         "tfhe_ctx_create": [PP, C.c_int, C.POINTER(VP)], "tfhe_ctx_set_stream": [VP, VP],
-        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_ks_path": [VP, C.c_int], "tfhe_ctx_set_fft_check": [VP, C.c_int],
+        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_ks_path": [VP, C.c_int], "tfhe_ctx_set_fft_check": [VP, C.c_int], "tfhe_ctx_set_latency_config": [VP, C.c_int],
         "tfhe_fft_rounding_margin": [VP, C.POINTER(C.c_double)],
         "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)], "tfhe_bk_read_transformed": [VP, VP, SZ],
         "tfhe_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP],
@@ -161,7 +161,7 @@ EXPORTS = [
     "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_ctx_set_ks_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
     "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed", "tfhe_bootstrap_batch_ks_first", "tfhe_gate_k_batch",
     "tfhe_file_write", "tfhe_file_read", "tfhe_keygen_bmmp", "tfhe_bk_upload_bmmp", "tfhe_bk_get_path", "tfhe_ctx_get_stream",
-    "tfhe_mgpu_create", "tfhe_mgpu_destroy", "tfhe_mgpu_n_gpus", "tfhe_mgpu_ctx", "tfhe_mgpu_last_error", "tfhe_mgpu_bk_upload",
+    "tfhe_ctx_set_latency_config", "tfhe_mgpu_create", "tfhe_mgpu_destroy", "tfhe_mgpu_n_gpus", "tfhe_mgpu_ctx", "tfhe_mgpu_last_error", "tfhe_mgpu_bk_upload",
     "tfhe_mgpu_bk_upload_bmmp", "tfhe_mgpu_bk_free", "tfhe_mgpu_bootstrap_batch", "tfhe_mgpu_gates_batch", "tfhe_mgpu_last_timing",
 ]
 
@@ -403,6 +403,10 @@ class Context:
         """FFT path: run the kernel variant that records the rounding margin (see fft_rounding_margin)."""
         self._ck(lib().tfhe_ctx_set_fft_check(self._h, 1 if on else 0))
 
+    def set_latency_config(self, on: bool = True):
+        """FFT path: small batches (<= one ciphertext per SM) use the one-ciphertext-per-CTA, deep-ring kernel configuration."""
+        self._ck(lib().tfhe_ctx_set_latency_config(self._h, 1 if on else 0))
+
     def fft_rounding_margin(self) -> float:
         """Largest distance to an integer of any value rounded by the FFT path since the last call (must be << 0.5)."""
         out = C.c_double()
@@ -422,8 +426,8 @@ class Context:
 
     def _on_device(self, *xs):
         for x in xs:
-            if x is not None and _is_torch(x) and (not x.is_cuda or x.device.index != self.device):
-                raise ValueError(f"tensor on {x.device}: this context drives cuda:{self.device} (pass numpy arrays for host data)")
+            if x is not None and _is_torch(x) and x.is_cuda and x.device.index != self.device:   # CPU (e.g. pinned) tensors are host pointers
+                raise ValueError(f"tensor on {x.device}: this context drives cuda:{self.device}")
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(lib().tfhe_ctx_set_stream(self._h, cuda_stream_ptr))

@@ -195,7 +195,9 @@ struct TwTablesF {
 // SINGLE_BUF: one exchange buffer per sub-team instead of two (N = 2048: 17 KB each), at the price of a barrier between
 // every load and the next store.  HALVES: a key slot holds both limbs of one GGSW row for 1/HALVES of the points, so the
 // two-slot TMA ring stays at 2 x 32 KB when a row is 64 KB.
-template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true, bool SINGLE_BUF_ = false, int HALVES_ = 1>
+// NSLOT: depth of the key ring.  Two slots feed a CTA whose 2-4 ciphertexts keep the SM busy; a CTA that holds ONE ciphertext
+// (small batches: latency) is bound by the round trip of each ring refill instead, and uses the idle shared memory for a deep ring.
+template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true, bool SINGLE_BUF_ = false, int HALVES_ = 1, int NSLOT_ = TFHE_FFT_NSLOT>
 struct FftPbsCfg {
     using F = FftCfg<LOGN_ - 1, LOGE_>;
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2;
@@ -214,7 +216,7 @@ struct FftPbsCfg {
     // key stream: one SLOT = one GGSW row (or 1/HALVES of its points), both limbs: [2 limbs][P columns][MH] complex in slot
     // order; rows are stored in consumption order (level-major: row index lev*P + p for polynomial p, level lev)
     static constexpr int POLY_BYTES = MH * 16, LIMB_BYTES = P * POLY_BYTES, SLOT_BYTES = 2 * LIMB_BYTES, SLOTS_PER_STEP = ROWS * HALVES;
-    static constexpr int NSLOT = TFHE_FFT_NSLOT;
+    static constexpr int NSLOT = NSLOT_;
     static constexpr size_t GGSW_BYTES = (size_t)SLOTS_PER_STEP * SLOT_BYTES;
     // shared memory per team: acc, then per sub-team {stash, buf0, buf1}, then the mod-switched mask
     static constexpr int TM_ACC = 0;                                   // u32 acc[P][N]
@@ -226,7 +228,7 @@ struct FftPbsCfg {
     static constexpr int team_bytes(int n) { return (TM_AT + (n + 1) * 2 + 127) & ~127; }
     // single-ciphertext modes borrow idle shared memory for the polynomial to decompose and a zero subtrahend: the
     // accumulators of teams 1 and 2, or (two teams) the accumulator and the first exchange buffer of team 1
-    static_assert(CTS >= 3 || (CTS == 2 && F::MPAD * 16 >= P * N * 4), "single-ciphertext modes need two spare accumulator-sized regions");
+    static constexpr bool HAS_SINGLE_MODES = CTS >= 3 || (CTS == 2 && F::MPAD * 16 >= P * N * 4);   // CTS == 1 (latency configuration): blind rotation only
     static constexpr int SPARE_DIN = 1 * 0 + TM_ACC;                         // offset inside team 1
     static constexpr int SPARE_ZERO_TEAM = CTS >= 3 ? 2 : 1;
     static constexpr int SPARE_ZERO = CTS >= 3 ? TM_ACC : TM_SUB + STASH_BYTES;   // offset inside team SPARE_ZERO_TEAM

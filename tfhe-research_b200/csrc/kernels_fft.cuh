@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #endif
     constexpr bool SELF_REFILL = (TFHE_FFT_SELFREFILL != 0) && (OWN_FIRST || (K::HALVES > 1 && !BMMP));
 
-    const bool single = a.mode != 0;   // sub-operation entry points: one ciphertext (team 0) per CTA, its own GGSW
+    const bool single = K::HAS_SINGLE_MODES && a.mode != 0;   // sub-operation entry points: one ciphertext (team 0) per CTA, its own GGSW
     // blind rotation: the batch is split over the grid as evenly as possible (CTA b gets base or base+1 ciphertexts,
     // base+1 <= CTS), so a partially filled last wave shortens every CTA instead of leaving SMs idle
     const uint32_t base = a.batch / gridDim.x, rem = a.batch % gridDim.x;

@@ -44,6 +44,7 @@ struct tfhe_ctx {
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
     bool ks_mma = true;                     // key switch on the integer tensor cores where the key has a byte-plane copy
+    bool latency_cfg = true;                // FFT path: batches of at most one ciphertext per SM run the one-ciphertext-per-CTA, deep-ring configuration
     fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
@@ -191,8 +192,13 @@ using KF0C = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, true>;
 using KF2 = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, false, true, 2>;
 using KF2C = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2>;
 static_assert(fft::key_slot_layout_ok<KF0>() && fft::key_slot_layout_ok<KF1>() && fft::key_slot_layout_ok<KF2>(), "diagonal-major key layout");
+// latency configurations: ONE ciphertext per CTA, the rest of the shared memory is a deep key ring (batches of at most one
+// ciphertext per SM; the production two-slot ring would leave such a CTA waiting for the round trip of every refill)
+using KF0L = fft::FftPbsCfg<9, 3, 2, 6, 4, 1, false, false, 1, 7>;
+using KF1L = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, 1, false, TFHE_FFT_P1_SINGLE != 0, 1, 5>;
+using KF2L = fft::FftPbsCfg<11, 4, 1, 3, 8, 1, false, true, 2, 5>;
 template <class K>
-constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 16; }
+constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 4 * K::NSLOT + 16; }
 // the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
 // resident ciphertext, which bounds the LWE dimension (P1 shape: n <= 1151, P0 shape: n <= 2111; above that the NTT path serves)
 bool fft_available(int pbs_id, size_t n = 0) {
@@ -262,6 +268,16 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
         return fail(ctx, TFHE_E_PARAM, "no BMMP instantiation for this parameter set");
     }
     if (bk->path == TFHE_PATH_FFT) {
+#ifndef TFHE_FFT_LATENCY_CFG
+#define TFHE_FFT_LATENCY_CFG 1
+#endif
+        if (TFHE_FFT_LATENCY_CFG && ctx->latency_cfg && a.mode == 0 && !ctx->fft_check && a.batch <= (uint32_t)ctx->sm_count) {
+            switch (ctx->pbs_id) {
+            case 0: if (fft_smem_bytes<KF0L>(a.n) <= 227 * 1024) return launch_pbs_fft_t<KF0L>(ctx, a, bk->d_bsk_fft); break;
+            case 1: if (fft_smem_bytes<KF1L>(a.n) <= 227 * 1024) return launch_pbs_fft_t<KF1L>(ctx, a, bk->d_bsk_fft); break;
+            case 2: if (fft_smem_bytes<KF2L>(a.n) <= 227 * 1024) return launch_pbs_fft_t<KF2L>(ctx, a, bk->d_bsk_fft); break;
+            }
+        }
         switch (ctx->pbs_id) {
         case 0: return ctx->fft_check ? launch_pbs_fft_t<KF0C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0>(ctx, a, bk->d_bsk_fft);
         case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
@@ -499,6 +515,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_mma = strcmp(e, "imad") != 0;
+    if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) ctx->latency_cfg = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
         if (!strcmp(e, "fft") && fft_available(ctx->pbs_id, ctx->n())) ctx->path = TFHE_PATH_FFT;
         if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
@@ -553,6 +570,11 @@ int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path) {
     if (!ctx) return TFHE_E_PARAM;
     if (path != TFHE_KS_IMAD && path != TFHE_KS_MMA) return fail(ctx, TFHE_E_PARAM, "unknown key-switch path");
     ctx->ks_mma = path == TFHE_KS_MMA;
+    return TFHE_OK;
+}
+int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on) {
+    if (!ctx) return TFHE_E_PARAM;
+    ctx->latency_cfg = on != 0;
     return TFHE_OK;
 }
 int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on) {
