@@ -12,11 +12,13 @@
 //   * digits d are small signed integers, |d| <= B = 2^LOGB (decomposer.rs:42-80 incl. the +B quirk);
 //   * every key word g is lifted to its centred representative s in [-2^31, 2^31) and split into two centred limbs
 //     s = lo + 2^16 hi, lo in [-2^15, 2^15), hi in [-2^15, 2^15];  out = sum d(*)lo + 2^16 sum d(*)hi  (mod 2^32);
-//   * each limb convolution is an integer of magnitude <= ROWS*N*B*2^15 <= 2^36.6 (P2); the floating-point result
-//     differs from it by at most  c * 2^-53 * sum_r ||d_r||_2 ||limb_r||_2  with c ~ 2^7.2 (Percival-type bound for
-//     a length-2^10 transform incl. the pointwise products and twiddle errors) <= 2^-9, so rounding to nearest
-//     recovers the exact integer;  static_assert below keeps a 2^9 safety factor, and the kernel can record the
-//     largest distance to an integer it ever saw (CHECK), which the full-size GPU tests assert to be < 2^-6.
+//   * each limb convolution is an integer of magnitude <= S = ROWS*N*B*2^15 <= 2^36.6 (P2); the floating-point result
+//     differs from it by at most  c * 2^-53 * sum_r ||d_r||_2 ||limb_r||_2,  c = 3 (log2(M) (1 + sqrt 5) + sum over stages of
+//     the twiddle error in ulps) <= 332 = 2^8.4 INCLUDING the twiddles derived by repeated squaring (derive_pass_tw: an
+//     entry v squarings below the loaded one is off by <= 2^v + 3.2 (2^v - 1) + 3 ulps), i.e. <= 2^-8.0 (P2), 2^-9.3 (P1),
+//     2^-12.8 (P0), so rounding to nearest recovers the exact integer;  the static_assert below is S c 2^-53 < 1/4 for any
+//     c <= 2^9, and the kernel can record the largest distance to an integer it ever saw (CHECK), which the GPU tests
+//     assert to be < 2^-6 on random AND adversarial inputs (tests/test_gpu_exactness.py).
 //
 // Transform: the fold z_j = a_j + i a_{j+M} maps R[X]/(X^N+1) to C[X]/(X^M - i); the forward transform evaluates at
 // the M roots of X^M = i (zeta^(4k+1), zeta = exp(2 pi i / 4M)) with a Cooley-Tukey flow (natural in, bit-reversed
@@ -456,6 +458,8 @@ TFHE_HD void phase_mac_bmmp(FftRegs<K> &r, uint32_t t, uint32_t col, const cplx 
                             const cplx base) {
     using C = typename K::F;
     static_assert(K::HALVES == 1, "the BMMP variant is instantiated for whole-row key slots only");
+    // exactness: three keys per row, each times a monomial factor of modulus <= 2 -> the limb convolution is up to 6x larger
+    static_assert(6.0 * (double)K::ROWS * K::N * (double)(1 << K::LOGB) * 32768.0 * 512.0 < 2251799813685248.0, "FP64 exactness bound (BMMP)");
     const cplx *g0 = slot + col * K::M + t, *g1 = g0 + K::P * K::M;
     static_for<0, K::E>([&](auto ei) {
         constexpr int e = decltype(ei)::value;

@@ -27,11 +27,16 @@ __global__ void __launch_bounds__(384, 1) k(uint32_t *sink, int iters, long long
     for (int it = 0; it < iters; it++) {
 #pragma unroll
         for (int i = 0; i < 8; i++) {
+            // asm volatile: the loads must stay in the loop (the addresses repeat, nothing is stored in between)
             if (WIDTH == 16) {
-                uint4 r = base[i * 64 + ((it & 1) << 5)];
+                uint4 r;
+                const uint32_t ad = (uint32_t)__cvta_generic_to_shared(base + i * 64 + ((it & 1) << 5));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(ad));
                 a.x += r.x; a.y ^= r.y; a.z += r.z; a.w ^= r.w;
             } else {
-                uint2 r = reinterpret_cast<const uint2 *>(base)[i * 128 + ((it & 1) << 6)];
+                uint2 r;
+                const uint32_t ad = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<const uint2 *>(base) + i * 128 + ((it & 1) << 6));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(ad));
                 a.x += r.x; a.y ^= r.y;
             }
         }
