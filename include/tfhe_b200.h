@@ -123,12 +123,15 @@ int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path);
  * records the largest distance to the nearest integer of every value it rounds (about 5 % slower);
  * tfhe_fft_rounding_margin returns that maximum since the last call and resets it (0 when nothing was recorded). */
 int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on);
-/* FFT path, blind rotations of at most one ciphertext per SM (small batches, single-PBS latency).  on (default; env
- * TFHE_B200_LATENCY_CFG=0|1): such a batch runs a kernel configuration with ONE ciphertext per CTA whose otherwise idle
- * shared memory holds a deep key ring (5-7 GGSW rows in flight instead of 2) -- a lone ciphertext is bound by the round trip
- * of each ring refill, not by arithmetic.  off: always the throughput configuration (2-4 ciphertexts per CTA, two-slot ring).
- * Same bits either way. */
-int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on);
+/* FFT path, blind rotations of at most one ciphertext per SM (small batches, single-PBS latency); env
+ * TFHE_B200_LATENCY_CFG=0|1|2.  A lone ciphertext on an SM is a chain of n dependent CMUX steps, each L levels + one inverse:
+ *   2 (default)  one ciphertext per CTA, ALL teams of the CTA on it: the L levels of a step (forward transforms and
+ *                multiply-accumulates) are spread over the teams, partial sums are combined by the owner team
+ *                (kernels_fft_latency.cuh; instantiated for the P0 and P1 shapes, otherwise mode 1);
+ *   1            one ciphertext per CTA, one team, the idle shared memory holds a deep key ring (5-7 rows in flight);
+ *   0            always the throughput configuration (2-4 ciphertexts per CTA, two-slot ring).
+ * Same bits in every mode. */
+int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int mode);
 int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out);
 
 /* Copies BSK+KSK (host or device pointers) to the ctx's device and transforms the BSK into the domain of the ctx's

@@ -185,9 +185,10 @@ def test_bmmp_p0_full_n_decrypts_and_matches_oracle():
 
 @pytest.mark.parametrize("preset", ["P0", "P1", "P2"])
 def test_latency_configuration_same_bits_as_throughput_configuration(preset):
-    """Small batches (at most one ciphertext per SM) run the one-ciphertext-per-CTA, deep-ring configuration of the blind
-    rotation; it must give the bits of the throughput configuration (several ciphertexts per CTA, two-slot ring) and of the
-    oracle, at full n, for batch sizes around the switch-over."""
+    """Small batches (at most one ciphertext per SM) run one ciphertext per CTA -- with all teams of the CTA sharing its
+    levels (kernels_fft_latency.cuh) or with one team and a deep key ring; both must give the bits of the throughput
+    configuration (several ciphertexts per CTA, two-slot ring) and of the oracle, at full n, for batch sizes around the
+    switch-over, incl. ciphertexts whose steps are skipped."""
     p = T.TfheParams.preset(preset)
     lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 0xB200)
     pm = 1 << p.log_p
@@ -199,13 +200,15 @@ def test_latency_configuration_same_bits_as_throughput_configuration(preset):
     cts[8, :p.n // 2] = 0
     ref = None
     for B in (150, 148, 37, 1):                                    # 150: throughput configuration either way
-        ctx.set_latency_config(True)
-        lat = ctx.bootstrap(bk, cts[:B], tv)
-        ctx.set_latency_config(False)
+        ctx.set_latency_config(0)
         thr = ctx.bootstrap(bk, cts[:B], tv)
-        assert np.array_equal(lat, thr), B
         ref = thr if ref is None else ref
-        assert np.array_equal(lat, ref[:B]), B                     # batch invariance across configurations
+        for mode in (2, 1):                                        # all teams on the one ciphertext / one team with a deep key ring
+            ctx.set_latency_config(mode)
+            lat = ctx.bootstrap(bk, cts[:B], tv)
+            assert np.array_equal(lat, thr), (B, mode)
+            assert np.array_equal(lat, ref[:B]), (B, mode)         # batch invariance across configurations
+            assert np.array_equal(ctx.blind_rotate(bk, cts[:min(B, 9)], tv), ctx.blind_rotate(bk, cts[:150], tv)[:min(B, 9)]), (B, mode)
     for i in (0, 5):
         assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, ref[i])) == i % pm
     if preset != "P2":

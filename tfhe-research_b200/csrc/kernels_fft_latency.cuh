@@ -16,8 +16,10 @@
 // a-priori bound of an integer, so the output bits are those of the throughput kernel and of the oracle
 // (tests/test_gpu_exactness.py::test_latency_configuration_*).
 //
-// Key stream: one ring of NSLOT whole GGSW rows, filled by TMA in the order the teams consume them (round r, slot d of the
-// level, team): every ring entry is read by ONE team, whose last warp to release it issues the copy that reuses it.
+// Key stream: every team has ONE shared-memory slot for a whole GGSW row, with its own full/empty mbarriers and its own
+// sequence of rows (round r of its levels, slot d of the level); the last warp of the team to release a row issues the TMA
+// copy of the team's next row -- possibly the first row of the next step, which then lands while the owner inverts.  (A slot
+// is never shared between teams: mbarrier parity waits are only unambiguous for consumers at most one phase apart.)
 #pragma once
 #include "kernels_fft.cuh"
 
@@ -36,27 +38,14 @@ struct LatencyLayout {
     static constexpr int AT = BUFS + K::CTS * K::P * SUBBUF_BYTES;       // u16 at[n+1]
     static constexpr size_t ring_offset(size_t n) { return ((size_t)AT + (n + 1) * 2 + 127) & ~(size_t)127; }
     static constexpr size_t smem_bytes(size_t n) { return ring_offset(n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 4 * K::NSLOT + 16; }
-    // position q of a step's key stream -> storage row (level-major: lev * P + d) of the row consumed there
-    __device__ static uint32_t row_of_position(uint32_t q) {
-        constexpr uint32_t FULL = (uint32_t)(FULL_ROUNDS * K::P * K::CTS);
-        uint32_t r, d, team;
-        if (q < FULL) {
-            r = q / (uint32_t)(K::P * K::CTS);
-            const uint32_t rem = q % (uint32_t)(K::P * K::CTS);
-            d = rem / (uint32_t)K::CTS;
-            team = rem % (uint32_t)K::CTS;
-        } else {
-            constexpr uint32_t NT = LAST_TEAMS ? LAST_TEAMS : 1;
-            r = (uint32_t)FULL_ROUNDS;
-            d = (q - FULL) / NT;
-            team = (q - FULL) % NT;
-        }
-        return (r * (uint32_t)K::CTS + team) * (uint32_t)K::P + d;
-    }
-    // position of (round r, slot d of the level, team) inside a step
-    __device__ static uint32_t position(uint32_t r, uint32_t d, uint32_t team) {
-        const uint32_t nt = r < (uint32_t)FULL_ROUNDS ? (uint32_t)K::CTS : (uint32_t)LAST_TEAMS;
-        return r * (uint32_t)(K::P * K::CTS) + d * nt + team;
+    static_assert(K::NSLOT == K::CTS, "one key slot per team");
+    // team h runs levels h, h + CTS, ...: rows it consumes per step, and the storage row (level-major: lev * P + d) of the
+    // seq-th row of its sequence
+    __device__ static uint32_t levels_of(uint32_t team) { return (uint32_t)FULL_ROUNDS + (team < (uint32_t)LAST_TEAMS ? 1u : 0u); }
+    __device__ static size_t row_of(uint32_t team, uint32_t seq) {
+        const uint32_t rps = levels_of(team) * (uint32_t)K::P, step = seq / rps, q = seq % rps;
+        const uint32_t r = q / (uint32_t)K::P, d = q % (uint32_t)K::P;
+        return (size_t)step * K::ROWS + (r * (uint32_t)K::CTS + team) * (uint32_t)K::P + d;
     }
 };
 
@@ -86,12 +75,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
     const uint32_t jbB = jbase_B<C>(t);
     const cplx twB_base = pass_tw_base<C::QB>(a.tw.twB + (t >> C::QB) * C::NB_TW, 1);
     const cplx twC_base = pass_tw_base<C::LOGE>(a.tw.twC + t, C::T);
-    const uint32_t total_pos = a.n * (uint32_t)K::ROWS;
+    // teams that have work: team h runs levels h, h + CTS, ...
+    constexpr uint32_t NTEAMS = K::CTS < K::L ? K::CTS : K::L;
+    const bool works = team < NTEAMS;
+    const uint32_t my_levels = LL::levels_of(team), my_rows = a.n * my_levels * (uint32_t)K::P;   // rows this team consumes in all
 
     if (tid == 0) {
         for (int s = 0; s < K::NSLOT; s++) {
             mbar_init(full + s, 1);
-            mbar_init(empty + s, K::P * K::WARPS_PER_SUB);   // every ring entry is read by the warps of ONE team
+            mbar_init(empty + s, K::P * K::WARPS_PER_SUB);   // slot s is read by the warps of team s only
             claimed[s] = 0;
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -124,22 +116,23 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
     __syncthreads();
 
     const uint8_t *ksrc = reinterpret_cast<const uint8_t *>(a.bsk_fft);
-    auto issue_pos = [&](uint32_t g) {   // global stream position g -> TMA copy of its row into ring entry g % NSLOT
-        const uint32_t s = g % K::NSLOT;
-        const size_t row = (size_t)(g / (uint32_t)K::ROWS) * K::ROWS + LL::row_of_position(g % (uint32_t)K::ROWS);
-        mbar_expect_tx(full + s, K::SLOT_BYTES);
-        bulk_g2s(ring + s * K::SLOT_BYTES, ksrc + row * K::SLOT_BYTES, K::LIMB_BYTES, full + s);
-        bulk_g2s(ring + s * K::SLOT_BYTES + K::LIMB_BYTES, ksrc + row * K::SLOT_BYTES + K::LIMB_BYTES, K::LIMB_BYTES, full + s);
+    auto issue_row = [&](uint32_t tm_, uint32_t seq) {   // TMA copy of the seq-th row of team tm_'s sequence into the team's slot
+        const size_t row = LL::row_of(tm_, seq);
+        mbar_expect_tx(full + tm_, K::SLOT_BYTES);
+        bulk_g2s(ring + tm_ * K::SLOT_BYTES, ksrc + row * K::SLOT_BYTES, K::LIMB_BYTES, full + tm_);
+        bulk_g2s(ring + tm_ * K::SLOT_BYTES + K::LIMB_BYTES, ksrc + row * K::SLOT_BYTES + K::LIMB_BYTES, K::LIMB_BYTES, full + tm_);
     };
-    auto release_pos = [&](uint32_t g) {   // lane 0 of a warp that is done with position g
-        const uint32_t s = g % K::NSLOT, u = g / K::NSLOT, nx = g + (uint32_t)K::NSLOT;
-        mbar_arrive(empty + s);
-        if (nx < total_pos && mbar_test(empty + s, u & 1u)) {
-            if (atomicCAS(claimed + s, u, u + 1u) == u) issue_pos(nx);
+    uint32_t seq = 0;   // rows of my team's sequence consumed so far (the same in every warp of the team)
+    auto wait_row = [&]() { mbar_wait(full + team, seq & 1u, a.err_flag); };
+    auto release_row = [&]() {   // lane 0 of a warp that is done with the team's current row; advances seq in every lane's copy via the caller
+        mbar_arrive(empty + team);
+        if (seq + 1u < my_rows && mbar_test(empty + team, seq & 1u)) {
+            if (atomicCAS(claimed + team, seq, seq + 1u) == seq) issue_row(team, seq + 1u);
         }
     };
+    const cplx *slot = reinterpret_cast<const cplx *>(ring + team * K::SLOT_BYTES);
     if (tid == 0)
-        for (uint32_t g = 0; g < (uint32_t)K::NSLOT && g < total_pos; g++) issue_pos(g);
+        for (uint32_t h = 0; h < NTEAMS; h++) issue_row(h, 0u);
 
     FftRegs<K> R;
     double maxfrac = 0.0;
@@ -150,26 +143,18 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
         accv[2 * e] = acc[sub * K::N + j];
         accv[2 * e + 1] = acc[sub * K::N + j + K::M];
     }
-    // teams that have work: team h runs levels h, h + CTS, ...
-    constexpr uint32_t NTEAMS = K::CTS < K::L ? K::CTS : K::L;
-    const bool works = team < NTEAMS;
-
 #pragma unroll 1
     for (uint32_t i = 0; i < a.n; i++) {
-        const uint32_t rot = at[i], base = i * (uint32_t)K::ROWS;
+        const uint32_t rot = at[i];
         if (rot == 0) {
             // diff == 0 => external product == 0 exactly: every team consumes its ring entries of this step without using them
             if (works) {
 #pragma unroll 1
-                for (uint32_t r = 0; r < (uint32_t)LL::ROUNDS; r++) {
-                    if (r * K::CTS + team >= (uint32_t)K::L) break;
-#pragma unroll 1
-                    for (uint32_t d = 0; d < (uint32_t)K::P; d++) {
-                        const uint32_t g = base + LL::position(r, d, team);
-                        mbar_wait(full + (g % K::NSLOT), (g / K::NSLOT) & 1u, a.err_flag);
-                        __syncwarp();
-                        if (lane == 0) release_pos(g);
-                    }
+                for (uint32_t q = 0; q < my_levels * (uint32_t)K::P; q++) {
+                    wait_row();
+                    __syncwarp();
+                    if (lane == 0) release_row();
+                    seq++;
                 }
             }
             continue;
@@ -191,21 +176,19 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
                 sub_sync();
                 phase_F3v<K>(R, t, twC_base, buf1);
                 phase_xstore<K>(R, t, buf0);
-                {   // own row: slot 0 of the level
-                    const uint32_t g = base + LL::position(r, 0u, team), s = g % K::NSLOT;
-                    mbar_wait(full + s, (g / K::NSLOT) & 1u, a.err_flag);
-                    phase_mac<K, true>(R, t, sub, reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES), buf0, 0u);
-                    __syncwarp();
-                    if (lane == 0) release_pos(g);
-                }
+                wait_row();   // own row: slot 0 of the level
+                phase_mac<K, true>(R, t, sub, slot, buf0, 0u);
+                __syncwarp();
+                if (lane == 0) release_row();
+                seq++;
                 team_bar_id(team_bar, K::TEAM_THREADS);   // all P transformed rows of this level are published
 #pragma unroll 1
                 for (uint32_t d = 1; d < (uint32_t)K::P; d++) {
-                    const uint32_t g = base + LL::position(r, d, team), s = g % K::NSLOT;
-                    mbar_wait(full + s, (g / K::NSLOT) & 1u, a.err_flag);
-                    phase_mac<K, false>(R, t, sub, reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES), subbuf(team, (sub + d) % (uint32_t)K::P), 0u);
+                    wait_row();
+                    phase_mac<K, false>(R, t, sub, slot, subbuf(team, (sub + d) % (uint32_t)K::P), 0u);
                     __syncwarp();
-                    if (lane == 0) release_pos(g);
+                    if (lane == 0) release_row();
+                    seq++;
                 }
             }
             team_bar_id(team_bar, K::TEAM_THREADS);       // the last published rows have been read: the buffers are free

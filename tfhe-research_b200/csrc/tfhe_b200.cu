@@ -14,6 +14,7 @@
 #include "host_tables_fft.hpp"
 #include "kernels.cuh"
 #include "kernels_fft.cuh"
+#include "kernels_fft_latency.cuh"
 
 using namespace tfhe;
 
@@ -44,7 +45,7 @@ struct tfhe_ctx {
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
     bool ks_mma = true;                     // key switch on the integer tensor cores where the key has a byte-plane copy
-    bool latency_cfg = true;                // FFT path: batches of at most one ciphertext per SM run the one-ciphertext-per-CTA, deep-ring configuration
+    int latency_cfg = 2;                    // FFT path, batches of at most one ciphertext per SM: 0 throughput kernel, 1 one team + deep key ring, 2 all teams of the CTA on the one ciphertext
     fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
@@ -197,6 +198,9 @@ static_assert(fft::key_slot_layout_ok<KF0>() && fft::key_slot_layout_ok<KF1>() &
 using KF0L = fft::FftPbsCfg<9, 3, 2, 6, 4, 1, false, false, 1, 7>;
 using KF1L = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, 1, false, TFHE_FFT_P1_SINGLE != 0, 1, 5>;
 using KF2L = fft::FftPbsCfg<11, 4, 1, 3, 8, 1, false, true, 2, 5>;
+// all-teams-on-one-ciphertext configurations (kernels_fft_latency.cuh): the ring holds one GGSW row per team
+using KF0H = fft::FftPbsCfg<9, 3, 2, 6, 4, 4, false, false, 1, 4>;
+using KF1H = fft::FftPbsCfg<10, 3, 1, 3, 8, 3, false, false, 1, 3>;
 template <class K>
 constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 4 * K::NSLOT + 16; }
 // the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
@@ -230,6 +234,22 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
         if (grid > a.batch) grid = (unsigned)a.batch;
     }
     kern<<<grid, K::THREADS, smem, ctx->stream>>>(f);
+    CU(cudaGetLastError());
+    ctx->launches++;
+    return TFHE_OK;
+}
+template <class K>
+int launch_pbs_fft_latency_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
+    fft::FftArgs f = {};
+    f.tw = ctx->ftw;
+    f.bsk_fft = key;
+    f.lwe_in = a.lwe_in; f.luts = a.luts; f.lut_idx = a.lut_idx;
+    f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
+    f.n = a.n; f.batch = a.batch; f.mode = 0; f.log_p = a.log_p; f.enc_shift = a.enc_shift; f.n_luts = a.n_luts;
+    const size_t smem = fft::LatencyLayout<K>::smem_bytes(a.n);
+    auto kern = fft::pbs_fft_latency_kernel<K>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)a.batch, K::THREADS, smem, ctx->stream>>>(f);
     CU(cudaGetLastError());
     ctx->launches++;
     return TFHE_OK;
@@ -272,6 +292,10 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
 #define TFHE_FFT_LATENCY_CFG 1
 #endif
         if (TFHE_FFT_LATENCY_CFG && ctx->latency_cfg && a.mode == 0 && !ctx->fft_check && a.batch <= (uint32_t)ctx->sm_count) {
+            if (ctx->latency_cfg == 2) {
+                if (ctx->pbs_id == 0 && fft::LatencyLayout<KF0H>::smem_bytes(a.n) <= 227 * 1024) return launch_pbs_fft_latency_t<KF0H>(ctx, a, bk->d_bsk_fft);
+                if (ctx->pbs_id == 1 && fft::LatencyLayout<KF1H>::smem_bytes(a.n) <= 227 * 1024) return launch_pbs_fft_latency_t<KF1H>(ctx, a, bk->d_bsk_fft);
+            }
             switch (ctx->pbs_id) {
             case 0: if (fft_smem_bytes<KF0L>(a.n) <= 227 * 1024) return launch_pbs_fft_t<KF0L>(ctx, a, bk->d_bsk_fft); break;
             case 1: if (fft_smem_bytes<KF1L>(a.n) <= 227 * 1024) return launch_pbs_fft_t<KF1L>(ctx, a, bk->d_bsk_fft); break;
@@ -515,7 +539,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_mma = strcmp(e, "imad") != 0;
-    if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) ctx->latency_cfg = atoi(e) != 0;
+    if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) { const int v = atoi(e); if (v >= 0 && v <= 2) ctx->latency_cfg = v; }
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
         if (!strcmp(e, "fft") && fft_available(ctx->pbs_id, ctx->n())) ctx->path = TFHE_PATH_FFT;
         if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
@@ -574,7 +598,8 @@ int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path) {
 }
 int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on) {
     if (!ctx) return TFHE_E_PARAM;
-    ctx->latency_cfg = on != 0;
+    if (on < 0 || on > 2) return fail(ctx, TFHE_E_PARAM, "latency configuration: 0, 1 or 2");
+    ctx->latency_cfg = on;
     return TFHE_OK;
 }
 int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on) {
