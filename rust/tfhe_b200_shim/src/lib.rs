@@ -175,3 +175,57 @@ impl B200 {
 impl Drop for B200 {
     fn drop(&mut self) { unsafe { if !self.bk.is_null() { tfhe_bk_free(self.bk); } tfhe_ctx_destroy(self.ctx); } }
 }
+
+// ------------------------------------------------------------------ all GPUs of the box behind one handle (tfhe_mgpu_*)
+#[repr(C)] pub struct RawMgpu { _p: [u8; 0] }
+#[repr(C)] pub struct RawMgpuBk { _p: [u8; 0] }
+
+extern "C" {
+    fn tfhe_mgpu_create(p: *const TfheParams, n_gpus: c_int, devices: *const c_int, out: *mut *mut RawMgpu) -> c_int;
+    fn tfhe_mgpu_destroy(m: *mut RawMgpu);
+    fn tfhe_mgpu_last_error(m: *const RawMgpu) -> *const c_char;
+    fn tfhe_mgpu_bk_upload(m: *mut RawMgpu, bsk: *const u32, ksk: *const u32, out: *mut *mut RawMgpuBk) -> c_int;
+    fn tfhe_mgpu_bk_free(bk: *mut RawMgpuBk);
+    fn tfhe_mgpu_bootstrap_batch(m: *mut RawMgpu, bk: *const RawMgpuBk, lwe_in: *const u32, luts: *const u32, n_luts: usize,
+                                 lut_idx: *const u32, batch: usize, lwe_out: *mut u32) -> c_int;
+    fn tfhe_mgpu_gates_batch(m: *mut RawMgpu, bk: *const RawMgpuBk, gates: *const u8, ct0: *const u32, ct1: *const u32,
+                             batch: usize, out: *mut u32) -> c_int;
+}
+
+/// `B200` over every GPU of the box: batches are split into contiguous balanced ranges, keys replicated.
+pub struct B200Multi { m: *mut RawMgpu, bk: *mut RawMgpuBk, n: usize }
+
+impl B200Multi {
+    pub fn new(params: TfheParams, n_gpus: i32, bsk: &[u32], ksk: &[u32]) -> Result<Self, Error> {
+        let mut m = std::ptr::null_mut();
+        let rc = unsafe { tfhe_mgpu_create(&params, n_gpus, std::ptr::null(), &mut m) };
+        if rc != 0 { return Err(Error { code: rc, message: "tfhe_mgpu_create (no CUDA device? there is no CPU fallback)".into() }); }
+        let mut bk = std::ptr::null_mut();
+        let rc = unsafe { tfhe_mgpu_bk_upload(m, bsk.as_ptr(), ksk.as_ptr(), &mut bk) };
+        if rc != 0 {
+            let message = unsafe { CStr::from_ptr(tfhe_mgpu_last_error(m)) }.to_string_lossy().into_owned();
+            unsafe { tfhe_mgpu_destroy(m) };
+            return Err(Error { code: rc, message });
+        }
+        Ok(B200Multi { m, bk, n: params.lwe_dimension as usize })
+    }
+    fn check(&self, rc: c_int) -> Result<(), Error> {
+        if rc == 0 { Ok(()) } else { Err(Error { code: rc, message: unsafe { CStr::from_ptr(tfhe_mgpu_last_error(self.m)) }.to_string_lossy().into_owned() }) }
+    }
+    /// `bootstrap` (bootstrapping.rs:58) over a batch of flat LWE ciphertexts, sharded over all GPUs.
+    pub fn bootstrap(&self, lwe_cts: &[u32], test_vector_poly: &[u32]) -> Result<Vec<u32>, Error> {
+        let batch = lwe_cts.len() / (self.n + 1);
+        let mut out = vec![0u32; lwe_cts.len()];
+        let rc = unsafe { tfhe_mgpu_bootstrap_batch(self.m, self.bk, lwe_cts.as_ptr(), test_vector_poly.as_ptr(), 1, std::ptr::null(), batch, out.as_mut_ptr()) };
+        self.check(rc).map(|_| out)
+    }
+    /// one gate opcode per ciphertext pair (`and`/`or` boolean.rs:9-53 + XOR/NAND/NOR/XNOR), sharded over all GPUs.
+    pub fn gates(&self, gates: &[u8], ct0: &[u32], ct1: &[u32]) -> Result<Vec<u32>, Error> {
+        let mut out = vec![0u32; ct0.len()];
+        let rc = unsafe { tfhe_mgpu_gates_batch(self.m, self.bk, gates.as_ptr(), ct0.as_ptr(), ct1.as_ptr(), gates.len(), out.as_mut_ptr()) };
+        self.check(rc).map(|_| out)
+    }
+}
+impl Drop for B200Multi {
+    fn drop(&mut self) { unsafe { tfhe_mgpu_bk_free(self.bk); tfhe_mgpu_destroy(self.m); } }
+}
