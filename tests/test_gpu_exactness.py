@@ -185,9 +185,9 @@ def test_bmmp_p0_full_n_decrypts_and_matches_oracle():
 
 @pytest.mark.parametrize("preset", ["P0", "P1", "P2"])
 def test_latency_configuration_same_bits_as_throughput_configuration(preset):
-    """Small batches (at most one ciphertext per SM) run one ciphertext per CTA -- with all teams of the CTA sharing its
-    levels (kernels_fft_latency.cuh) or with one team and a deep key ring; both must give the bits of the throughput
-    configuration (several ciphertexts per CTA, two-slot ring) and of the oracle, at full n, for batch sizes around the
+    """Small batches run one ciphertext per cluster of L CTAs (one gadget level each, kernels_fft_cluster.cuh), per CTA with
+    all its teams sharing the levels (kernels_fft_latency.cuh), or per CTA with one team and a deep key ring; all must give the
+    bits of the throughput configuration (several ciphertexts per CTA, two-slot ring) and of the oracle, at full n, for batch sizes around the
     switch-over, incl. ciphertexts whose steps are skipped."""
     p = T.TfheParams.preset(preset)
     lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 0xB200)
@@ -199,11 +199,11 @@ def test_latency_configuration_same_bits_as_throughput_configuration(preset):
     cts[7, :p.n] = 0                                               # every step skipped
     cts[8, :p.n // 2] = 0
     ref = None
-    for B in (150, 148, 37, 1):                                    # 150: throughput configuration either way
+    for B in (150, 148, 37, 20, 1):                                # 150: throughput configuration either way
         ctx.set_latency_config(0)
         thr = ctx.bootstrap(bk, cts[:B], tv)
         ref = thr if ref is None else ref
-        for mode in (2, 1):                                        # all teams on the one ciphertext / one team with a deep key ring
+        for mode in (3, 2, 1):    # a cluster of L CTAs per ciphertext (B <= SMs / L) / all teams of a CTA on one ciphertext / one team, deep key ring
             ctx.set_latency_config(mode)
             lat = ctx.bootstrap(bk, cts[:B], tv)
             assert np.array_equal(lat, thr), (B, mode)

@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-ldl"]
 _SOURCES = ["tfhe_b200.cu", "host_api.cpp", "tfhe_mgpu.cpp"]
 _DEPS = _SOURCES + ["kernels.cuh", "pbs_team.cuh", "tfhe_core.cuh", "host_tables.hpp", "api_internal.hpp",
-                    "kernels_fft.cuh", "kernels_fft_latency.cuh", "fft_team.cuh", "host_tables_fft.hpp", "tfhe_mgpu.cpp",
+                    "kernels_fft.cuh", "kernels_fft_latency.cuh", "kernels_fft_cluster.cuh", "fft_team.cuh", "host_tables_fft.hpp", "tfhe_mgpu.cpp",
                     os.path.join("..", "..", "include", "tfhe_b200.h")]
 
 TFHE_OK, TFHE_E_PARAM, TFHE_E_CUDA, TFHE_E_OOM, TFHE_E_ASSERT, TFHE_E_NCCL = 0, -1, -2, -3, -4, -5
@@ -403,10 +403,11 @@ class Context:
         """FFT path: run the kernel variant that records the rounding margin (see fft_rounding_margin)."""
         self._ck(lib().tfhe_ctx_set_fft_check(self._h, 1 if on else 0))
 
-    def set_latency_config(self, mode=2):
-        """FFT path, batches of at most one ciphertext per SM: 2 (default) all teams of a CTA work on its one ciphertext,
-        1 one team with a deep key ring, 0 / False the throughput configuration.  Same bits."""
-        self._ck(lib().tfhe_ctx_set_latency_config(self._h, 2 if mode is True else int(mode)))
+    def set_latency_config(self, mode=3):
+        """FFT path, small batches: 3 (default) a cluster of L CTAs per ciphertext, one gadget level each (batch <= SMs / L),
+        2 all teams of a CTA on its one ciphertext (batch <= SMs), 1 one team with a deep key ring, 0 / False the throughput
+        configuration.  Same bits."""
+        self._ck(lib().tfhe_ctx_set_latency_config(self._h, 3 if mode is True else int(mode)))
 
     def fft_rounding_margin(self) -> float:
         """Largest distance to an integer of any value rounded by the FFT path since the last call (must be << 0.5)."""

@@ -29,6 +29,7 @@ struct FftArgs {
     uint32_t *glwe_out;        // [B][P][N]
     uint32_t *err_flag;        // bit 0: test-vector entry >= 2^log_p (glwe.rs:144); bit 1: TMA wait timed out; bit 2: lut_idx out of range
     unsigned long long *margin;  // largest |x - rint(x)| before rounding (bits of a non-negative double), CHECK only
+    unsigned long long *prof;    // optional phase-cycle counters of the latency kernel (measurement only; nullptr in production)
     uint32_t n, batch, mode, log_p, enc_shift;
     uint32_t n_luts;           // lut_idx[b] >= n_luts sets err_flag bit 2 and selects test vector 0
 };

@@ -134,6 +134,19 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
     if (tid == 0)
         for (uint32_t h = 0; h < NTEAMS; h++) issue_row(h, 0u);
 
+    // measurement only (a.prof != nullptr): cycles of thread 0 of CTA 0 per phase: [0] decompose, [1] wait B1, [2] levels, [3] wait B2,
+    // [4] add partial sums, [5] inverse + update, [6] whole loop; of thread 0 of team 1: [8] wait B1, [9] levels, [10] wait B2
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && tt == 0 && team < 2;
+    unsigned long long pc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // [8] forward transform, [9] wait own row, [10] mac own, [11] team barrier, [12] wait peer row, [13] mac peer
+    long long tprev = prof ? clock64() : 0;
+    auto tick = [&](int k) {
+        if (prof) {
+            const long long now = clock64();
+            pc[k] += (unsigned long long)(now - tprev);
+            tprev = now;
+        }
+    };
+    const long long tstart = tprev;
     FftRegs<K> R;
     double maxfrac = 0.0;
     uint32_t accv[2 * K::E];   // owner: the 2E words of acc[sub] this thread decomposes and updates
@@ -146,6 +159,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
 #pragma unroll 1
     for (uint32_t i = 0; i < a.n; i++) {
         const uint32_t rot = at[i];
+        // the GGSW two steps ahead -> L2 (a lone ciphertext streams the key from HBM exactly once: without this every ring
+        // refill pays the DRAM round trip on the critical path); one bulk prefetch per row, issued by one thread per team
+        if (tt == 0 && works && i + 2u < a.n) {
+#pragma unroll 1
+            for (uint32_t q = team; q < (uint32_t)K::ROWS; q += NTEAMS) {
+                const uint8_t *src = ksrc + ((size_t)(i + 2u) * K::ROWS + q) * K::SLOT_BYTES;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)K::SLOT_BYTES) : "memory");
+            }
+        }
         if (rot == 0) {
             // diff == 0 => external product == 0 exactly: every team consumes its ring entries of this step without using them
             if (works) {
@@ -162,7 +184,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
         zero_acc<K>(R);
         if (team == 0)   // decompose polynomial `sub` of rot(acc) - acc: level 0 stays in R.x (pass A done), the other levels go to the stash
             phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j, int k) { return rot_coeff(acc + pp * K::N, j, rot, K::LOGN) - accv[k]; });
+        tick(0);
         __syncthreads();   // B1: the digits of this step are in the stash
+        tick(1);
         if (works) {
 #pragma unroll 1
             for (uint32_t r = 0; r < (uint32_t)LL::ROUNDS; r++) {
@@ -176,19 +200,25 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
                 sub_sync();
                 phase_F3v<K>(R, t, twC_base, buf1);
                 phase_xstore<K>(R, t, buf0);
+                tick(8);
                 wait_row();   // own row: slot 0 of the level
+                tick(9);
                 phase_mac<K, true>(R, t, sub, slot, buf0, 0u);
                 __syncwarp();
                 if (lane == 0) release_row();
                 seq++;
+                tick(10);
                 team_bar_id(team_bar, K::TEAM_THREADS);   // all P transformed rows of this level are published
+                tick(11);
 #pragma unroll 1
                 for (uint32_t d = 1; d < (uint32_t)K::P; d++) {
                     wait_row();
+                    tick(12);
                     phase_mac<K, false>(R, t, sub, slot, subbuf(team, (sub + d) % (uint32_t)K::P), 0u);
                     __syncwarp();
                     if (lane == 0) release_row();
                     seq++;
+                    tick(13);
                 }
             }
             team_bar_id(team_bar, K::TEAM_THREADS);       // the last published rows have been read: the buffers are free
@@ -197,19 +227,22 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
                 store_C<C>(R.acc[1], buf1, t);
             }
         }
+        tick(2);
         __syncthreads();   // B2: partial sums are in the helpers' buffers
+        tick(3);
         if (team == 0) {
-#pragma unroll 1
-            for (uint32_t h = 1; h < NTEAMS; h++) {
+#pragma unroll
+            for (uint32_t h = 1; h < NTEAMS; h++) {   // both limbs of a helper are requested before the first is added
                 const cplx *p0 = subbuf(h, sub), *p1 = p0 + C::MPAD;
-                cplx v[K::E];
-                load_C<C>(v, p0, t);
+                cplx v0[K::E], v1[K::E];
+                load_C<C>(v0, p0, t);
+                load_C<C>(v1, p1, t);
 #pragma unroll
-                for (int e = 0; e < K::E; e++) { R.acc[0][e].re = add_d(R.acc[0][e].re, v[e].re); R.acc[0][e].im = add_d(R.acc[0][e].im, v[e].im); }
-                load_C<C>(v, p1, t);
+                for (int e = 0; e < K::E; e++) { R.acc[0][e].re = add_d(R.acc[0][e].re, v0[e].re); R.acc[0][e].im = add_d(R.acc[0][e].im, v0[e].im); }
 #pragma unroll
-                for (int e = 0; e < K::E; e++) { R.acc[1][e].re = add_d(R.acc[1][e].re, v[e].re); R.acc[1][e].im = add_d(R.acc[1][e].im, v[e].im); }
+                for (int e = 0; e < K::E; e++) { R.acc[1][e].re = add_d(R.acc[1][e].re, v1[e].re); R.acc[1][e].im = add_d(R.acc[1][e].im, v1[e].im); }
             }
+            tick(4);
             phase_J1v<K>(R, t, twC_base, buf0, buf1);
             sub_sync();
             phase_J2av<K>(R, jbB, twB_base, buf0, buf1);
@@ -218,7 +251,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_latency_kernel(const __
             sub_sync();
             phase_J3r<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, accv, maxfrac);
             team_bar_id(team_bar, K::TEAM_THREADS);       // acc is up to date for every sub-team's rotated reads of the next step
+            tick(5);
         }
+    }
+    if (prof) {
+        pc[6] = (unsigned long long)(clock64() - tstart);
+        for (int k = 0; k < 16; k++) a.prof[team * 16 + k] = pc[k];
     }
     if (team == 0) {
         uint32_t *out = a.glwe_out + ((size_t)ct * K::P + sub) * K::N;

@@ -15,6 +15,7 @@
 #include "kernels.cuh"
 #include "kernels_fft.cuh"
 #include "kernels_fft_latency.cuh"
+#include "kernels_fft_cluster.cuh"
 
 using namespace tfhe;
 
@@ -45,7 +46,7 @@ struct tfhe_ctx {
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
     bool ks_mma = true;                     // key switch on the integer tensor cores where the key has a byte-plane copy
-    int latency_cfg = 2;                    // FFT path, batches of at most one ciphertext per SM: 0 throughput kernel, 1 one team + deep key ring, 2 all teams of the CTA on the one ciphertext
+    int latency_cfg = 3;                    // FFT path, small batches: 0 throughput kernel, 1 one team + deep key ring, 2 all teams of a CTA on one ciphertext, 3 a cluster of L CTAs per ciphertext (then 2, then 0 as the batch grows)
     fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
@@ -201,6 +202,9 @@ using KF2L = fft::FftPbsCfg<11, 4, 1, 3, 8, 1, false, true, 2, 5>;
 // all-teams-on-one-ciphertext configurations (kernels_fft_latency.cuh): the ring holds one GGSW row per team
 using KF0H = fft::FftPbsCfg<9, 3, 2, 6, 4, 4, false, false, 1, 4>;
 using KF1H = fft::FftPbsCfg<10, 3, 1, 3, 8, 3, false, false, 1, 3>;
+// one-level-per-CTA cluster configurations (kernels_fft_cluster.cuh): cluster of L CTAs per ciphertext
+using KF0X = fft::FftPbsCfg<9, 3, 2, 6, 4, 1, false, false, 1, 4>;
+using KF1X = fft::FftPbsCfg<10, 3, 1, 3, 8, 1, false, false, 1, 4>;
 template <class K>
 constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 4 * K::NSLOT + 16; }
 // the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
@@ -238,6 +242,63 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     ctx->launches++;
     return TFHE_OK;
 }
+// returns TFHE_OK, or -100 when the cluster shape cannot be launched on this device (the caller falls back)
+template <class K>
+int launch_pbs_fft_cluster_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
+    fft::FftArgs f = {};
+    f.tw = ctx->ftw;
+    f.bsk_fft = key;
+    f.lwe_in = a.lwe_in; f.luts = a.luts; f.lut_idx = a.lut_idx;
+    f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
+    f.n = a.n; f.batch = a.batch; f.mode = 0; f.log_p = a.log_p; f.enc_shift = a.enc_shift; f.n_luts = a.n_luts;
+    const size_t smem = fft::ClusterLayout<K>::smem_bytes(a.n);
+    auto kern = fft::pbs_fft_cluster_kernel<K>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        false) {
+        cudaGetLastError();
+        return -100;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.batch * K::L), 1, 1);
+    cfg.blockDim = dim3(K::TEAM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = K::L;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int max_clusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+        cudaGetLastError();
+        return -100;
+    }
+    unsigned long long *d_prof = nullptr;
+    if (getenv("TFHE_B200_LAT_PROF")) {   // measurement only: phase cycles of the first CTA (kernels_fft_cluster.cuh)
+        CU(cudaMalloc(&d_prof, 16 * 8));
+        CU(cudaMemsetAsync(d_prof, 0, 16 * 8, ctx->stream));
+        f.prof = d_prof;
+    }
+    if (cudaLaunchKernelEx(&cfg, kern, f) != cudaSuccess) {
+        cudaGetLastError();
+        if (d_prof) cudaFree(d_prof);
+        return -100;
+    }
+    ctx->launches++;
+    if (d_prof) {
+        unsigned long long h[16];
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
+        cudaFree(d_prof);
+        fprintf(stderr, "cluster kernel (L = %d CTAs per ciphertext), first CTA, cycles per step (n = %u): digits + pass A %.0f, forward rest %.0f, wait own row %.0f, mac own %.0f, "
+                        "team barrier %.0f, wait + mac peer rows %.0f, inverse + rounding %.0f, cluster barrier %.0f, accumulate via DSMEM %.0f, total %.0f\n", K::L, a.n,
+                (double)h[0] / a.n, (double)h[1] / a.n, (double)h[2] / a.n, (double)h[3] / a.n, (double)h[4] / a.n, (double)h[5] / a.n, (double)h[6] / a.n, (double)h[7] / a.n,
+                (double)h[8] / a.n, (double)h[9] / a.n);
+    }
+    return TFHE_OK;
+}
 template <class K>
 int launch_pbs_fft_latency_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     fft::FftArgs f = {};
@@ -249,9 +310,29 @@ int launch_pbs_fft_latency_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *k
     const size_t smem = fft::LatencyLayout<K>::smem_bytes(a.n);
     auto kern = fft::pbs_fft_latency_kernel<K>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned long long *d_prof = nullptr;
+    if (getenv("TFHE_B200_LAT_PROF")) {   // measurement only: phase cycles of CTA 0 (kernels_fft_latency.cuh)
+        CU(cudaMalloc(&d_prof, 32 * 8));
+        CU(cudaMemsetAsync(d_prof, 0, 32 * 8, ctx->stream));
+        f.prof = d_prof;
+    }
     kern<<<(unsigned)a.batch, K::THREADS, smem, ctx->stream>>>(f);
     CU(cudaGetLastError());
     ctx->launches++;
+    if (d_prof) {
+        unsigned long long h[32];
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
+        cudaFree(d_prof);
+        fprintf(stderr, "latency kernel, CTA 0, cycles per step (n = %u): owner: decompose %.0f, wait B1 %.0f, levels %.0f, wait B2 %.0f, add partials %.0f, inverse+update %.0f, total %.0f | "
+                        "team 1: wait B1 %.0f (incl. idle since B2), levels %.0f, wait B2 %.0f\n", a.n,
+                (double)h[0] / a.n, (double)h[1] / a.n, (double)h[2] / a.n, (double)h[3] / a.n, (double)h[4] / a.n, (double)h[5] / a.n, (double)h[6] / a.n,
+                ((double)h[16] + h[17]) / a.n, (double)h[18] / a.n, (double)h[19] / a.n);
+        for (int tm_ = 0; tm_ < 2; tm_++)
+            fprintf(stderr, "   team %d levels split: forward %.0f, wait own row %.0f, mac own %.0f, team barrier %.0f, wait peer rows %.0f, mac peer rows %.0f\n", tm_,
+                    (double)h[tm_ * 16 + 8] / a.n, (double)h[tm_ * 16 + 9] / a.n, (double)h[tm_ * 16 + 10] / a.n, (double)h[tm_ * 16 + 11] / a.n, (double)h[tm_ * 16 + 12] / a.n,
+                    (double)h[tm_ * 16 + 13] / a.n);
+    }
     return TFHE_OK;
 }
 template <class K>
@@ -292,7 +373,15 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
 #define TFHE_FFT_LATENCY_CFG 1
 #endif
         if (TFHE_FFT_LATENCY_CFG && ctx->latency_cfg && a.mode == 0 && !ctx->fft_check && a.batch <= (uint32_t)ctx->sm_count) {
-            if (ctx->latency_cfg == 2) {
+            if (ctx->latency_cfg == 3) {   // one CTA per gadget level, a cluster per ciphertext
+                int rc = -100;
+                if (ctx->pbs_id == 0 && a.batch * KF0X::L <= (uint32_t)ctx->sm_count && fft::ClusterLayout<KF0X>::smem_bytes(a.n) <= 227 * 1024)
+                    rc = launch_pbs_fft_cluster_t<KF0X>(ctx, a, bk->d_bsk_fft);
+                if (ctx->pbs_id == 1 && a.batch * KF1X::L <= (uint32_t)ctx->sm_count && fft::ClusterLayout<KF1X>::smem_bytes(a.n) <= 227 * 1024)
+                    rc = launch_pbs_fft_cluster_t<KF1X>(ctx, a, bk->d_bsk_fft);
+                if (rc != -100) return rc;
+            }
+            if (ctx->latency_cfg >= 2) {
                 if (ctx->pbs_id == 0 && fft::LatencyLayout<KF0H>::smem_bytes(a.n) <= 227 * 1024) return launch_pbs_fft_latency_t<KF0H>(ctx, a, bk->d_bsk_fft);
                 if (ctx->pbs_id == 1 && fft::LatencyLayout<KF1H>::smem_bytes(a.n) <= 227 * 1024) return launch_pbs_fft_latency_t<KF1H>(ctx, a, bk->d_bsk_fft);
             }
@@ -539,7 +628,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_mma = strcmp(e, "imad") != 0;
-    if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) { const int v = atoi(e); if (v >= 0 && v <= 2) ctx->latency_cfg = v; }
+    if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) { const int v = atoi(e); if (v >= 0 && v <= 3) ctx->latency_cfg = v; }
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
         if (!strcmp(e, "fft") && fft_available(ctx->pbs_id, ctx->n())) ctx->path = TFHE_PATH_FFT;
         if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
@@ -598,7 +687,7 @@ int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path) {
 }
 int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on) {
     if (!ctx) return TFHE_E_PARAM;
-    if (on < 0 || on > 2) return fail(ctx, TFHE_E_PARAM, "latency configuration: 0, 1 or 2");
+    if (on < 0 || on > 3) return fail(ctx, TFHE_E_PARAM, "latency configuration: 0 .. 3");
     ctx->latency_cfg = on;
     return TFHE_OK;
 }
