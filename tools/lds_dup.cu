@@ -11,7 +11,8 @@
 //   4: lane + (lane >> 3)        the kernel's padded layout: four runs of 8 elements, 16 B gaps
 //   5: lane * 9                  layout C of the kernel: stride 9 elements (conflict-free per quarter-warp)
 //   6: (lane & 15) + ((lane & 15) >> 3)   padded AND duplicated across half-warps
-// OP 0 = LDS.128, 1 = STS.128, 2 = alternating STS.128 / LDS.128 (no dependence between them).
+// OP 0 = LDS.128, 1 = STS.128, 2 = alternating STS.128 / LDS.128 (no dependence between them), 3 = STS.64, 4 = LDS.64
+// (8-byte elements at 8-byte stride: lane -> element lane, 256 B per instruction).
 // Prints cycles per warp-level instruction per SM, timed over ALL warps of the CTA.
 #include <cstdint>
 #include <cstdio>
@@ -32,7 +33,16 @@ __global__ void __launch_bounds__(384, 1) k(uint32_t *sink, int iters, long long
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const uint32_t ad = base + (uint32_t)(i * 64 + ((it & 1) << 5)) * 16u;   // 8 rows of 64 elements, two column halves
-            if (OP == 0 || (OP == 2 && (i & 1))) {
+            if (OP == 3 || OP == 4) {
+                const uint32_t ad8 = (uint32_t)__cvta_generic_to_shared(sm + warp * 1024) + (uint32_t)(lane + i * 128 + ((it & 1) << 6)) * 8u;
+                if (OP == 4) {
+                    uint2 r;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(ad8));
+                    a.x += r.x; a.y ^= r.y;
+                } else {
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ad8), "r"(a.x), "r"(a.y) : "memory");
+                }
+            } else if (OP == 0 || (OP == 2 && (i & 1))) {
                 uint4 r;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(ad));
                 a.x += r.x; a.y ^= r.y; a.z += r.z; a.w ^= r.w;
@@ -60,10 +70,10 @@ int main() {
         RUN(0, 0, "lds128_contiguous") RUN(1, 0, "lds128_dup_halfwarps") RUN(2, 0, "lds128_dup_4x") RUN(3, 0, "lds128_broadcast")
         RUN(4, 0, "lds128_padded") RUN(5, 0, "lds128_stride9") RUN(6, 0, "lds128_padded_dup_halfwarps")
         RUN(0, 1, "sts128_contiguous") RUN(4, 1, "sts128_padded") RUN(5, 1, "sts128_stride9")
-        RUN(0, 2, "mix_contiguous") RUN(4, 2, "mix_padded")
+        RUN(0, 2, "mix_contiguous") RUN(4, 2, "mix_padded") RUN(0, 3, "sts64_contiguous") RUN(0, 4, "lds64_contiguous")
         if (cudaDeviceSynchronize() != cudaSuccess) { printf("{\"error\": \"%s\"}\n", cudaGetErrorString(cudaGetLastError())); return 1; }
     }
-    printf("{\"unit\": \"cycles per warp-level 128-bit instruction per SM (12 warps)\"");
+    printf("{\"unit\": \"cycles per warp-level instruction per SM (12 warps)\"");
     for (int i = 0; i < slot; i++) printf(", \"%s\": %.2f", names[i], (double)cyc[i] / iters / 96.0);
     printf("}\n");
     return 0;
