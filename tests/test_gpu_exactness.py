@@ -203,7 +203,7 @@ def test_latency_configuration_same_bits_as_throughput_configuration(preset):
         ctx.set_latency_config(0)
         thr = ctx.bootstrap(bk, cts[:B], tv)
         ref = thr if ref is None else ref
-        for mode in (3, 2, 1):    # a cluster of L CTAs per ciphertext (B <= SMs / L) / all teams of a CTA on one ciphertext / one team, deep key ring
+        for mode in (4, 3, 2, 1):    # (4: the cluster with every CTA split by key limb) a cluster of L CTAs per ciphertext (B <= SMs / L) / all teams of a CTA on one ciphertext / one team, deep key ring
             ctx.set_latency_config(mode)
             lat = ctx.bootstrap(bk, cts[:B], tv)
             assert np.array_equal(lat, thr), (B, mode)

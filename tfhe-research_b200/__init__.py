@@ -403,11 +403,12 @@ class Context:
         """FFT path: run the kernel variant that records the rounding margin (see fft_rounding_margin)."""
         self._ck(lib().tfhe_ctx_set_fft_check(self._h, 1 if on else 0))
 
-    def set_latency_config(self, mode=3):
-        """FFT path, small batches: 3 (default) a cluster of L CTAs per ciphertext, one gadget level each (batch <= SMs / L),
+    def set_latency_config(self, mode=4):
+        """FFT path, small batches: 4 (default) / 3 a cluster of L CTAs per ciphertext, one gadget level each (batch <= SMs / L;
+        4 also splits every CTA by key limb over twice the warps),
         2 all teams of a CTA on its one ciphertext (batch <= SMs), 1 one team with a deep key ring, 0 / False the throughput
         configuration.  Same bits."""
-        self._ck(lib().tfhe_ctx_set_latency_config(self._h, 3 if mode is True else int(mode)))
+        self._ck(lib().tfhe_ctx_set_latency_config(self._h, 4 if mode is True else int(mode)))
 
     def fft_rounding_margin(self) -> float:
         """Largest distance to an integer of any value rounded by the FFT path since the last call (must be << 0.5)."""

@@ -284,5 +284,286 @@ __global__ void __launch_bounds__(K::TEAM_THREADS, 1) pbs_fft_cluster_kernel(con
     (void)maxfrac;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same cluster scheme with every CTA's work split by KEY LIMB over twice the warps: 2P sub-teams (column c, limb).  The P
+// limb-0 sub-teams decompose and transform the digit rows and publish them; all 2P sub-teams then multiply-accumulate and
+// inverse-transform ONE limb each (single-limb inverse through two buffers: two sub-team barriers) -- half the dependent FP64 work
+// per warp and two warps per scheduler instead of one, which is what a lone ciphertext lacks (a single team runs at a third of
+// its FP64 issue rate, profiles/r02_latency_phases.txt).  The two rounded limbs of a column are combined locally
+// (lo + (hi << 16)) before the push, so the cluster exchange is unchanged.
+template <class K>
+struct ClusterSplitLayout {
+    using C = typename K::F;
+    static_assert(K::CTS == 1 && K::HALVES == 1 && !K::SINGLE_BUF && K::L <= 8, "cluster kernel configuration");
+    static constexpr int SUBS = 2 * K::P, THREADS = SUBS * K::T;
+    static constexpr int ACC = 0;                                        // u32 acc[P][N]          (replica)
+    static constexpr int PART = ACC + K::P * K::N * 4;                   // u32 part[2][L][P][N]
+    static constexpr int BUFS = PART + 2 * K::L * K::P * K::N * 4;       // cplx [2P][2][MPAD]
+    static constexpr int SUBBUF_BYTES = 2 * C::MPAD * 16;
+    static constexpr int AT = BUFS + SUBS * SUBBUF_BYTES;                // u16 at[n+1]
+    static constexpr size_t ring_offset(size_t n) { return ((size_t)AT + (n + 1) * 2 + 127) & ~(size_t)127; }
+    static constexpr size_t smem_bytes(size_t n) { return ring_offset(n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 4 * K::NSLOT + 16; }
+};
+
+template <class K>
+__global__ void __launch_bounds__(ClusterSplitLayout<K>::THREADS, 1) pbs_fft_cluster_split_kernel(const __grid_constant__ FftArgs a) {
+    using C = typename K::F;
+    using LL = ClusterSplitLayout<K>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, sub2 = tid / K::T, t = tid % K::T;
+    const uint32_t col = sub2 % (uint32_t)K::P, limb = sub2 / (uint32_t)K::P;   // sub-teams 0..P-1: limb 0 (+ digits and forward transforms)
+    const uint32_t lev = cluster_ctarank();
+    const uint32_t ct = blockIdx.x / (uint32_t)K::L;
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem + LL::ACC);
+    uint32_t *part = reinterpret_cast<uint32_t *>(smem + LL::PART);
+    auto subbuf = [&](uint32_t sb_) { return reinterpret_cast<cplx *>(smem + LL::BUFS + sb_ * LL::SUBBUF_BYTES); };
+    cplx *buf0 = subbuf(sub2), *buf1 = buf0 + C::MPAD;
+    uint16_t *at = reinterpret_cast<uint16_t *>(smem + LL::AT);
+    uint8_t *ring = smem + LL::ring_offset(a.n);
+    uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
+    uint32_t *claimed = reinterpret_cast<uint32_t *>(empty + K::NSLOT);
+    constexpr bool WARP_SUB = K::T == 32;
+    const uint32_t sub_bar = 1 + sub2;
+    static_assert(WARP_SUB || LL::SUBS <= 15, "named barrier ids");
+    auto sub_sync = [&]() {
+        if constexpr (WARP_SUB) __syncwarp();
+        else team_bar_id(sub_bar, K::T);
+    };
+    const uint32_t jbB = jbase_B<C>(t);
+    const cplx twB_base = pass_tw_base<C::QB>(a.tw.twB + (t >> C::QB) * C::NB_TW, 1);
+    const cplx twC_base = pass_tw_base<C::LOGE>(a.tw.twC + t, C::T);
+    const uint32_t total_rows = a.n * (uint32_t)K::P;
+
+    if (tid == 0) {
+        for (int s = 0; s < K::NSLOT; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, LL::SUBS * K::WARPS_PER_SUB);   // every warp of the CTA consumes every ring entry
+            claimed[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const uint32_t *lwe = a.lwe_in + (size_t)ct * (a.n + 1);
+    for (uint32_t i = tid; i <= a.n; i += LL::THREADS) at[i] = (uint16_t)mod_switch(__ldg(lwe + i), K::LOGN);
+    __syncthreads();
+    {
+        const uint32_t b = at[a.n];
+        uint32_t li = a.lut_idx ? __ldg(a.lut_idx + ct) : 0u;
+        if (li >= a.n_luts) {
+            atomicOr(a.err_flag, 4u);
+            li = 0u;
+        }
+        const uint32_t *lut = a.luts + (size_t)li * K::N;
+        for (uint32_t idx = tid; idx < (uint32_t)(K::P * K::N); idx += LL::THREADS) {
+            const uint32_t p = idx >> K::LOGN, j = idx & (K::N - 1u);
+            uint32_t v = 0;
+            if (p == (uint32_t)K::K) {
+                const uint32_t src = (j + b) & (2u * K::N - 1u);
+                const uint32_t m = __ldg(lut + (src & (K::N - 1u)));
+                if (m >> a.log_p) atomicOr(a.err_flag, 1u);
+                v = m << a.enc_shift;
+                if (src & K::N) v = 0u - v;
+            }
+            acc[idx] = v;
+        }
+    }
+    __syncthreads();
+
+    const uint8_t *ksrc = reinterpret_cast<const uint8_t *>(a.bsk_fft);
+    auto issue_row = [&](uint32_t q) {
+        const uint32_t s = q % K::NSLOT;
+        const size_t row = (size_t)(q / (uint32_t)K::P) * K::ROWS + (size_t)lev * K::P + q % (uint32_t)K::P;
+        mbar_expect_tx(full + s, K::SLOT_BYTES);
+        bulk_g2s(ring + s * K::SLOT_BYTES, ksrc + row * K::SLOT_BYTES, K::LIMB_BYTES, full + s);
+        bulk_g2s(ring + s * K::SLOT_BYTES + K::LIMB_BYTES, ksrc + row * K::SLOT_BYTES + K::LIMB_BYTES, K::LIMB_BYTES, full + s);
+    };
+    auto release_row = [&](uint32_t q) {
+        const uint32_t s = q % K::NSLOT, u = q / K::NSLOT, nx = q + (uint32_t)K::NSLOT;
+        mbar_arrive(empty + s);
+        if (nx < total_rows && mbar_test(empty + s, u & 1u)) {
+            if (atomicCAS(claimed + s, u, u + 1u) == u) issue_row(nx);
+        }
+    };
+    if (tid == 0)
+        for (uint32_t q = 0; q < (uint32_t)K::NSLOT && q < total_rows; q++) issue_row(q);
+
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    unsigned long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = prof ? clock64() : 0;
+    auto tick = [&](int k) {
+        if (prof) {
+            const long long now = clock64();
+            pc[k] += (unsigned long long)(now - tprev);
+            tprev = now;
+        }
+    };
+    const long long tstart = tprev;
+    cplx x[K::E], ac[K::E];    // transformed digit row (limb-0 sub-teams) / this sub-team's accumulator: column `col`, limb `limb`
+    double maxfrac = 0.0;
+    uint32_t accv[2 * K::E];   // limb-0 sub-teams: the 2E words of acc[col] this thread decomposes and updates
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+        accv[2 * e] = acc[col * K::N + j];
+        accv[2 * e + 1] = acc[col * K::N + j + K::M];
+    }
+    uint32_t q = 0, nexec = 0;
+    cluster_sync_all();
+
+#pragma unroll 1
+    for (uint32_t i = 0; i < a.n; i++) {
+        const uint32_t rot = at[i];
+        if (rot == 0) {
+#pragma unroll 1
+            for (uint32_t d = 0; d < (uint32_t)K::P; d++, q++) {
+                mbar_wait(full + (q % K::NSLOT), (q / K::NSLOT) & 1u, a.err_flag);
+                __syncwarp();
+                if (lane == 0) release_row(q);
+            }
+            continue;
+        }
+#pragma unroll
+        for (int e = 0; e < K::E; e++) ac[e] = cplx{0.0, 0.0};
+        if (limb == 0) {
+            // digits of level `lev` of rot(acc) - acc, polynomial `col`, and their forward transform; published in buf0
+#pragma unroll
+            for (int e = 0; e < K::E; e++) {
+                int32_t dl[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t j = (((uint32_t)e << C::LOGT) | t) + (uint32_t)h * K::M;
+                    int32_t d[K::L];
+                    decompose_signed<K::LOGB, K::L>(rot_coeff(acc + col * K::N, j, rot, K::LOGN) - accv[2 * e + h], d);
+                    dl[h] = d[0];
+#pragma unroll
+                    for (int l = 1; l < K::L; l++) dl[h] = lev == (uint32_t)l ? d[l] : dl[h];
+                }
+                x[e] = cplx{i2d(dl[0]), i2d(dl[1])};
+            }
+            fwd_pass<C::LOGE, C::LOGE>(x, a.tw.twA);
+            tick(0);
+            store_A<C>(x, buf0, t);
+            sub_sync();
+            {
+                cplx tw[C::NB_TW];
+                derive_pass_tw<C::QB>(tw, twB_base);
+                load_B<C>(x, buf0, jbB);
+                fwd_pass<C::LOGE, C::QB>(x, tw);
+                store_B<C>(x, buf1, jbB);
+            }
+            sub_sync();
+            {
+                cplx tw[C::NC_TW];
+                derive_pass_tw<C::LOGE>(tw, twC_base);
+                load_C<C>(x, buf1, t);
+                fwd_pass<C::LOGE, C::LOGE>(x, tw);
+            }
+#pragma unroll
+            for (int e = 0; e < K::E; e++) buf0[e * K::T + t] = x[e];   // slot order, as phase_xstore
+            tick(1);
+        }
+        __syncthreads();   // all P transformed rows of this level are published
+        tick(2);
+        // multiply-accumulate of ONE limb: slot d of the level holds at column position `col` the row of polynomial (col + d) mod P
+#pragma unroll 1
+        for (uint32_t d = 0; d < (uint32_t)K::P; d++, q++) {
+            const uint32_t s = q % K::NSLOT;
+            mbar_wait(full + s, (q / K::NSLOT) & 1u, a.err_flag);
+            const cplx *g = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES) + (limb * (uint32_t)K::P + col) * (uint32_t)K::M + t;
+            const cplx *xb = subbuf((col + d) % (uint32_t)K::P);   // the publishing (limb-0) sub-team's buf0
+#pragma unroll
+            for (int e = 0; e < K::E; e++) {
+                const cplx xv = xb[e * K::T + t], gv = g[e * K::T];
+                ac[e].re = fma_d(-xv.im, gv.im, fma_d(xv.re, gv.re, ac[e].re));
+                ac[e].im = fma_d(xv.im, gv.re, fma_d(xv.re, gv.im, ac[e].im));
+            }
+            __syncwarp();
+            if (lane == 0) release_row(q);
+        }
+        tick(3);
+        __syncthreads();   // the published rows have been read: the buffers are free
+        tick(4);
+        // single-limb inverse through the sub-team's two buffers
+        {
+            cplx tw[C::NC_TW];
+            derive_pass_tw<C::LOGE>(tw, twC_base);
+            inv_pass<C::LOGE, C::LOGE>(ac, tw);
+            store_C<C>(ac, buf0, t);
+        }
+        sub_sync();
+        {
+            cplx tw[C::NB_TW];
+            derive_pass_tw<C::QB>(tw, twB_base);
+            load_B<C>(ac, buf0, jbB);
+            inv_pass<C::LOGE, C::QB>(ac, tw);
+            store_B<C>(ac, buf1, jbB);
+        }
+        sub_sync();
+        load_A<C>(ac, buf1, t);
+        inv_pass<C::LOGE, C::LOGE>(ac, a.tw.twA);
+        uint32_t pv[2 * K::E];
+#pragma unroll
+        for (int e = 0; e < K::E; e++) {
+            pv[2 * e] = round_u32<false>(ac[e].re, maxfrac);
+            pv[2 * e + 1] = round_u32<false>(ac[e].im, maxfrac);
+        }
+        // the high limb hands its words (already shifted) to the low-limb sub-team of the same column through its own buf0
+        uint32_t *hand = reinterpret_cast<uint32_t *>(subbuf(col + (uint32_t)K::P));
+        if (limb == 1) {
+#pragma unroll
+            for (int k = 0; k < 2 * K::E; k++) hand[k * K::T + t] = pv[k] << 16;
+        }
+        tick(5);
+        __syncthreads();
+        uint32_t *stepbuf = part + (size_t)(nexec & 1u) * K::L * K::P * K::N;
+        nexec++;
+        if (limb == 0) {
+#pragma unroll
+            for (int k = 0; k < 2 * K::E; k++) pv[k] += hand[k * K::T + t];
+            uint32_t *mine = stepbuf + ((size_t)lev * K::P + col) * K::N;
+            const uint32_t mine_addr = smem_u32(mine);
+#pragma unroll
+            for (uint32_t r = 1; r < (uint32_t)K::L; r++) {   // push to the peers (same offset in their shared memory)
+                uint32_t peer = lev + r;
+                peer = peer >= (uint32_t)K::L ? peer - (uint32_t)K::L : peer;
+                uint32_t remote;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine_addr), "r"(peer));
+#pragma unroll
+                for (int k = 0; k < 2 * K::E; k++) {
+                    const uint32_t j = (((uint32_t)(k >> 1) << C::LOGT) | t) + (uint32_t)(k & 1) * K::M;
+                    asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + j * 4u), "r"(pv[k]) : "memory");
+                }
+            }
+        }
+        tick(6);
+        cluster_sync_all();
+        tick(7);
+        if (limb == 0) {
+#pragma unroll
+            for (int k = 0; k < 2 * K::E; k++) {
+                const uint32_t j = (((uint32_t)(k >> 1) << C::LOGT) | t) + (uint32_t)(k & 1) * K::M;
+                uint32_t sum = pv[k];
+#pragma unroll
+                for (uint32_t l = 0; l < (uint32_t)K::L; l++)
+                    if (l != lev) sum += stepbuf[((size_t)l * K::P + col) * K::N + j];
+                accv[k] += sum;
+                acc[col * K::N + j] = accv[k];
+            }
+            sub_sync();   // acc[col] (read with a rotation by this sub-team only) is up to date before the next step's digits
+        }
+        tick(8);
+    }
+    if (prof) {
+        pc[9] = (unsigned long long)(clock64() - tstart);
+        for (int k = 0; k < 10; k++) a.prof[k] = pc[k];
+    }
+    cluster_sync_all();
+    if (lev == 0 && limb == 0) {
+        uint32_t *out = a.glwe_out + ((size_t)ct * K::P + col) * K::N;
+        for (uint32_t idx = t; idx < (uint32_t)K::N; idx += K::T) out[idx] = acc[col * K::N + idx];
+    }
+    (void)maxfrac;
+}
+
 }  // namespace fft
 }  // namespace tfhe

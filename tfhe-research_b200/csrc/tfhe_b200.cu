@@ -46,7 +46,7 @@ struct tfhe_ctx {
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
     bool ks_mma = true;                     // key switch on the integer tensor cores where the key has a byte-plane copy
-    int latency_cfg = 3;                    // FFT path, small batches: 0 throughput kernel, 1 one team + deep key ring, 2 all teams of a CTA on one ciphertext, 3 a cluster of L CTAs per ciphertext (then 2, then 0 as the batch grows)
+    int latency_cfg = 4;                    // FFT path, small batches: 0 throughput kernel, 1 one team + deep key ring, 2 all teams of a CTA on one ciphertext, 3 a cluster of L CTAs per ciphertext, 4 the same with every CTA split by key limb (then 2, then 0 as the batch grows)
     fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
@@ -205,6 +205,9 @@ using KF1H = fft::FftPbsCfg<10, 3, 1, 3, 8, 3, false, false, 1, 3>;
 // one-level-per-CTA cluster configurations (kernels_fft_cluster.cuh): cluster of L CTAs per ciphertext
 using KF0X = fft::FftPbsCfg<9, 3, 2, 6, 4, 1, false, false, 1, 4>;
 using KF1X = fft::FftPbsCfg<10, 3, 1, 3, 8, 1, false, false, 1, 4>;
+// ... with each CTA's work split by key limb over twice the warps (two more exchange buffers per CTA: a three-row ring)
+using KF0S = fft::FftPbsCfg<9, 3, 2, 6, 4, 1, false, false, 1, 3>;
+using KF1S = fft::FftPbsCfg<10, 3, 1, 3, 8, 1, false, false, 1, 3>;
 template <class K>
 constexpr size_t fft_smem_bytes(size_t n) { return (size_t)K::CTS * K::team_bytes((int)n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 4 * K::NSLOT + 16; }
 // the FFT path is instantiated for P0 and P1 shapes; its shared-memory layout holds the mod-switched mask of every
@@ -243,7 +246,7 @@ int launch_pbs_fft_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     return TFHE_OK;
 }
 // returns TFHE_OK, or -100 when the cluster shape cannot be launched on this device (the caller falls back)
-template <class K>
+template <class K, bool SPLIT = false>
 int launch_pbs_fft_cluster_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *key) {
     fft::FftArgs f = {};
     f.tw = ctx->ftw;
@@ -251,16 +254,16 @@ int launch_pbs_fft_cluster_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *k
     f.lwe_in = a.lwe_in; f.luts = a.luts; f.lut_idx = a.lut_idx;
     f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
     f.n = a.n; f.batch = a.batch; f.mode = 0; f.log_p = a.log_p; f.enc_shift = a.enc_shift; f.n_luts = a.n_luts;
-    const size_t smem = fft::ClusterLayout<K>::smem_bytes(a.n);
-    auto kern = fft::pbs_fft_cluster_kernel<K>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-        false) {
+    const size_t smem = SPLIT ? fft::ClusterSplitLayout<K>::smem_bytes(a.n) : fft::ClusterLayout<K>::smem_bytes(a.n);
+    if (smem > 227 * 1024) return -100;
+    auto kern = SPLIT ? fft::pbs_fft_cluster_split_kernel<K> : fft::pbs_fft_cluster_kernel<K>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return -100;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(a.batch * K::L), 1, 1);
-    cfg.blockDim = dim3(K::TEAM_THREADS, 1, 1);
+    cfg.blockDim = dim3(SPLIT ? fft::ClusterSplitLayout<K>::THREADS : K::TEAM_THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
@@ -271,7 +274,9 @@ int launch_pbs_fft_cluster_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *k
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1) {
+    // all clusters of the batch must be co-resident (a second wave of clusters would double the latency: the all-teams kernel is
+    // faster then); clusters are placed inside GPCs, so this is fewer than sm_count / L (measured: 24 clusters of 6 do not fit)
+    if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg) != cudaSuccess || max_clusters < 1 || (int)a.batch > max_clusters) {
         cudaGetLastError();
         return -100;
     }
@@ -292,10 +297,13 @@ int launch_pbs_fft_cluster_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *k
         CU(cudaStreamSynchronize(ctx->stream));
         CU(cudaMemcpy(h, d_prof, sizeof h, cudaMemcpyDeviceToHost));
         cudaFree(d_prof);
-        fprintf(stderr, "cluster kernel (L = %d CTAs per ciphertext), first CTA, cycles per step (n = %u): digits + pass A %.0f, forward rest %.0f, wait own row %.0f, mac own %.0f, "
-                        "team barrier %.0f, wait + mac peer rows %.0f, inverse + rounding %.0f, cluster barrier %.0f, accumulate via DSMEM %.0f, total %.0f\n", K::L, a.n,
-                (double)h[0] / a.n, (double)h[1] / a.n, (double)h[2] / a.n, (double)h[3] / a.n, (double)h[4] / a.n, (double)h[5] / a.n, (double)h[6] / a.n, (double)h[7] / a.n,
-                (double)h[8] / a.n, (double)h[9] / a.n);
+        const char *lab[9] = {"digits + pass A", "forward rest", "wait own row", "mac own row", "team barrier", "wait + mac peer rows", "inverse + rounding + push",
+                              "cluster barrier", "accumulate"};
+        const char *labs[9] = {"digits + pass A", "forward rest", "barrier (rows published)", "mac (one limb, all rows)", "barrier (rows read)", "inverse (one limb) + rounding",
+                               "combine limbs + push", "cluster barrier", "accumulate"};
+        fprintf(stderr, "%s (L = %d CTAs per ciphertext), first CTA, cycles per step (n = %u):", SPLIT ? "cluster kernel, CTAs split by key limb" : "cluster kernel", K::L, a.n);
+        for (int k = 0; k < 9; k++) fprintf(stderr, " %s %.0f,", SPLIT ? labs[k] : lab[k], (double)h[k] / a.n);
+        fprintf(stderr, " total %.0f\n", (double)h[9] / a.n);
     }
     return TFHE_OK;
 }
@@ -373,7 +381,13 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
 #define TFHE_FFT_LATENCY_CFG 1
 #endif
         if (TFHE_FFT_LATENCY_CFG && ctx->latency_cfg && a.mode == 0 && !ctx->fft_check && a.batch <= (uint32_t)ctx->sm_count) {
-            if (ctx->latency_cfg == 3) {   // one CTA per gadget level, a cluster per ciphertext
+            if (ctx->latency_cfg == 4) {   // one CTA per gadget level, a cluster per ciphertext, every CTA split by key limb
+                int rc = -100;
+                if (ctx->pbs_id == 0 && a.batch * KF0S::L <= (uint32_t)ctx->sm_count) rc = launch_pbs_fft_cluster_t<KF0S, true>(ctx, a, bk->d_bsk_fft);
+                if (ctx->pbs_id == 1 && a.batch * KF1S::L <= (uint32_t)ctx->sm_count) rc = launch_pbs_fft_cluster_t<KF1S, true>(ctx, a, bk->d_bsk_fft);
+                if (rc != -100) return rc;
+            }
+            if (ctx->latency_cfg >= 3) {   // one CTA per gadget level, a cluster per ciphertext
                 int rc = -100;
                 if (ctx->pbs_id == 0 && a.batch * KF0X::L <= (uint32_t)ctx->sm_count && fft::ClusterLayout<KF0X>::smem_bytes(a.n) <= 227 * 1024)
                     rc = launch_pbs_fft_cluster_t<KF0X>(ctx, a, bk->d_bsk_fft);
@@ -628,7 +642,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_mma = strcmp(e, "imad") != 0;
-    if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) { const int v = atoi(e); if (v >= 0 && v <= 3) ctx->latency_cfg = v; }
+    if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) { const int v = atoi(e); if (v >= 0 && v <= 4) ctx->latency_cfg = v; }
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
         if (!strcmp(e, "fft") && fft_available(ctx->pbs_id, ctx->n())) ctx->path = TFHE_PATH_FFT;
         if (!strcmp(e, "ntt")) ctx->path = TFHE_PATH_NTT;
@@ -687,7 +701,7 @@ int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path) {
 }
 int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on) {
     if (!ctx) return TFHE_E_PARAM;
-    if (on < 0 || on > 3) return fail(ctx, TFHE_E_PARAM, "latency configuration: 0 .. 3");
+    if (on < 0 || on > 4) return fail(ctx, TFHE_E_PARAM, "latency configuration: 0 .. 4");
     ctx->latency_cfg = on;
     return TFHE_OK;
 }

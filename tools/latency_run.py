@@ -25,7 +25,7 @@ def main():
         d_tv = torch.from_numpy(T.construct_identity_test_vector(p).view(np.int32).copy()).cuda()
         rec = {}
         for B in (1, 8, 24, 148):
-            for name, on in (("cluster", 3), ("all_teams", 2), ("deep_ring", 1), ("throughput_cfg", 0)):
+            for name, on in (("cluster_split", 4), ("cluster", 3), ("all_teams", 2), ("deep_ring", 1), ("throughput_cfg", 0)):
                 ctx.set_latency_config(on)
                 x = d_in[:B].contiguous()
                 o = torch.empty((B, p.n + 1), dtype=torch.int32, device="cuda")
@@ -41,7 +41,7 @@ def main():
         if preset == "P0":       # config #1: one bootstrapped NAND
             c0 = torch.from_numpy(T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, 1), 1, 9001).view(np.int32)[None].copy()).cuda()
             c1 = torch.from_numpy(T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, 1), 1, 9002).view(np.int32)[None].copy()).cuda()
-            for name, on in (("cluster", 3), ("all_teams", 2), ("deep_ring", 1), ("throughput_cfg", 0)):
+            for name, on in (("cluster_split", 4), ("cluster", 3), ("all_teams", 2), ("deep_ring", 1), ("throughput_cfg", 0)):
                 ctx.set_latency_config(on)
                 ts = []
                 for _ in range(5):
