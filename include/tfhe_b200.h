@@ -114,9 +114,13 @@ int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx);
  *   TFHE_KS_IMAD  wrapping 32-bit multiply-adds on the integer pipe, every parameter set;
  *   TFHE_KS_MMA   integer tensor cores, exact through the four byte planes of the key (s8 x u8 -> s32 sums, recombined
  *                 mod 2^32); needs k*N*ks_levels % 64 == 0 and k*N*ks_levels * 2^ks_log_base * 255 < 2^31, else IMAD runs.
- * Default: env TFHE_B200_KS=imad|mma, else MMA where it applies.  May be switched at any time. */
+ *   TFHE_KS_TCGEN05  the same byte-plane product on the 5th-generation tensor cores: tcgen05.mma kind::i8 (s8 x u8 -> s32) with
+ *                 the accumulator in tensor memory and both operands streamed by TMA (kernels_ks_tcgen05.cuh); additionally
+ *                 needs k*N*ks_levels % 128 == 0, else MMA runs.
+ * Default: env TFHE_B200_KS=imad|mma|tcgen05, else the fastest that applies.  May be switched at any time. */
 #define TFHE_KS_IMAD 0
 #define TFHE_KS_MMA 1
+#define TFHE_KS_TCGEN05 2
 int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path);
 /* FFT path only.  Exactness rests on the a-priori error bound (2^-9 before rounding).  With checking
  * switched on (env TFHE_B200_FFT_CHECK=1 or tfhe_ctx_set_fft_check) the blind rotation runs a kernel variant that also

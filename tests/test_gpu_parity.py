@@ -144,8 +144,9 @@ def test_blind_rotate_extract_keyswitch_bootstrap(preset, n):
 
 @pytest.mark.parametrize("preset,n", [("P1:fft", 21), ("P0:fft", 7), ("P2:fft", 5), ("P1:fft", 630)])
 def test_key_switch_tensor_core_path_vs_imad_vs_oracle(preset, n):
-    """key_switching.rs:63-103 on arbitrary input words: the integer-tensor-core product (byte planes, KS_MMA) and the
-    32-bit multiply-add product (KS_IMAD) give the oracle's bits, for ragged batch sizes and extreme words."""
+    """key_switching.rs:63-103 on arbitrary input words: the integer-tensor-core products (byte planes; KS_MMA = mma.sync,
+    KS_TCGEN05 = tcgen05.mma with the accumulator in tensor memory) and the 32-bit multiply-add product (KS_IMAD) give the
+    oracle's bits, for ragged batch sizes and extreme words."""
     import ctypes as C
     e = env(preset, n)
     L = orc.lib()
@@ -161,8 +162,11 @@ def test_key_switch_tensor_core_path_vs_imad_vs_oracle(preset, n):
         got_mma = e.ctx.key_switch(e.bk, lwe)
         e.ctx.set_ks_path(T.KS_IMAD)
         got_imad = e.ctx.key_switch(e.bk, lwe)
+        e.ctx.set_ks_path(T.KS_TCGEN05)               # tcgen05.mma kind::i8 + TMEM + TMA (falls back to MMA where it does not apply)
+        got_tc5 = e.ctx.key_switch(e.bk, lwe)
         e.ctx.set_ks_path(T.KS_MMA)
         assert np.array_equal(got_mma, got_imad), B
+        assert np.array_equal(got_tc5, got_imad), B
         for b in (0, 1, 2, 3, B - 1):
             exp = orc.z(n + 1)
             L.orc_key_switch_lwe(C.byref(e.o), lwe[b], e.ksk, exp)

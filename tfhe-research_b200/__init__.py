@@ -25,13 +25,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-ldl"]
 _SOURCES = ["tfhe_b200.cu", "host_api.cpp", "tfhe_mgpu.cpp"]
 _DEPS = _SOURCES + ["kernels.cuh", "pbs_team.cuh", "tfhe_core.cuh", "host_tables.hpp", "api_internal.hpp",
-                    "kernels_fft.cuh", "kernels_fft_latency.cuh", "kernels_fft_cluster.cuh", "fft_team.cuh", "host_tables_fft.hpp", "tfhe_mgpu.cpp",
+                    "kernels_fft.cuh", "kernels_fft_latency.cuh", "kernels_fft_cluster.cuh", "kernels_ks_tcgen05.cuh", "fft_team.cuh", "host_tables_fft.hpp", "tfhe_mgpu.cpp",
                     os.path.join("..", "..", "include", "tfhe_b200.h")]
 
 TFHE_OK, TFHE_E_PARAM, TFHE_E_CUDA, TFHE_E_OOM, TFHE_E_ASSERT, TFHE_E_NCCL = 0, -1, -2, -3, -4, -5
 AND, OR, XOR, NAND, NOR, XNOR = range(6)
 PATH_NTT, PATH_FFT = 0, 1   # arithmetic path of the external product (include/tfhe_b200.h TFHE_PATH_*)
-KS_IMAD, KS_MMA = 0, 1      # arithmetic of the key-switching product (include/tfhe_b200.h TFHE_KS_*)
+KS_IMAD, KS_MMA, KS_TCGEN05 = 0, 1, 2   # arithmetic of the key-switching product (include/tfhe_b200.h TFHE_KS_*)
 
 
 class TfheError(RuntimeError):
@@ -392,7 +392,8 @@ class Context:
         self._ck(lib().tfhe_ctx_set_pbs_path(self._h, int(path)))
 
     def set_ks_path(self, path: int):
-        """KS_IMAD (32-bit multiply-adds) or KS_MMA (integer tensor cores, exact through byte planes); same bits."""
+        """KS_IMAD (32-bit multiply-adds), KS_MMA (integer tensor cores via mma.sync, exact through byte planes) or KS_TCGEN05
+        (the same product with tcgen05.mma + TMEM + TMA); same bits."""
         self._ck(lib().tfhe_ctx_set_ks_path(self._h, int(path)))
 
     @property

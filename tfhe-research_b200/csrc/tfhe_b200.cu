@@ -16,6 +16,7 @@
 #include "kernels_fft.cuh"
 #include "kernels_fft_latency.cuh"
 #include "kernels_fft_cluster.cuh"
+#include "kernels_ks_tcgen05.cuh"
 
 using namespace tfhe;
 
@@ -45,7 +46,7 @@ struct tfhe_ctx {
     int pbs_id = -1, ks_id = -1;
     int path = TFHE_PATH_NTT;               // arithmetic path of the external product (tfhe_ctx_set_pbs_path)
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
-    bool ks_mma = true;                     // key switch on the integer tensor cores where the key has a byte-plane copy
+    int ks_path = TFHE_KS_TCGEN05;          // arithmetic of the key-switching product: TFHE_KS_IMAD / TFHE_KS_MMA (mma.sync) / TFHE_KS_TCGEN05 (tcgen05.mma + TMEM + TMA)
     int latency_cfg = 4;                    // FFT path, small batches: 0 throughput kernel, 1 one team + deep key ring, 2 all teams of a CTA on one ciphertext, 3 a cluster of L CTAs per ciphertext, 4 the same with every CTA split by key limb (then 2, then 0 as the batch grows)
     fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
     fft::TwTablesF ftw;
@@ -77,7 +78,9 @@ struct tfhe_bk {
     uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]                      (TFHE_PATH_NTT)
     fft::cplx *d_bsk_fft = nullptr; // [n][ROWS][2 limbs][P][N/2], scaled 2/N  (TFHE_PATH_FFT)
     uint32_t *d_ksk = nullptr;      // [kN*l_ks][ksk_stride], ksk_stride = n+1 rounded up to 128 words, zero padded
-    uint8_t *d_ksk_t = nullptr;     // [ksk_stride*4][kN*l_ks] byte planes, k contiguous (ks_mma_kernel); null if not applicable
+    uint8_t *d_ksk_t = nullptr;     // [ksk_stride*4][kN*l_ks] byte planes, k contiguous (ks_mma_kernel, ks_tcgen05_kernel); null if not applicable
+    CUtensorMap map_kskt;           // TMA descriptor of d_ksk_t (ks_tcgen05_kernel)
+    bool tc5 = false;               // map_kskt is valid
     size_t ksk_stride = 0;
 };
 
@@ -440,6 +443,28 @@ int launch_transform(tfhe_ctx *ctx, const uint32_t *raw, uint32_t *out, size_t n
     return fail(ctx, TFHE_E_PARAM, "no kernel instantiation for this parameter set");
 }
 
+// TMA descriptor of a K-major byte matrix [rows][kd] with a [box_rows][128-byte] box and the 128-byte swizzle the tcgen05
+// shared-memory descriptors of ks_tcgen05_kernel expect.  cuTensorMapEncodeTiled is a driver entry point: resolved at run time.
+bool make_byte_tensor_map(CUtensorMap *map, const void *base, size_t rows, size_t kd, uint32_t box_rows) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            cudaGetLastError();
+            return false;
+        }
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)kd, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kd};
+    const cuuint32_t box[2] = {(cuuint32_t)KT_BK, box_rows}, estr[2] = {1, 1};
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // key switch of `batch` ciphertexts; src is GLWE accumulators [B][P][N] (from_lwe=0) or extracted LWEs
 // [B][kN+1] (from_lwe=1), all device pointers.
 int run_key_switch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *src, int from_lwe, size_t batch, uint32_t *d_out) {
@@ -468,7 +493,17 @@ int run_key_switch(tfhe_ctx *ctx, const tfhe_bk *bk, const uint32_t *src, int fr
         ctx->launches += 3;
         return TFHE_OK;
     }
-    if (bk->d_ksk_t && ctx->ks_mma) {
+    if (bk->tc5 && ctx->ks_path == TFHE_KS_TCGEN05) {
+        // 5th-generation tensor cores: tcgen05.mma kind::i8, accumulator in TMEM, operands by TMA (kernels_ks_tcgen05.cuh)
+        CUtensorMap map_a;
+        if (!make_byte_tensor_map(&map_a, dg, batch, KD, KT_BM)) return fail(ctx, TFHE_E_CUDA, "cuTensorMapEncodeTiled failed for the digit matrix");
+        dim3 grid((unsigned)(bk->ksk_stride * 4 / KT_BN), (unsigned)((batch + KT_BM - 1) / KT_BM));
+        ks_tcgen05_kernel<<<grid, KT_THREADS, KT_SMEM, ctx->stream>>>(map_a, bk->map_kskt, bd, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch, ctx->d_err);
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        return TFHE_OK;
+    }
+    if (bk->d_ksk_t && ctx->ks_path != TFHE_KS_IMAD) {   // TFHE_KS_MMA, or TFHE_KS_TCGEN05 where that form does not apply
         // integer tensor cores, exact through byte planes (kernels.cuh K4-MMA)
         dim3 grid((unsigned)(bk->ksk_stride * 4 / KM_BN), (unsigned)((batch + KM_BM - 1) / KM_BM));
         ks_mma_kernel<<<grid, KM_THREADS, KM_SMEM, ctx->stream>>>(dg, bk->d_ksk_t, bd, d_out, (uint32_t)KD, (uint32_t)ctx->n(), (uint32_t)batch);
@@ -504,6 +539,12 @@ cudaError_t copy_ksk(tfhe_ctx *ctx, tfhe_bk *bk, const uint32_t *ksk) {
         ksk_byte_transpose_kernel<<<grid, 128, 0, ctx->stream>>>(bk->d_ksk, bk->d_ksk_t, (uint32_t)KD, (uint32_t)bk->ksk_stride);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
         if ((e = cudaFuncSetAttribute(ks_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KM_SMEM)) != cudaSuccess) return e;
+        // tcgen05 form: whole 128-byte K slabs and 256-column tiles (ksk_stride is a multiple of 128 words = 512 byte columns)
+        if (KD % KT_BK == 0 && make_byte_tensor_map(&bk->map_kskt, bk->d_ksk_t, bk->ksk_stride * 4, KD, KT_BN) &&
+            cudaFuncSetAttribute(ks_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KT_SMEM) == cudaSuccess)
+            bk->tc5 = true;
+        else
+            cudaGetLastError();
         ctx->launches++;
     }
     return cudaSuccess;
@@ -641,7 +682,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         ctx->path = TFHE_DEFAULT_PATH;
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
-    if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_mma = strcmp(e, "imad") != 0;
+    if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_path = !strcmp(e, "imad") ? TFHE_KS_IMAD : !strcmp(e, "tcgen05") ? TFHE_KS_TCGEN05 : TFHE_KS_MMA;
     if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) { const int v = atoi(e); if (v >= 0 && v <= 4) ctx->latency_cfg = v; }
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
         if (!strcmp(e, "fft") && fft_available(ctx->pbs_id, ctx->n())) ctx->path = TFHE_PATH_FFT;
@@ -695,8 +736,8 @@ int tfhe_ctx_set_pbs_path(tfhe_ctx *ctx, int path) {
 int tfhe_ctx_get_pbs_path(const tfhe_ctx *ctx) { return ctx ? ctx->path : TFHE_E_PARAM; }
 int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path) {
     if (!ctx) return TFHE_E_PARAM;
-    if (path != TFHE_KS_IMAD && path != TFHE_KS_MMA) return fail(ctx, TFHE_E_PARAM, "unknown key-switch path");
-    ctx->ks_mma = path == TFHE_KS_MMA;
+    if (path != TFHE_KS_IMAD && path != TFHE_KS_MMA && path != TFHE_KS_TCGEN05) return fail(ctx, TFHE_E_PARAM, "unknown key-switch path");
+    ctx->ks_path = path;
     return TFHE_OK;
 }
 int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on) {
