@@ -100,6 +100,23 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(T.TfheError) as e:
         T.Context(T.TfheParams.default(True), 0)
     assert e.value.code == T.TFHE_E_CUDA
+    with pytest.raises(T.TfheError) as e:          # the all-GPUs handle has no fallback either
+        T.MultiGpuContext(T.TfheParams.default(True), 2)
+    assert e.value.code == T.TFHE_E_CUDA
+
+
+def test_mgpu_argument_checks_without_gpu():
+    import ctypes as C
+    L, p, h = T.lib(), T.TfheParams.default(True), C.c_void_p()
+    assert L.tfhe_mgpu_create(C.byref(p), 0, None, C.byref(h)) == T.TFHE_E_PARAM          # n_gpus < 1
+    bad = T.TfheParams.preset("P0", log_q=64)
+    assert L.tfhe_mgpu_create(C.byref(bad), 1, None, C.byref(h)) == T.TFHE_E_PARAM        # invalid parameter set
+    assert L.tfhe_mgpu_n_gpus(None) == T.TFHE_E_PARAM
+    assert L.tfhe_mgpu_last_error(None) == b"null tfhe_mgpu"
+    L.tfhe_mgpu_destroy(None)
+    L.tfhe_mgpu_bk_free(None)
+    assert L.tfhe_mgpu_bootstrap_batch(None, None, None, None, 0, None, 0, None) == T.TFHE_E_PARAM
+    assert L.tfhe_ctx_get_stream(None) is None and L.tfhe_bk_get_path(None) == T.TFHE_E_PARAM
 
 
 def test_product_never_imports_oracle():
