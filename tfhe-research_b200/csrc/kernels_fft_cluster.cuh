@@ -43,13 +43,6 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ uint32_t ld_dsmem_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
-    uint32_t remote, v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(cta_rank));
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
-    return v;
-}
-
 template <class K>
 __global__ void __launch_bounds__(K::TEAM_THREADS, 1) pbs_fft_cluster_kernel(const __grid_constant__ FftArgs a) {
     using C = typename K::F;

@@ -257,9 +257,12 @@ int launch_pbs_fft_cluster_t(tfhe_ctx *ctx, const PbsArgs &a, const fft::cplx *k
     f.lwe_in = a.lwe_in; f.luts = a.luts; f.lut_idx = a.lut_idx;
     f.glwe_out = a.glwe_out; f.err_flag = a.err_flag; f.margin = ctx->d_margin;
     f.n = a.n; f.batch = a.batch; f.mode = 0; f.log_p = a.log_p; f.enc_shift = a.enc_shift; f.n_luts = a.n_luts;
-    const size_t smem = SPLIT ? fft::ClusterSplitLayout<K>::smem_bytes(a.n) : fft::ClusterLayout<K>::smem_bytes(a.n);
+    using Layout = typename std::conditional<SPLIT, fft::ClusterSplitLayout<K>, fft::ClusterLayout<K>>::type;
+    const size_t smem = Layout::smem_bytes(a.n);
     if (smem > 227 * 1024) return -100;
-    auto kern = SPLIT ? fft::pbs_fft_cluster_split_kernel<K> : fft::pbs_fft_cluster_kernel<K>;
+    void (*kern)(fft::FftArgs);
+    if constexpr (SPLIT) kern = fft::pbs_fft_cluster_split_kernel<K>;
+    else kern = fft::pbs_fft_cluster_kernel<K>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return -100;
