@@ -214,3 +214,50 @@ def test_latency_configuration_same_bits_as_throughput_configuration(preset):
     if preset != "P2":
         assert np.array_equal(ref[1], orc.bootstrap(oparams(p), cts[1], bsk, ksk, tv))
     bk.free(); ctx.close()
+
+
+def test_tensor_memory_exchange_same_bits_as_shared_memory_exchange():
+    """N = 512 (the reference's default set, lib.rs:101-123): the throughput kernel exchanges the register passes of its transforms
+    through tensor memory (fft_tmem.cuh, another butterfly order and spectral layout, twiddles derived per lane).  Same bits as
+    the shared-memory kernel, the NTT path and the oracle -- at full n, over partially filled CTAs and several waves, with skipped
+    steps -- and a rounding margin of the same size."""
+    p = T.TfheParams.preset("P0")
+    lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 0xB200)
+    pm = 1 << p.log_p
+    ctx = T.Context(p, 0, path=T.PATH_FFT)
+    ctx.set_latency_config(0)                                      # the throughput kernel at every batch size
+    ctx.set_fft_exchange(True)
+    bk = ctx.upload_key(bsk, ksk)
+    tv = T.construct_identity_test_vector(p)
+    cts = np.stack([T.encrypt_lwe_plaintext(p, lwe_sk, T.encode_message(p, i % pm), 1, i) for i in range(700)])
+    cts[7, :p.n] = 0
+    cts[8, :p.n // 2] = 0
+    rng = np.random.default_rng(3)
+    cts[9] = rng.integers(0, 1 << 32, p.n + 1, dtype=np.uint64).astype(np.uint32)   # not a valid encryption: any bits must agree
+    margins = {}
+    for B in (1, 3, 150, 593, 700):
+        outs = {}
+        for tm in (True, False):
+            ctx.set_fft_exchange(tm)
+            outs[tm] = ctx.bootstrap(bk, cts[:B], tv)
+            outs[tm, "acc"] = ctx.blind_rotate(bk, cts[:B], tv)
+        assert np.array_equal(outs[True], outs[False]), B
+        assert np.array_equal(outs[True, "acc"], outs[False, "acc"]), B
+    for tm in (True, False):
+        ctx.set_fft_exchange(tm)
+        ctx.set_fft_check(True)
+        ctx.fft_rounding_margin()
+        chk = ctx.bootstrap(bk, cts[:150], tv)
+        margins[tm] = ctx.fft_rounding_margin()
+        ctx.set_fft_check(False)
+        assert np.array_equal(chk, outs[True][:150])
+    assert 0 < margins[True] < 2.0 ** -20 and margins[True] < 4 * margins[False] + 2.0 ** -30, margins
+    full = outs[True]
+    ntt = T.Context(p, 0, path=T.PATH_NTT)
+    bkn = ntt.upload_key(bsk, ksk)
+    assert np.array_equal(ntt.bootstrap(bkn, cts[:64], tv), full[:64])
+    bkn.free(); ntt.close()
+    assert np.array_equal(full[1], orc.bootstrap(oparams(p), cts[1], bsk, ksk, tv))
+    for i in (0, 5, 699):
+        assert T.decode_rounded(p, T.decrypt_lwe(lwe_sk, full[i])) == i % pm
+    bk.free(); ctx.close()

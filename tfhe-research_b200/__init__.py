@@ -111,7 +111,7 @@ def lib():
         "tfhe_keygen": [PP, C.c_uint64, VP, VP, VP, VP], "tfhe_keygen_bmmp": [PP, C.c_uint64, VP, VP, VP, VP],
         "tfhe_bk_upload_bmmp": [VP, VP, VP, C.POINTER(VP)],
         "tfhe_ctx_create": [PP, C.c_int, C.POINTER(VP)], "tfhe_ctx_set_stream": [VP, VP],
-        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_ks_path": [VP, C.c_int], "tfhe_ctx_set_fft_check": [VP, C.c_int], "tfhe_ctx_set_latency_config": [VP, C.c_int],
+        "tfhe_ctx_set_pbs_path": [VP, C.c_int], "tfhe_ctx_get_pbs_path": [VP], "tfhe_ctx_set_ks_path": [VP, C.c_int], "tfhe_ctx_set_fft_check": [VP, C.c_int], "tfhe_ctx_set_latency_config": [VP, C.c_int], "tfhe_ctx_set_fft_exchange": [VP, C.c_int],
         "tfhe_fft_rounding_margin": [VP, C.POINTER(C.c_double)],
         "tfhe_bk_upload": [VP, VP, VP, C.POINTER(VP)], "tfhe_bk_read_transformed": [VP, VP, SZ],
         "tfhe_bootstrap_batch": [VP, VP, VP, VP, SZ, VP, SZ, VP],
@@ -161,7 +161,7 @@ EXPORTS = [
     "tfhe_measure_int_peak", "tfhe_last_timing", "tfhe_ctx_set_pbs_path", "tfhe_ctx_get_pbs_path", "tfhe_ctx_set_ks_path", "tfhe_fft_rounding_margin", "tfhe_ctx_set_fft_check", "tfhe_measure_fp64_peak",
     "tfhe_bk_transformed_bytes", "tfhe_bk_read_transformed", "tfhe_bootstrap_batch_ks_first", "tfhe_gate_k_batch",
     "tfhe_file_write", "tfhe_file_read", "tfhe_keygen_bmmp", "tfhe_bk_upload_bmmp", "tfhe_bk_get_path", "tfhe_ctx_get_stream",
-    "tfhe_ctx_set_latency_config", "tfhe_mgpu_create", "tfhe_mgpu_destroy", "tfhe_mgpu_n_gpus", "tfhe_mgpu_ctx", "tfhe_mgpu_last_error", "tfhe_mgpu_bk_upload",
+    "tfhe_ctx_set_latency_config", "tfhe_ctx_set_fft_exchange", "tfhe_mgpu_create", "tfhe_mgpu_destroy", "tfhe_mgpu_n_gpus", "tfhe_mgpu_ctx", "tfhe_mgpu_last_error", "tfhe_mgpu_bk_upload",
     "tfhe_mgpu_bk_upload_bmmp", "tfhe_mgpu_bk_free", "tfhe_mgpu_bootstrap_batch", "tfhe_mgpu_gates_batch", "tfhe_mgpu_last_timing",
 ]
 
@@ -410,6 +410,11 @@ class Context:
         2 all teams of a CTA on its one ciphertext (batch <= SMs), 1 one team with a deep key ring, 0 / False the throughput
         configuration.  Same bits."""
         self._ck(lib().tfhe_ctx_set_latency_config(self._h, 4 if mode is True else int(mode)))
+
+    def set_fft_exchange(self, tensor_memory: bool = True):
+        """FFT path, N = 512: exchange the register passes of the transforms through tensor memory (default) or shared memory.
+        Keys uploaded while it is on carry the second key copy that kernel needs; same bits either way."""
+        self._ck(lib().tfhe_ctx_set_fft_exchange(self._h, 1 if tensor_memory else 0))
 
     def fft_rounding_margin(self) -> float:
         """Largest distance to an integer of any value rounded by the FFT path since the last call (must be << 0.5)."""

@@ -187,6 +187,7 @@ struct TwTablesF {
     const cplx *twB;     // [2^LOGE (hA)][NB_TW]
     const cplx *twC;     // [NC_TW][T]  (consecutive lanes read consecutive 16 bytes)
     const cplx *ztab;    // [2N] zeta^m, zeta = exp(2 pi i / 2N): monomial factors of the BMMP variant
+    const cplx *twX;     // [52] per-lane entries of the tensor-memory-exchange passes (fft_tmem.cuh TmemTw), M = 256 only
 };
 
 // Work split of one ciphertext (one "team"): P = k+1 SUB-TEAMS of T threads.  Sub-team s owns polynomial s of the GLWE
@@ -199,14 +200,17 @@ struct TwTablesF {
 // two-slot TMA ring stays at 2 x 32 KB when a row is 64 KB.
 // NSLOT: depth of the key ring.  Two slots feed a CTA whose 2-4 ciphertexts keep the SM busy; a CTA that holds ONE ciphertext
 // (small batches: latency) is bound by the round trip of each ring refill instead, and uses the idle shared memory for a deep ring.
-template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true, bool SINGLE_BUF_ = false, int HALVES_ = 1, int NSLOT_ = TFHE_FFT_NSLOT>
+// XCHG: 0 = the register passes of a transform exchange through shared memory (store_A/load_B, ...); 1 = through tensor memory
+// (fft_tmem.cuh: warp-sized sub-teams, M = 256), which also changes the spectral layout of the stored key.
+template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true, bool SINGLE_BUF_ = false, int HALVES_ = 1, int NSLOT_ = TFHE_FFT_NSLOT, int XCHG_ = 0>
 struct FftPbsCfg {
     using F = FftCfg<LOGN_ - 1, LOGE_>;
     static constexpr int LOGN = LOGN_, N = 1 << LOGN_, M = N / 2;
     static constexpr int K = K_, P = K_ + 1, L = L_, LOGB = LOGB_, ROWS = P * L;
     static constexpr int E = F::E, T = F::T;
     static constexpr int CTS = CTS_;                    // ciphertexts (teams) per CTA, sharing one key stream
-    static constexpr bool CHECK = CHECK_, SINGLE_BUF = SINGLE_BUF_;
+    static constexpr bool CHECK = CHECK_, SINGLE_BUF = SINGLE_BUF_, XCHG = XCHG_ != 0;
+    static_assert(!XCHG || (LOGN_ == 9 && LOGE_ == 3 && !SINGLE_BUF_ && HALVES_ == 1 && CTS_ == 4 && K_ <= 3), "tensor-memory exchanges: M = 256, 8 points per thread, one warp per sub-team, one team per lane quarter");
     static constexpr int HALVES = HALVES_, EH = E / HALVES_, MH = M / HALVES_;   // points per thread / per polynomial in one slot
     static constexpr int WARPS_PER_SUB = T / 32, TEAM_THREADS = P * T, THREADS = CTS * TEAM_THREADS;
     static_assert(LOGB * L <= 32 && 32 % LOGB == 0, "decomposer must divide log_q (SURVEY 9-B H2)");
@@ -223,14 +227,14 @@ struct FftPbsCfg {
     // shared memory per team: acc, then per sub-team {stash, buf0, buf1}, then the mod-switched mask
     static constexpr int TM_ACC = 0;                                   // u32 acc[P][N]
     static constexpr int STASH_BYTES = ((L > 1 ? (L - 1) : 1) * 2 * E * T * (int)sizeof(stash_t) + 15) & ~15;  // [(L-1)*2E][T]
-    static constexpr int NBUF = SINGLE_BUF ? 1 : 2;
+    static constexpr int NBUF = XCHG ? 0 : SINGLE_BUF ? 1 : 2;   // tensor-memory exchanges: no exchange buffer, rows are published in tensor memory too
     static constexpr int SUB_BYTES = STASH_BYTES + NBUF * F::MPAD * 16;   // + cplx buf[NBUF][MPAD]
     static constexpr int TM_SUB = TM_ACC + P * N * 4;
     static constexpr int TM_AT = TM_SUB + P * SUB_BYTES;               // u16 at[n+1] (size known at launch)
     static constexpr int team_bytes(int n) { return (TM_AT + (n + 1) * 2 + 127) & ~127; }
     // single-ciphertext modes borrow idle shared memory for the polynomial to decompose and a zero subtrahend: the
     // accumulators of teams 1 and 2, or (two teams) the accumulator and the first exchange buffer of team 1
-    static constexpr bool HAS_SINGLE_MODES = CTS >= 3 || (CTS == 2 && F::MPAD * 16 >= P * N * 4);   // CTS == 1 (latency configuration): blind rotation only
+    static constexpr bool HAS_SINGLE_MODES = !XCHG && (CTS >= 3 || (CTS == 2 && F::MPAD * 16 >= P * N * 4));   // CTS == 1 (latency configuration): blind rotation only
     static constexpr int SPARE_DIN = 1 * 0 + TM_ACC;                         // offset inside team 1
     static constexpr int SPARE_ZERO_TEAM = CTS >= 3 ? 2 : 1;
     static constexpr int SPARE_ZERO = CTS >= 3 ? TM_ACC : TM_SUB + STASH_BYTES;   // offset inside team SPARE_ZERO_TEAM
@@ -550,6 +554,21 @@ TFHE_HD void phase_J3r(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *b
     using C = typename K::F;
     load_A<C>(r.acc[0], buf0, t);
     load_A<C>(r.acc[1], buf1, t);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], twA);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], twA);
+#pragma unroll
+    for (int e = 0; e < K::E; e++) {
+        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+        accv[2 * e] = acc_c[j] + round_u32<K::CHECK>(r.acc[0][e].re, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].re, maxfrac) << 16);
+        accv[2 * e + 1] = acc_c[j + K::M] + round_u32<K::CHECK>(r.acc[0][e].im, maxfrac) + (round_u32<K::CHECK>(r.acc[1][e].im, maxfrac) << 16);
+        acc_c[j] = accv[2 * e];
+        acc_c[j + K::M] = accv[2 * e + 1];
+    }
+}
+// the same when both accumulators already sit in layout A in their registers (tensor-memory exchanges, fft_tmem.cuh)
+template <class K>
+TFHE_HD void phase_J3r_regs(FftRegs<K> &r, uint32_t t, const cplx *twA, uint32_t *acc_c, uint32_t *accv, double &maxfrac) {
+    using C = typename K::F;
     inv_pass<C::LOGE, C::LOGE>(r.acc[0], twA);
     inv_pass<C::LOGE, C::LOGE>(r.acc[1], twA);
 #pragma unroll

@@ -1,0 +1,311 @@
+// fft_tmem.cuh -- the register passes of the folded FFT exchanged through TENSOR MEMORY instead of shared memory
+// (sub-teams of one warp: M = 256 points, 8 per thread -- the reference's default parameter set).
+//
+// Why: the blind rotation is bound by the shared-memory data pipe (128 B/clk/SM), and a third of its bytes are the exchanges
+// between the register passes of the transforms.  Tensor memory has its own data path: a warp that stores its registers with
+// one tcgen05.st shape and loads them back with another gets them TRANSPOSED between lanes, and that traffic runs beside the
+// shared-memory pipe, not on it (tools/tmem_xchg.cu, profiles/r02_tmem_xchg.txt: an exchange of 8 complex doubles per thread
+// costs 777 cycles per 12 warps through shared memory, 276 through tensor memory, 794 for BOTH at once).
+//
+// The primitive (measured lane for lane by tools/tmem_xchg.cu): tcgen05.st.32x32b -- thread = TMEM lane L, its words = columns --
+// followed by tcgen05.ld.16x256b at lane offsets 0 and 16 -- thread t receives lanes t/4 + {0, 8, 16, 24}, columns 2 (t%4) + {0, 1} of
+// every group of 8 columns.  With the 8 complex values of a thread laid out as column 8 (2 part + r2) + 2 (r1 r0) + word
+// (part = re / im, r = register index (r2 r1 r0)) this is the index-bit permutation
+//       writer lane (L4 L3 L2 L1 L0), register (r2 r1 r0)   ->   reader lane (L2 L1 L0 r1 r0), register (L4 L3 r2):
+// two register bits and two lane bits swap places.  The reverse (st.16x256b, ld.32x32b) undoes it.
+//
+// The transform (same butterfly network and twiddles as fft_team.cuh: stage s pairs index bit LOGM-1-s with w(s, j >> (LOGM - s))):
+//   layout A   lane (j4 j3 j2 j1 j0)  regs (j7 j6 j5)   stages 0 1 2  (pass A of fft_team.cuh, twiddles from the constant bank)
+//   swap  ->   lane (j2 j1 j0 j6 j5)  regs (j4 j3 j7)   stages 3 4
+//   swap  ->   lane (j0 j6 j5 j4 j3)  regs (j2 j1 j7)   stages 5 6
+//   swap  ->   lane (j5 j4 j3 j2 j1)  regs (j0 j6 j7)   stage  7      = layout F: the spectral layout of this path
+// (a register renaming between the passes puts the two bits just processed into the (r1 r0) position: free).  The inverse runs
+// the mirror image.  Twiddles: one table entry per thread and pass (the block with all register-borne bits zero); the entries for
+// the register-borne bits follow by squaring (w(s, b) = w(s+1, 2b)^2), by i (the bit processed in the previous stage of the pass)
+// and by fixed roots of unity (bit j7 / j6, which ride along in the registers) -- the error terms are those of derive_pass_tw
+// (at most one squaring and two constant multiplications per entry).
+// Device-only code (tcgen05): not part of the CPU emulation; pinned by the GPU parity tests on both arithmetic paths.
+#pragma once
+#include "fft_team.cuh"
+
+namespace tfhe {
+namespace fft {
+
+// spectral position of index j in layout F: lane (j5 j4 j3 j2 j1), register (j0 j6 j7) -> r * 32 + lane  (slot order of this path)
+__host__ __device__ constexpr uint32_t tmem_slot_of_index(uint32_t j) {
+    const uint32_t lane = (j >> 1) & 31u, r = ((j & 1u) << 2) | (((j >> 6) & 1u) << 1) | ((j >> 7) & 1u);
+    return r * 32u + lane;
+}
+
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// tcgen05.ld is asynchronous: its destination registers may only be read after tcgen05.wait::ld.  The words are passed through the
+// wait as in/out operands so that the compiler cannot schedule a use of them above it.
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&w)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]),
+                   "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15]), "+r"(w[16]), "+r"(w[17]), "+r"(w[18]), "+r"(w[19]), "+r"(w[20]), "+r"(w[21]), "+r"(w[22]),
+                   "+r"(w[23]), "+r"(w[24]), "+r"(w[25]), "+r"(w[26]), "+r"(w[27]), "+r"(w[28]), "+r"(w[29]), "+r"(w[30]), "+r"(w[31])
+                 :
+                 : "memory");
+}
+
+// stores of the swap: all 32 words of the thread, column 8 (2 part + r2) + 2 (r1 r0) + word
+__device__ __forceinline__ void tmem_swap2_store(const cplx (&x)[8], uint32_t taddr) {
+    uint32_t v[32];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int c = 8 * (r >> 2) + 2 * (r & 3);
+        v[c] = (uint32_t)__double2loint(x[r].re);
+        v[c + 1] = (uint32_t)__double2hiint(x[r].re);
+        v[16 + c] = (uint32_t)__double2loint(x[r].im);
+        v[16 + c + 1] = (uint32_t)__double2hiint(x[r].im);
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+// loads of the swap: new register (L4 L3 r2) <- lane half h = L4, row + 8 = L3, column group parity = r2
+__device__ __forceinline__ void tmem_swap2_load(cplx (&x)[8], uint32_t taddr) {
+    uint32_t w[32];
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int o = 4 * (4 * h + g);
+            asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(w[o]), "=r"(w[o + 1]), "=r"(w[o + 2]), "=r"(w[o + 3])
+                         : "r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(8 * g))
+                         : "memory");
+        }
+    tmem_wait_ld(w);
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int o = 4 * (4 * h + g), r0 = (h << 2) | (g & 1), r1 = r0 | 2;
+            if (g < 2) {
+                x[r0].re = __hiloint2double((int)w[o + 1], (int)w[o]);
+                x[r1].re = __hiloint2double((int)w[o + 3], (int)w[o + 2]);
+            } else {
+                x[r0].im = __hiloint2double((int)w[o + 1], (int)w[o]);
+                x[r1].im = __hiloint2double((int)w[o + 3], (int)w[o + 2]);
+            }
+        }
+}
+// the reverse direction: registers (c2 c1 c0) = (L4 L3 r2) go back to lane (L4 L3 ...), register (r2 r1 r0)
+__device__ __forceinline__ void tmem_unswap2_store(const cplx (&x)[8], uint32_t taddr) {
+#pragma unroll
+    for (int h = 0; h < 2; h++)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int r0 = (h << 2) | (g & 1), r1 = r0 | 2;
+            const double d0 = g < 2 ? x[r0].re : x[r0].im, d1 = g < 2 ? x[r1].re : x[r1].im;
+            asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(8 * g)),
+                         "r"((uint32_t)__double2loint(d0)), "r"((uint32_t)__double2hiint(d0)), "r"((uint32_t)__double2loint(d1)), "r"((uint32_t)__double2hiint(d1))
+                         : "memory");
+        }
+}
+__device__ __forceinline__ void tmem_unswap2_load(cplx (&x)[8], uint32_t taddr) {
+    uint32_t v[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+        "%26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+          "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    tmem_wait_ld(v);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int c = 8 * (r >> 2) + 2 * (r & 3);
+        x[r].re = __hiloint2double((int)v[c + 1], (int)v[c]);
+        x[r].im = __hiloint2double((int)v[16 + c + 1], (int)v[16 + c]);
+    }
+}
+// whole swaps (store, wait, load, wait)
+__device__ __forceinline__ void tmem_swap2(cplx (&x)[8], uint32_t taddr) {
+    tmem_swap2_store(x, taddr);
+    tmem_wait_st();
+    tmem_swap2_load(x, taddr);
+}
+__device__ __forceinline__ void tmem_unswap2(cplx (&x)[8], uint32_t taddr) {
+    tmem_unswap2_store(x, taddr);
+    tmem_wait_st();
+    tmem_unswap2_load(x, taddr);
+}
+
+// fixed roots of unity exp(2 pi i / 2^k)
+template <int K> struct RootOfUnity;
+template <> struct RootOfUnity<4> { static constexpr double c = 0.92387953251128675613, s = 0.38268343236508977173; };   // 2 pi / 16
+template <> struct RootOfUnity<5> { static constexpr double c = 0.98078528040323044913, s = 0.19509032201612826785; };   // 2 pi / 32
+template <> struct RootOfUnity<6> { static constexpr double c = 0.99518472667219688624, s = 0.09801714032956060199; };   // 2 pi / 64
+template <> struct RootOfUnity<7> { static constexpr double c = 0.99879545620517239271, s = 0.04906767432741801426; };   // 2 pi / 128
+template <> struct RootOfUnity<8> { static constexpr double c = 0.99969881869620422012, s = 0.02454122852291228803; };   // 2 pi / 256
+
+// twiddles of a two-stage pass on registers (b_hi b_lo j7): stage s on b_hi with w(s, (j7 | lane bits)), stage s+1 on b_lo with
+// w(s+1, (j7 | lane bits | b_hi)).  wb = w(s+1, block with j7 = 0, b_hi = 0) from the table; KA / KB: the root of unity that bit j7
+// contributes at stage s / s+1 (exp(2 pi i / 2^(s+1)), exp(2 pi i / 2^(s+2)))
+template <int KA, int KB>
+struct TwoStageTw {
+    cplx wa[2];      // [j7]
+    cplx wb[2][2];   // [j7][b_hi]
+    __device__ __forceinline__ explicit TwoStageTw(const cplx base) {
+        wb[0][0] = base;
+        wb[0][1] = cmul_i(base);                                                   // the block's low bit is the bit of the previous stage: times zeta^M = i
+        wb[1][0] = cmul_c(base, RootOfUnity<KB>::c, RootOfUnity<KB>::s);
+        wb[1][1] = cmul_i(wb[1][0]);
+        wa[0] = csq(base);                                                          // w(s, b) = w(s+1, 2b)^2
+        wa[1] = cmul_c(wa[0], RootOfUnity<KA>::c, RootOfUnity<KA>::s);
+    }
+};
+// forward: registers r = (b_hi b_lo j7)
+template <int KA, int KB>
+__device__ __forceinline__ void fwd_two_stages(cplx (&x)[8], const cplx base) {
+    const TwoStageTw<KA, KB> tw(base);
+#pragma unroll
+    for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], tw.wa[r & 1]);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        if ((r & 2) == 0) ct_bfly(x[r], x[r + 2], tw.wb[r & 1][(r >> 2) & 1]);
+}
+template <int KA, int KB>
+__device__ __forceinline__ void inv_two_stages(cplx (&x)[8], const cplx base) {
+    const TwoStageTw<KA, KB> tw(base);
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+        if ((r & 2) == 0) gs_bfly(x[r], x[r + 2], tw.wb[r & 1][(r >> 2) & 1]);
+#pragma unroll
+    for (int r = 0; r < 4; r++) gs_bfly(x[r], x[r + 4], tw.wa[r & 1]);
+}
+// last stage: registers r = (j0 j6 j7), twiddle w(7, (j7 j6 | lane bits)) = base * root256^j7 * root128^j6
+struct LastStageTw {
+    cplx w[2][2];   // [j7][j6]
+    __device__ __forceinline__ explicit LastStageTw(const cplx base) {
+        w[0][0] = base;
+        w[1][0] = cmul_c(base, RootOfUnity<8>::c, RootOfUnity<8>::s);
+        w[0][1] = cmul_c(base, RootOfUnity<7>::c, RootOfUnity<7>::s);
+        w[1][1] = cmul_c(w[1][0], RootOfUnity<7>::c, RootOfUnity<7>::s);
+    }
+};
+// register renaming between the passes: (b_hi b_lo j7) -> (j7 b_hi b_lo), so that the two bits just processed leave with the swap
+__device__ __forceinline__ void rename_out(cplx (&x)[8]) {
+    cplx y[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) y[((r & 1) << 2) | (r >> 1)] = x[r];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = y[r];
+}
+__device__ __forceinline__ void rename_in(cplx (&x)[8]) {   // the inverse renaming: (j7 b_hi b_lo) -> (b_hi b_lo j7)
+    cplx y[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) y[((r & 3) << 1) | (r >> 2)] = x[r];
+#pragma unroll
+    for (int r = 0; r < 8; r++) x[r] = y[r];
+}
+
+// per-thread table entries (host_tables_fft.hpp build_fft_tmem_table): [0..3] w(4, (0 j6 j5 0)) by lane & 3,
+// [4..19] w(6, (0 j6 j5 j4 j3 0)) by lane & 15, [20..51] w(7, (0 0 j5 j4 j3 j2 j1)) by lane
+struct TmemTw {
+    cplx p2, p3, p4;
+};
+__device__ __forceinline__ TmemTw load_tmem_tw(const cplx *table, uint32_t lane) {
+    TmemTw t;
+    t.p2 = table[lane & 3u];
+    t.p3 = table[4u + (lane & 15u)];
+    t.p4 = table[20u + lane];
+    return t;
+}
+// forward transform after pass A (x in layout A: registers (j7 j6 j5), stages 0..2 done) -> layout F
+__device__ __forceinline__ void tmem_fwd_rest(cplx (&x)[8], uint32_t taddr, const TmemTw &tw) {
+    tmem_swap2(x, taddr);                 // j7 stays, (j6 j5) leave: regs (j4 j3 j7)
+    fwd_two_stages<4, 5>(x, tw.p2);       // stages 3, 4
+    rename_out(x);                        // (j7 j4 j3)
+    tmem_swap2(x, taddr);                 // regs (j2 j1 j7)
+    fwd_two_stages<6, 7>(x, tw.p3);       // stages 5, 6
+    rename_out(x);                        // (j7 j2 j1)
+    tmem_swap2(x, taddr);                 // regs (j0 j6 j7)
+    const LastStageTw l(tw.p4);
+#pragma unroll
+    for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], l.w[r & 1][(r >> 1) & 1]);   // stage 7
+}
+// inverse of two accumulators (the low- and high-limb products of a column) from layout F back to layout A (stages 7..3 undone;
+// the caller finishes with the inverse of pass A); the two use disjoint column ranges so that their transfers overlap
+__device__ __forceinline__ void tmem_unswap2_pair(cplx (&a)[8], cplx (&b)[8], uint32_t taddr) {
+    tmem_unswap2_store(a, taddr);
+    tmem_unswap2_store(b, taddr + 32u);
+    tmem_wait_st();
+    tmem_unswap2_load(a, taddr);
+    tmem_unswap2_load(b, taddr + 32u);
+}
+__device__ __forceinline__ void tmem_inv_rest(cplx (&a)[8], cplx (&b)[8], uint32_t taddr, const TmemTw &tw) {
+    {
+        const LastStageTw l(tw.p4);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            gs_bfly(a[r], a[r + 4], l.w[r & 1][(r >> 1) & 1]);
+            gs_bfly(b[r], b[r + 4], l.w[r & 1][(r >> 1) & 1]);
+        }
+    }
+    tmem_unswap2_pair(a, b, taddr);       // regs (j7 j2 j1)
+    rename_in(a); rename_in(b);           // (j2 j1 j7)
+    inv_two_stages<6, 7>(a, tw.p3);
+    inv_two_stages<6, 7>(b, tw.p3);
+    tmem_unswap2_pair(a, b, taddr);       // regs (j7 j4 j3)
+    rename_in(a); rename_in(b);           // (j4 j3 j7)
+    inv_two_stages<4, 5>(a, tw.p2);
+    inv_two_stages<4, 5>(b, tw.p2);
+    tmem_unswap2_pair(a, b, taddr);       // regs (j7 j6 j5): layout A
+}
+
+// ---- rows published through tensor memory.  With team = lane quarter (warp % 4) the P sub-teams (warps) of a ciphertext share
+// their 32 lanes, and the multiply-accumulate is pointwise: thread t of every sub-team needs exactly the points thread t of the
+// publishing sub-team holds.  A transformed digit row is therefore published with one store of the thread's 8 points into the
+// publisher's columns (column 4 e + {re lo, re hi, im lo, im hi}) and fetched by the peers with one load of the same lane.
+__device__ __forceinline__ void tmem_store_row(const cplx (&x)[8], uint32_t taddr) {
+    uint32_t v[32];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        v[4 * e] = (uint32_t)__double2loint(x[e].re);
+        v[4 * e + 1] = (uint32_t)__double2hiint(x[e].re);
+        v[4 * e + 2] = (uint32_t)__double2loint(x[e].im);
+        v[4 * e + 3] = (uint32_t)__double2hiint(x[e].im);
+    }
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),
+        "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+    tmem_wait_st();
+}
+__device__ __forceinline__ void tmem_load_row(cplx (&x)[8], uint32_t taddr) {
+    uint32_t v[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+        "%26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]),
+          "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    tmem_wait_ld(v);
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        x[e].re = __hiloint2double((int)v[4 * e + 1], (int)v[4 * e]);
+        x[e].im = __hiloint2double((int)v[4 * e + 3], (int)v[4 * e + 2]);
+    }
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tensor-memory columns of a sub-team (warp): [0, 64) exchanges of the transforms (32 per limb for the paired inverse),
+// [64, 96) and [96, 128) the published row, double buffered by level parity
+constexpr uint32_t TMEM_SUB_COLS = 128, TMEM_PUB_COL = 64;
+
+}  // namespace fft
+}  // namespace tfhe

@@ -42,5 +42,14 @@ inline void build_fft_tables(int logm, int loge, HostFftTw &out) {
             for (uint32_t t = 0; t < (uint32_t)T; t++) out.C.push_back(fft_twiddle(logm, loge + qb + u, (t << u) | m));
 }
 
+// per-lane entries of the tensor-memory-exchange passes (fft_tmem.cuh TmemTw), M = 256: the twiddle of the LAST stage of each
+// pass for the block whose register-borne bits are zero
+inline void build_fft_tmem_table(std::vector<cplx> &out) {
+    out.clear();
+    for (uint32_t i = 0; i < 4; i++) out.push_back(fft_twiddle(8, 4, i << 1));     // w(4, (0 j6 j5 0)),         lane & 3  = (j6 j5)
+    for (uint32_t i = 0; i < 16; i++) out.push_back(fft_twiddle(8, 6, i << 1));    // w(6, (0 j6 j5 j4 j3 0)),   lane & 15 = (j6 j5 j4 j3)
+    for (uint32_t i = 0; i < 32; i++) out.push_back(fft_twiddle(8, 7, i));         // w(7, (0 0 j5 j4 j3 j2 j1)), lane      = (j5 j4 j3 j2 j1)
+}
+
 }  // namespace fft
 }  // namespace tfhe

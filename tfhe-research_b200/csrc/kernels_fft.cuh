@@ -13,6 +13,7 @@
 // Reference: bootstrapping.rs:58-105 (blind rotation), ggsw.rs:132-178 (external product, cmux).
 #pragma once
 #include "fft_team.cuh"
+#include "fft_tmem.cuh"
 #include "kernels.cuh"
 
 namespace tfhe {
@@ -97,7 +98,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     using C = typename K::F;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint32_t team = tid / K::TEAM_THREADS, tt = tid % K::TEAM_THREADS, sub = tt / K::T, t = tt % K::T;
+    // tensor-memory exchanges: a warp reaches only the 32 lanes of its quarter (warp % 4), and the sub-teams of a ciphertext publish
+    // their rows to each other through those lanes -- so team = lane quarter, sub-team = warp / 4
+    const uint32_t team = K::XCHG ? (tid >> 5) & 3u : tid / K::TEAM_THREADS, sub = K::XCHG ? tid >> 7 : (tid % K::TEAM_THREADS) / K::T;
+    const uint32_t t = K::XCHG ? lane : tid % K::T, tt = sub * K::T + t;
     const uint32_t team_bytes = (uint32_t)K::team_bytes((int)a.n);
     uint8_t *ring = smem + K::CTS * team_bytes;
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
@@ -130,9 +134,37 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // tensor-memory exchanges (fft_tmem.cuh): warp 0 allocates all 512 columns (one CTA per SM) -- every warp owns 128 columns
+    // (warp / 4) of its 32 lanes (warp % 4): 64 for the exchanges of its transforms, 2 x 32 for the rows it publishes
+    uint32_t *tmem_ptr = claimed + K::NSLOT;
+    if constexpr (K::XCHG) {
+        static_assert(K::P * TMEM_SUB_COLS <= 512, "tensor-memory columns");
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
     __syncthreads();   // the only CTA-wide barrier: teams are independent below
+    uint32_t taddr = 0, tquarter = 0, pubsel = 0;   // own columns / first column of the team's lanes / publish buffer of the next level
+    TmemTw twx = {};
+    if constexpr (K::XCHG) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tquarter = *tmem_ptr + ((team * 32u) << 16);
+        taddr = tquarter + sub * TMEM_SUB_COLS;
+        twx = load_tmem_tw(a.tw.twX, lane);
+    }
 
-    if (team >= active) return;
+    if (team >= active) {
+        if constexpr (K::XCHG) {   // warp 0 releases tensor memory once every warp has arrived here or at the end of the kernel
+            if (active == 0) {
+                if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_ptr) : "memory");
+            } else {
+                asm volatile("bar.arrive 15, %0;" ::"n"(K::THREADS) : "memory");
+            }
+        }
+        return;
+    }
     const uint32_t ct = ct0 + team;
     uint8_t *tm = smem + team * team_bytes;
     uint32_t *acc = reinterpret_cast<uint32_t *>(tm + K::TM_ACC);
@@ -294,7 +326,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 mbar_wait(full + s, (ir / K::NSLOT) & 1u, a.err_flag);
                 const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
                 const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
-                phase_mac<K, OWN>(R, t, sub, slot, peer, 0u);
+                if constexpr (K::XCHG && !OWN) tmem_load_row(R.x, tquarter + p * TMEM_SUB_COLS + TMEM_PUB_COL + 32u * pubsel);   // the peer's row: same lane, its columns
+                phase_mac<K, OWN || K::XCHG>(R, t, sub, slot, peer, 0u);
                 __syncwarp();
                 if (lane == 0) release_slot(ir);
             };
@@ -308,12 +341,28 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #else
                 phase_F1a<K>(R, t, sub, lev, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
-                if (!FIRST) team_bar_id(team_bar, K::TEAM_THREADS);   // the row published at the previous level has been read
-                store_A<C>(R.x, buf0, t);
-                sub_sync();
-                phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
-                sub_sync();
-                phase_F3v<K>(R, t, twC_base, buf1);
+                if constexpr (K::XCHG) {
+                    tmem_fwd_rest(R.x, taddr, twx);          // the other passes, exchanged through tensor memory: layout F
+                    // published in tensor memory, double buffered: the buffer written here was last read two levels ago, and
+                    // every peer finished that level before it arrived at the barrier of the level between
+                    tmem_store_row(R.x, taddr + TMEM_PUB_COL + 32u * pubsel);
+                    mac_slot(std::true_type{}, 0u);
+                    tmem_fence_before_sync();
+                    team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
+                    tmem_fence_after_sync();
+#pragma unroll 1
+                    for (uint32_t d = 1; d < (uint32_t)K::P; d++) mac_slot(std::false_type{}, d);
+                    it += (uint32_t)K::P;
+                    pubsel ^= 1u;
+                    return;
+                } else {
+                    if (!FIRST) team_bar_id(team_bar, K::TEAM_THREADS);   // the row published at the previous level has been read
+                    store_A<C>(R.x, buf0, t);
+                    sub_sync();
+                    phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
+                    sub_sync();
+                    phase_F3v<K>(R, t, twC_base, buf1);
+                }
                 phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
                 mac_slot(std::true_type{}, 0u);
                 team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
@@ -329,7 +378,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #pragma unroll 1
             for (uint32_t lev = 0; lev < (uint32_t)K::L; lev++) level(std::false_type{}, lev);
 #endif
-            team_bar_id(team_bar, K::TEAM_THREADS);      // the last published rows have been read: buf0 may be overwritten
+            if constexpr (!K::XCHG) team_bar_id(team_bar, K::TEAM_THREADS);      // the last published rows have been read: buf0 may be overwritten
         } else {
             auto level = [&](auto first_c, uint32_t lev) {
                 constexpr bool FIRST = decltype(first_c)::value;
@@ -418,7 +467,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             sub_sync();
             phase_K3_hi<K>(R, t, a.tw.twA, buf0, lo, acc + sub * K::N, maxfrac);
         } else {
-            if constexpr (OWN_FIRST) {
+            if constexpr (K::XCHG) {
+                tmem_inv_rest(R.acc[0], R.acc[1], taddr, twx);   // stages 7..3 of both limbs, exchanged through tensor memory: layout A
+            } else if constexpr (OWN_FIRST) {
                 phase_J1v<K>(R, t, twC_base, buf0, buf1);
                 sub_sync();
                 phase_J2av<K>(R, jbB, twB_base, buf0, buf1);
@@ -428,11 +479,15 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 phase_J2a<K>(R, jbB, twB, buf0, buf1);
                 if constexpr (!SELF_REFILL) { if (producer) pump(0, it); }   // ring entries freed by slower teams: refill them while this team inverts
             }
-            sub_sync();
-            phase_J2b<K>(R, jbB, buf0, buf1);
-            sub_sync();
-            if constexpr (ACC_REG) phase_J3r<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, accv, maxfrac);
-            else phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
+            if constexpr (K::XCHG) {
+                phase_J3r_regs<K>(R, t, a.tw.twA, acc + sub * K::N, accv, maxfrac);
+            } else {
+                sub_sync();
+                phase_J2b<K>(R, jbB, buf0, buf1);
+                sub_sync();
+                if constexpr (ACC_REG) phase_J3r<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, accv, maxfrac);
+                else phase_J3<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, maxfrac);
+            }
         }
 #endif
         sub_sync();   // acc[sub] (read only by this sub-team) is up to date before the next step's digits
@@ -444,6 +499,24 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         for (int o = 16; o > 0; o >>= 1) maxfrac = fmax(maxfrac, __shfl_xor_sync(0xFFFFFFFFu, maxfrac, o));
         if (lane == 0) atomicMax(a.margin, (unsigned long long)__double_as_longlong(maxfrac));
     }
+    if constexpr (K::XCHG) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 15, %0;" ::"n"(K::THREADS) : "memory");   // every warp of the CTA (idle teams arrive before they exit)
+        if (tid < 32) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_ptr) : "memory");
+        }
+    }
+}
+
+// the key of the tensor-memory-exchange path: the same numbers as the shared-memory path's key, every polynomial re-ordered from
+// slot order (point (t << 3) | e at e * 32 + t) to the spectral layout F of fft_tmem.cuh.  grid = polynomials (M points each).
+__global__ void bsk_fft_reslot_kernel(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
+    const size_t poly = blockIdx.x;
+    if (poly >= polys) return;
+    const uint32_t idx = threadIdx.x;                    // position in slot order: e * 32 + t
+    const uint32_t j = ((idx & 31u) << 3) | (idx >> 5);   // the point it holds
+    out[poly * 256 + tmem_slot_of_index(j)] = in[poly * 256 + idx];
 }
 
 // ------------------------------------------------------------------------------------------ key transform

@@ -48,7 +48,8 @@ struct tfhe_ctx {
     bool fft_check = false;                 // FFT path: run the kernel variant that records the rounding margin
     int ks_path = TFHE_KS_TCGEN05;          // arithmetic of the key-switching product: TFHE_KS_IMAD / TFHE_KS_MMA (mma.sync) / TFHE_KS_TCGEN05 (tcgen05.mma + TMEM + TMA)
     int latency_cfg = 4;                    // FFT path, small batches: 0 throughput kernel, 1 one team + deep key ring, 2 all teams of a CTA on one ciphertext, 3 a cluster of L CTAs per ciphertext, 4 the same with every CTA split by key limb (then 2, then 0 as the batch grows)
-    fft::cplx *d_ftw[3] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP)
+    fft::cplx *d_ftw[4] = {};                // FFT pass-B / pass-C twiddle tables, zeta^m table (BMMP), per-lane table of the tensor-memory exchanges
+    bool fft_tmem = true;                    // FFT path, N = 512: exchange the register passes of the transforms through tensor memory (fft_tmem.cuh)
     fft::TwTablesF ftw;
     unsigned long long *d_margin = nullptr;  // FFT path: largest distance to an integer seen before rounding
     std::string err;
@@ -77,6 +78,7 @@ struct tfhe_bk {
     bool bmmp = false;              // key triples of the unrolled-by-two blind rotation (FFT path only)
     uint32_t *d_bsk_ntt = nullptr;  // [n][2][ROWS][P][N]                      (TFHE_PATH_NTT)
     fft::cplx *d_bsk_fft = nullptr; // [n][ROWS][2 limbs][P][N/2], scaled 2/N  (TFHE_PATH_FFT)
+    fft::cplx *d_bsk_fft_x = nullptr; // the same key, every polynomial in the spectral order of the tensor-memory-exchange kernel (N = 512)
     uint32_t *d_ksk = nullptr;      // [kN*l_ks][ksk_stride], ksk_stride = n+1 rounded up to 128 words, zero padded
     uint8_t *d_ksk_t = nullptr;     // [ksk_stride*4][kN*l_ks] byte planes, k contiguous (ks_mma_kernel, ks_tcgen05_kernel); null if not applicable
     CUtensorMap map_kskt;           // TMA descriptor of d_ksk_t (ks_tcgen05_kernel)
@@ -188,8 +190,13 @@ using KF1C = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, true
 #ifndef TFHE_FFT_CTS_P0
 #define TFHE_FFT_CTS_P0 4
 #endif
+#ifndef TFHE_FFT_TMEM_NSLOT
+#define TFHE_FFT_TMEM_NSLOT 6   // the shared memory the exchange buffers no longer need holds a deeper key ring
+#endif
 using KF0 = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, false>;    // reference defaults (lib.rs:101-123)
 using KF0C = fft::FftPbsCfg<9, 3, 2, 6, 4, TFHE_FFT_CTS_P0, true>;
+using KF0T = fft::FftPbsCfg<9, 3, 2, 6, 4, 4, false, false, 1, TFHE_FFT_TMEM_NSLOT, 1>;   // register passes exchanged through tensor memory
+using KF0TC = fft::FftPbsCfg<9, 3, 2, 6, 4, 4, true, false, 1, TFHE_FFT_TMEM_NSLOT, 1>;
 #ifndef TFHE_FFT_CTS_P2
 #define TFHE_FFT_CTS_P2 2
 #endif
@@ -412,7 +419,10 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
             }
         }
         switch (ctx->pbs_id) {
-        case 0: return ctx->fft_check ? launch_pbs_fft_t<KF0C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0>(ctx, a, bk->d_bsk_fft);
+        case 0:
+            if (a.mode == 0 && bk->d_bsk_fft_x && ctx->fft_tmem)
+                return ctx->fft_check ? launch_pbs_fft_t<KF0TC>(ctx, a, bk->d_bsk_fft_x) : launch_pbs_fft_t<KF0T>(ctx, a, bk->d_bsk_fft_x);
+            return ctx->fft_check ? launch_pbs_fft_t<KF0C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0>(ctx, a, bk->d_bsk_fft);
         case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
         case 2: return ctx->fft_check ? launch_pbs_fft_t<KF2C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF2>(ctx, a, bk->d_bsk_fft);
         }
@@ -672,8 +682,11 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         fft::HostFftTw ft;
         fft::build_fft_tables(logm, floge, ft);
         for (size_t i = 0; i < ft.A.size(); i++) ctx->ftw.twA[i] = ft.A[i];
-        const std::vector<fft::cplx> *fsrc[3] = {&ft.B, &ft.C, &ft.Z};
-        for (int i = 0; i < 3; i++) {
+        std::vector<fft::cplx> fx;
+        if (logm == 8) fft::build_fft_tmem_table(fx);
+        const std::vector<fft::cplx> *fsrc[4] = {&ft.B, &ft.C, &ft.Z, &fx};
+        for (int i = 0; i < 4; i++) {
+            if (fsrc[i]->empty()) continue;
             if (cudaMalloc(&ctx->d_ftw[i], fsrc[i]->size() * sizeof(fft::cplx)) != cudaSuccess) return bail("cudaMalloc");
             if (cudaMemcpy(ctx->d_ftw[i], fsrc[i]->data(), fsrc[i]->size() * sizeof(fft::cplx), cudaMemcpyHostToDevice) != cudaSuccess)
                 return bail("cudaMemcpy");
@@ -681,10 +694,12 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         ctx->ftw.twB = ctx->d_ftw[0];
         ctx->ftw.twC = ctx->d_ftw[1];
         ctx->ftw.ztab = ctx->d_ftw[2];
+        ctx->ftw.twX = ctx->d_ftw[3];
         if (cudaMalloc(&ctx->d_margin, 8) != cudaSuccess || cudaMemset(ctx->d_margin, 0, 8) != cudaSuccess) return bail("cudaMalloc");
         ctx->path = TFHE_DEFAULT_PATH;
     }
     if (const char *e = getenv("TFHE_B200_FFT_CHECK")) ctx->fft_check = atoi(e) != 0;
+    if (const char *e = getenv("TFHE_B200_FFT_TMEM")) ctx->fft_tmem = atoi(e) != 0;
     if (const char *e = getenv("TFHE_B200_KS")) ctx->ks_path = !strcmp(e, "imad") ? TFHE_KS_IMAD : !strcmp(e, "tcgen05") ? TFHE_KS_TCGEN05 : TFHE_KS_MMA;
     if (const char *e = getenv("TFHE_B200_LATENCY_CFG")) { const int v = atoi(e); if (v >= 0 && v <= 4) ctx->latency_cfg = v; }
     if (const char *e = getenv("TFHE_B200_PBS_PATH")) {
@@ -706,7 +721,7 @@ void tfhe_ctx_destroy(tfhe_ctx *ctx) {
         for (int i = 0; i < 4; i++)
             if (ctx->d_tw[pr][i]) cudaFree(ctx->d_tw[pr][i]);
     if (ctx->d_err) cudaFree(ctx->d_err);
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 4; i++)
         if (ctx->d_ftw[i]) cudaFree(ctx->d_ftw[i]);
     if (ctx->d_margin) cudaFree(ctx->d_margin);
     for (auto &e : ctx->ev)
@@ -747,6 +762,11 @@ int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int on) {
     if (!ctx) return TFHE_E_PARAM;
     if (on < 0 || on > 4) return fail(ctx, TFHE_E_PARAM, "latency configuration: 0 .. 4");
     ctx->latency_cfg = on;
+    return TFHE_OK;
+}
+int tfhe_ctx_set_fft_exchange(tfhe_ctx *ctx, int tensor_memory) {
+    if (!ctx) return TFHE_E_PARAM;
+    ctx->fft_tmem = tensor_memory != 0;
     return TFHE_OK;
 }
 int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on) {
@@ -796,8 +816,18 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     e = copy_ksk(ctx, bk, ksk);
     int rc;
     if (e != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
-    else if (bk->path == TFHE_PATH_FFT) rc = launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, ctx->n(), 1);
-    else rc = launch_transform(ctx, raw_dev, bk->d_bsk_ntt, ctx->n());
+    else if (bk->path == TFHE_PATH_FFT) {
+        rc = launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, ctx->n(), 1);
+        if (rc == TFHE_OK && ctx->pbs_id == 0 && ctx->fft_tmem) {   // second copy in the order of the tensor-memory-exchange kernel
+            if ((e = cudaMalloc(&bk->d_bsk_fft_x, fft_key_bytes(ctx))) != cudaSuccess) rc = fail(ctx, TFHE_E_OOM, cudaGetErrorString(e));
+            else {
+                const size_t polys = fft_key_bytes(ctx) / (256 * sizeof(fft::cplx));
+                fft::bsk_fft_reslot_kernel<<<(unsigned)polys, 256, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, polys);
+                ctx->launches++;
+                if ((e = cudaGetLastError()) != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
+            }
+        }
+    } else rc = launch_transform(ctx, raw_dev, bk->d_bsk_ntt, ctx->n());
     cudaError_t es = cudaStreamSynchronize(ctx->stream);
     if (d_raw) cudaFree(d_raw);
     if (rc == TFHE_OK && es != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(es));
@@ -857,6 +887,7 @@ void tfhe_bk_free(tfhe_bk *bk) {
     cudaSetDevice(bk->device);
     if (bk->d_bsk_ntt) cudaFree(bk->d_bsk_ntt);
     if (bk->d_bsk_fft) cudaFree(bk->d_bsk_fft);
+    if (bk->d_bsk_fft_x) cudaFree(bk->d_bsk_fft_x);
     if (bk->d_ksk) cudaFree(bk->d_ksk);
     if (bk->d_ksk_t) cudaFree(bk->d_ksk_t);
     delete bk;
