@@ -25,7 +25,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-ldl"]
 _SOURCES = ["tfhe_b200.cu", "host_api.cpp", "tfhe_mgpu.cpp"]
 _DEPS = _SOURCES + ["kernels.cuh", "pbs_team.cuh", "tfhe_core.cuh", "host_tables.hpp", "api_internal.hpp",
-                    "kernels_fft.cuh", "kernels_fft_latency.cuh", "kernels_fft_cluster.cuh", "kernels_ks_tcgen05.cuh", "fft_team.cuh", "host_tables_fft.hpp", "tfhe_mgpu.cpp",
+                    "kernels_fft.cuh", "kernels_fft_latency.cuh", "kernels_fft_cluster.cuh", "kernels_ks_tcgen05.cuh", "fft_team.cuh", "fft_tmem.cuh", "host_tables_fft.hpp", "tfhe_mgpu.cpp",
                     os.path.join("..", "..", "include", "tfhe_b200.h")]
 
 TFHE_OK, TFHE_E_PARAM, TFHE_E_CUDA, TFHE_E_OOM, TFHE_E_ASSERT, TFHE_E_NCCL = 0, -1, -2, -3, -4, -5

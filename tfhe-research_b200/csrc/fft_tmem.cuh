@@ -28,6 +28,24 @@
 #pragma once
 #include "fft_team.cuh"
 
+// measured choices (tools/gpu_call8.sh, P0 batch 4096): the swap stores as 4 x tcgen05.st.x8 (fewer register moves than one x32:
+// 102.95 -> 99.49 ms), 16x256b loads / stores as .x4 (104.26 -> 102.18 ms), a peer's row requested before the wait for the key slot
+#ifndef TFHE_TMEM_ST8
+#define TFHE_TMEM_ST8 1
+#endif
+#ifndef TFHE_TMEM_PUB8
+#define TFHE_TMEM_PUB8 0
+#endif
+#ifndef TFHE_TMEM_ROWLD8
+#define TFHE_TMEM_ROWLD8 0
+#endif
+#ifndef TFHE_TMEM_LOADFIRST
+#define TFHE_TMEM_LOADFIRST 1
+#endif
+#ifndef TFHE_TMEM_X4
+#define TFHE_TMEM_X4 1
+#endif
+
 namespace tfhe {
 namespace fft {
 
@@ -60,6 +78,13 @@ __device__ __forceinline__ void tmem_swap2_store(const cplx (&x)[8], uint32_t ta
         v[16 + c] = (uint32_t)__double2loint(x[r].im);
         v[16 + c + 1] = (uint32_t)__double2hiint(x[r].im);
     }
+#if TFHE_TMEM_ST8
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + 8u * q), "r"(v[8 * q]), "r"(v[8 * q + 1]), "r"(v[8 * q + 2]),
+                     "r"(v[8 * q + 3]), "r"(v[8 * q + 4]), "r"(v[8 * q + 5]), "r"(v[8 * q + 6]), "r"(v[8 * q + 7])
+                     : "memory");
+#else
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
         "%25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
@@ -67,12 +92,22 @@ __device__ __forceinline__ void tmem_swap2_store(const cplx (&x)[8], uint32_t ta
         "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
+#endif
 }
-// loads of the swap: new register (L4 L3 r2) <- lane half h = L4, row + 8 = L3, column group parity = r2
+// loads of the swap: new register (L4 L3 r2) <- lane half h = L4, row + 8 = L3, column group parity = r2.
+// One 16x256b.x4 per lane half: repetition g reads column group g (8 columns), 4 words each (rows t/4 and t/4 + 8).
 __device__ __forceinline__ void tmem_swap2_load(cplx (&x)[8], uint32_t taddr) {
     uint32_t w[32];
 #pragma unroll
-    for (int h = 0; h < 2; h++)
+    for (int h = 0; h < 2; h++) {
+#if TFHE_TMEM_X4
+        const int o = 16 * h;
+        asm volatile("tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(w[o]), "=r"(w[o + 1]), "=r"(w[o + 2]), "=r"(w[o + 3]), "=r"(w[o + 4]), "=r"(w[o + 5]), "=r"(w[o + 6]), "=r"(w[o + 7]), "=r"(w[o + 8]),
+                       "=r"(w[o + 9]), "=r"(w[o + 10]), "=r"(w[o + 11]), "=r"(w[o + 12]), "=r"(w[o + 13]), "=r"(w[o + 14]), "=r"(w[o + 15])
+                     : "r"(taddr + ((uint32_t)(16 * h) << 16))
+                     : "memory");
+#else
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             const int o = 4 * (4 * h + g);
@@ -81,6 +116,8 @@ __device__ __forceinline__ void tmem_swap2_load(cplx (&x)[8], uint32_t taddr) {
                          : "r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(8 * g))
                          : "memory");
         }
+#endif
+    }
     tmem_wait_ld(w);
 #pragma unroll
     for (int h = 0; h < 2; h++)
@@ -99,15 +136,30 @@ __device__ __forceinline__ void tmem_swap2_load(cplx (&x)[8], uint32_t taddr) {
 // the reverse direction: registers (c2 c1 c0) = (L4 L3 r2) go back to lane (L4 L3 ...), register (r2 r1 r0)
 __device__ __forceinline__ void tmem_unswap2_store(const cplx (&x)[8], uint32_t taddr) {
 #pragma unroll
-    for (int h = 0; h < 2; h++)
+    for (int h = 0; h < 2; h++) {
+        uint32_t v[16];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             const int r0 = (h << 2) | (g & 1), r1 = r0 | 2;
             const double d0 = g < 2 ? x[r0].re : x[r0].im, d1 = g < 2 ? x[r1].re : x[r1].im;
-            asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(8 * g)),
-                         "r"((uint32_t)__double2loint(d0)), "r"((uint32_t)__double2hiint(d0)), "r"((uint32_t)__double2loint(d1)), "r"((uint32_t)__double2hiint(d1))
-                         : "memory");
+            v[4 * g] = (uint32_t)__double2loint(d0);
+            v[4 * g + 1] = (uint32_t)__double2hiint(d0);
+            v[4 * g + 2] = (uint32_t)__double2loint(d1);
+            v[4 * g + 3] = (uint32_t)__double2hiint(d1);
         }
+#if TFHE_TMEM_X4
+        asm volatile("tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr + ((uint32_t)(16 * h) << 16)),
+                     "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]),
+                     "r"(v[13]), "r"(v[14]), "r"(v[15])
+                     : "memory");
+#else
+#pragma unroll
+        for (int g = 0; g < 4; g++)
+            asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr + ((uint32_t)(16 * h) << 16) + (uint32_t)(8 * g)), "r"(v[4 * g]),
+                         "r"(v[4 * g + 1]), "r"(v[4 * g + 2]), "r"(v[4 * g + 3])
+                         : "memory");
+#endif
+    }
 }
 __device__ __forceinline__ void tmem_unswap2_load(cplx (&x)[8], uint32_t taddr) {
     uint32_t v[32];
@@ -275,6 +327,13 @@ __device__ __forceinline__ void tmem_store_row(const cplx (&x)[8], uint32_t tadd
         v[4 * e + 2] = (uint32_t)__double2loint(x[e].im);
         v[4 * e + 3] = (uint32_t)__double2hiint(x[e].im);
     }
+#if TFHE_TMEM_PUB8
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + 8u * q), "r"(v[8 * q]), "r"(v[8 * q + 1]), "r"(v[8 * q + 2]),
+                     "r"(v[8 * q + 3]), "r"(v[8 * q + 4]), "r"(v[8 * q + 5]), "r"(v[8 * q + 6]), "r"(v[8 * q + 7])
+                     : "memory");
+#else
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
         "%25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
@@ -282,10 +341,18 @@ __device__ __forceinline__ void tmem_store_row(const cplx (&x)[8], uint32_t tadd
         "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
-    tmem_wait_st();
+#endif   // the caller waits (tmem_wait_st) before it tells its peers
 }
 __device__ __forceinline__ void tmem_load_row(cplx (&x)[8], uint32_t taddr) {
     uint32_t v[32];
+#if TFHE_TMEM_ROWLD8
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[8 * q]), "=r"(v[8 * q + 1]), "=r"(v[8 * q + 2]), "=r"(v[8 * q + 3]), "=r"(v[8 * q + 4]), "=r"(v[8 * q + 5]), "=r"(v[8 * q + 6]), "=r"(v[8 * q + 7])
+                     : "r"(taddr + 8u * q)
+                     : "memory");
+#else
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
         "%26, %27, %28, %29, %30, %31}, [%32];"
@@ -294,6 +361,7 @@ __device__ __forceinline__ void tmem_load_row(cplx (&x)[8], uint32_t taddr) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
+#endif
     tmem_wait_ld(v);
 #pragma unroll
     for (int e = 0; e < 8; e++) {

@@ -323,10 +323,11 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 constexpr bool OWN = decltype(own_c)::value;
                 const uint32_t ir = it + d, s = ir % K::NSLOT, p = (sub + d) % (uint32_t)K::P;
                 if constexpr (!SELF_REFILL) { if (producer) pump(ir + 1, ir); }
+                if constexpr (K::XCHG && !OWN && TFHE_TMEM_LOADFIRST) tmem_load_row(R.x, tquarter + p * TMEM_SUB_COLS + TMEM_PUB_COL + 32u * pubsel);
                 mbar_wait(full + s, (ir / K::NSLOT) & 1u, a.err_flag);
+                if constexpr (K::XCHG && !OWN && !TFHE_TMEM_LOADFIRST) tmem_load_row(R.x, tquarter + p * TMEM_SUB_COLS + TMEM_PUB_COL + 32u * pubsel);   // the peer's row: same lane, its columns
                 const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
                 const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
-                if constexpr (K::XCHG && !OWN) tmem_load_row(R.x, tquarter + p * TMEM_SUB_COLS + TMEM_PUB_COL + 32u * pubsel);   // the peer's row: same lane, its columns
                 phase_mac<K, OWN || K::XCHG>(R, t, sub, slot, peer, 0u);
                 __syncwarp();
                 if (lane == 0) release_slot(ir);
@@ -347,6 +348,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                     // every peer finished that level before it arrived at the barrier of the level between
                     tmem_store_row(R.x, taddr + TMEM_PUB_COL + 32u * pubsel);
                     mac_slot(std::true_type{}, 0u);
+                    tmem_wait_st();                          // the published row has landed
                     tmem_fence_before_sync();
                     team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
                     tmem_fence_after_sync();
