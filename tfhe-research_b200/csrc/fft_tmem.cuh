@@ -214,11 +214,19 @@ struct TwoStageTw {
         wa[0] = csq(base);                                                          // w(s, b) = w(s+1, 2b)^2
         wa[1] = cmul_c(wa[0], RootOfUnity<KA>::c, RootOfUnity<KA>::s);
     }
+    // the same from stored values (d[0] = wb[1][0], d[1] = wa[0], d[2] = wa[1]: what the constructor above computes)
+    __device__ __forceinline__ TwoStageTw(const cplx base, const cplx (&d)[3]) {
+        wb[0][0] = base;
+        wb[0][1] = cmul_i(base);
+        wb[1][0] = d[0];
+        wb[1][1] = cmul_i(d[0]);
+        wa[0] = d[1];
+        wa[1] = d[2];
+    }
 };
 // forward: registers r = (b_hi b_lo j7)
 template <int KA, int KB>
-__device__ __forceinline__ void fwd_two_stages(cplx (&x)[8], const cplx base) {
-    const TwoStageTw<KA, KB> tw(base);
+__device__ __forceinline__ void fwd_two_stages(cplx (&x)[8], const TwoStageTw<KA, KB> &tw) {
 #pragma unroll
     for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], tw.wa[r & 1]);
 #pragma unroll
@@ -226,8 +234,7 @@ __device__ __forceinline__ void fwd_two_stages(cplx (&x)[8], const cplx base) {
         if ((r & 2) == 0) ct_bfly(x[r], x[r + 2], tw.wb[r & 1][(r >> 2) & 1]);
 }
 template <int KA, int KB>
-__device__ __forceinline__ void inv_two_stages(cplx (&x)[8], const cplx base) {
-    const TwoStageTw<KA, KB> tw(base);
+__device__ __forceinline__ void inv_two_stages(cplx (&x)[8], const TwoStageTw<KA, KB> &tw) {
 #pragma unroll
     for (int r = 0; r < 8; r++)
         if ((r & 2) == 0) gs_bfly(x[r], x[r + 2], tw.wb[r & 1][(r >> 2) & 1]);
@@ -242,6 +249,12 @@ struct LastStageTw {
         w[1][0] = cmul_c(base, RootOfUnity<8>::c, RootOfUnity<8>::s);
         w[0][1] = cmul_c(base, RootOfUnity<7>::c, RootOfUnity<7>::s);
         w[1][1] = cmul_c(w[1][0], RootOfUnity<7>::c, RootOfUnity<7>::s);
+    }
+    __device__ __forceinline__ LastStageTw(const cplx base, const cplx (&d)[3]) {   // d = w[1][0], w[0][1], w[1][1] as computed above
+        w[0][0] = base;
+        w[1][0] = d[0];
+        w[0][1] = d[1];
+        w[1][1] = d[2];
     }
 };
 // register renaming between the passes: (b_hi b_lo j7) -> (j7 b_hi b_lo), so that the two bits just processed leave with the swap
@@ -264,24 +277,102 @@ __device__ __forceinline__ void rename_in(cplx (&x)[8]) {   // the inverse renam
 // [4..19] w(6, (0 j6 j5 j4 j3 0)) by lane & 15, [20..51] w(7, (0 0 j5 j4 j3 j2 j1)) by lane
 struct TmemTw {
     cplx p2, p3, p4;
+    uint32_t cols;   // tensor-memory address of this warp's 40 twiddle columns (TFHE_TMEM_TWSTORE)
 };
 __device__ __forceinline__ TmemTw load_tmem_tw(const cplx *table, uint32_t lane) {
     TmemTw t;
     t.p2 = table[lane & 3u];
     t.p3 = table[4u + (lane & 15u)];
     t.p4 = table[20u + lane];
+    t.cols = 0;
     return t;
 }
+// A thread's derived twiddles never change.  They do not fit in registers, but they fit in tensor memory: computed once per kernel,
+// stored in 36 of the warp's columns ([0, 12) pass 2: wb[1][0], wa[0], wa[1]; [12, 24) pass 3; [24, 36) last stage: w[1][0], w[0][1],
+// w[1][1]) and fetched with one tcgen05.ld.x16 per pass instead of 13 / 13 / 12 FP64 operations (the same values: same bits).
+__device__ __forceinline__ void tmem_store_cplx(uint32_t taddr, const cplx v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"((uint32_t)__double2loint(v.re)), "r"((uint32_t)__double2hiint(v.re)),
+                 "r"((uint32_t)__double2loint(v.im)), "r"((uint32_t)__double2hiint(v.im))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_tw_setup(TmemTw &tw, uint32_t cols) {
+    tw.cols = cols;
+    const TwoStageTw<4, 5> a(tw.p2);
+    const TwoStageTw<6, 7> b(tw.p3);
+    const LastStageTw l(tw.p4);
+    tmem_store_cplx(cols + 0u, a.wb[1][0]);
+    tmem_store_cplx(cols + 4u, a.wa[0]);
+    tmem_store_cplx(cols + 8u, a.wa[1]);
+    tmem_store_cplx(cols + 12u, b.wb[1][0]);
+    tmem_store_cplx(cols + 16u, b.wa[0]);
+    tmem_store_cplx(cols + 20u, b.wa[1]);
+    tmem_store_cplx(cols + 24u, l.w[1][0]);
+    tmem_store_cplx(cols + 28u, l.w[0][1]);
+    tmem_store_cplx(cols + 32u, l.w[1][1]);
+    tmem_wait_st();
+}
+struct TwRaw {
+    uint32_t u[16];
+};
+__device__ __forceinline__ void tmem_tw_request(TwRaw &r, uint32_t taddr) {   // asynchronous: completed by the wait of the next swap
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r.u[0]), "=r"(r.u[1]), "=r"(r.u[2]), "=r"(r.u[3]), "=r"(r.u[4]), "=r"(r.u[5]), "=r"(r.u[6]), "=r"(r.u[7]), "=r"(r.u[8]), "=r"(r.u[9]),
+                   "=r"(r.u[10]), "=r"(r.u[11]), "=r"(r.u[12]), "=r"(r.u[13]), "=r"(r.u[14]), "=r"(r.u[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_tw_claim(const TwRaw &r0, cplx (&d)[3]) {   // after a tcgen05.wait::ld that follows the request
+    TwRaw r = r0;
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r.u[0]), "+r"(r.u[1]), "+r"(r.u[2]), "+r"(r.u[3]), "+r"(r.u[4]), "+r"(r.u[5]), "+r"(r.u[6]), "+r"(r.u[7]), "+r"(r.u[8]), "+r"(r.u[9]),
+                   "+r"(r.u[10]), "+r"(r.u[11])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        d[k].re = __hiloint2double((int)r.u[4 * k + 1], (int)r.u[4 * k]);
+        d[k].im = __hiloint2double((int)r.u[4 * k + 3], (int)r.u[4 * k + 2]);
+    }
+}
+#ifndef TFHE_TMEM_TWSTORE
+#define TFHE_TMEM_TWSTORE 1
+#endif
+constexpr uint32_t TMEM_TW_COLS = 40;
 // forward transform after pass A (x in layout A: registers (j7 j6 j5), stages 0..2 done) -> layout F
 __device__ __forceinline__ void tmem_fwd_rest(cplx (&x)[8], uint32_t taddr, const TmemTw &tw) {
+#if TFHE_TMEM_TWSTORE
+    TwRaw raw;
+    cplx d[3];
+    tmem_swap2_store(x, taddr);           // j7 stays, (j6 j5) leave: regs (j4 j3 j7)
+    tmem_tw_request(raw, tw.cols);          // x is dead here: the request costs no registers
+    tmem_wait_st();
+    tmem_swap2_load(x, taddr);
+    tmem_tw_claim(raw, d);
+    fwd_two_stages<4, 5>(x, TwoStageTw<4, 5>(tw.p2, d));   // stages 3, 4
+    rename_out(x);                        // (j7 j4 j3)
+    tmem_swap2_store(x, taddr);           // regs (j2 j1 j7)
+    tmem_tw_request(raw, tw.cols + 12u);          // x is dead here: the request costs no registers
+    tmem_wait_st();
+    tmem_swap2_load(x, taddr);
+    tmem_tw_claim(raw, d);
+    fwd_two_stages<6, 7>(x, TwoStageTw<6, 7>(tw.p3, d));   // stages 5, 6
+    rename_out(x);                        // (j7 j2 j1)
+    tmem_swap2_store(x, taddr);           // regs (j0 j6 j7)
+    tmem_tw_request(raw, tw.cols + 24u);          // x is dead here: the request costs no registers
+    tmem_wait_st();
+    tmem_swap2_load(x, taddr);
+    tmem_tw_claim(raw, d);
+    const LastStageTw l(tw.p4, d);
+#else
     tmem_swap2(x, taddr);                 // j7 stays, (j6 j5) leave: regs (j4 j3 j7)
-    fwd_two_stages<4, 5>(x, tw.p2);       // stages 3, 4
+    fwd_two_stages<4, 5>(x, TwoStageTw<4, 5>(tw.p2));   // stages 3, 4
     rename_out(x);                        // (j7 j4 j3)
     tmem_swap2(x, taddr);                 // regs (j2 j1 j7)
-    fwd_two_stages<6, 7>(x, tw.p3);       // stages 5, 6
+    fwd_two_stages<6, 7>(x, TwoStageTw<6, 7>(tw.p3));   // stages 5, 6
     rename_out(x);                        // (j7 j2 j1)
     tmem_swap2(x, taddr);                 // regs (j0 j6 j7)
     const LastStageTw l(tw.p4);
+#endif
 #pragma unroll
     for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], l.w[r & 1][(r >> 1) & 1]);   // stage 7
 }
@@ -295,22 +386,55 @@ __device__ __forceinline__ void tmem_unswap2_pair(cplx (&a)[8], cplx (&b)[8], ui
     tmem_unswap2_load(b, taddr + 32u);
 }
 __device__ __forceinline__ void tmem_inv_rest(cplx (&a)[8], cplx (&b)[8], uint32_t taddr, const TmemTw &tw) {
+#if TFHE_TMEM_TWSTORE
+    TwRaw raw;
+    cplx d[3];
+    tmem_tw_request(raw, tw.cols + 24u);
+    tmem_tw_claim(raw, d);
+    {
+        const LastStageTw l(tw.p4, d);
+#else
     {
         const LastStageTw l(tw.p4);
+#endif
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             gs_bfly(a[r], a[r + 4], l.w[r & 1][(r >> 1) & 1]);
             gs_bfly(b[r], b[r + 4], l.w[r & 1][(r >> 1) & 1]);
         }
     }
+#if TFHE_TMEM_TWSTORE
+    tmem_unswap2_store(a, taddr);         // regs (j7 j2 j1)
+    tmem_unswap2_store(b, taddr + 32u);
+    tmem_tw_request(raw, tw.cols + 12u);
+    tmem_wait_st();
+    tmem_unswap2_load(a, taddr);
+    tmem_unswap2_load(b, taddr + 32u);
+    tmem_tw_claim(raw, d);
+    const TwoStageTw<6, 7> t3(tw.p3, d);
+#else
     tmem_unswap2_pair(a, b, taddr);       // regs (j7 j2 j1)
+    const TwoStageTw<6, 7> t3(tw.p3);
+#endif
     rename_in(a); rename_in(b);           // (j2 j1 j7)
-    inv_two_stages<6, 7>(a, tw.p3);
-    inv_two_stages<6, 7>(b, tw.p3);
+    inv_two_stages<6, 7>(a, t3);
+    inv_two_stages<6, 7>(b, t3);
+#if TFHE_TMEM_TWSTORE
+    tmem_unswap2_store(a, taddr);         // regs (j7 j4 j3)
+    tmem_unswap2_store(b, taddr + 32u);
+    tmem_tw_request(raw, tw.cols);
+    tmem_wait_st();
+    tmem_unswap2_load(a, taddr);
+    tmem_unswap2_load(b, taddr + 32u);
+    tmem_tw_claim(raw, d);
+    const TwoStageTw<4, 5> t2(tw.p2, d);
+#else
     tmem_unswap2_pair(a, b, taddr);       // regs (j7 j4 j3)
+    const TwoStageTw<4, 5> t2(tw.p2);
+#endif
     rename_in(a); rename_in(b);           // (j4 j3 j7)
-    inv_two_stages<4, 5>(a, tw.p2);
-    inv_two_stages<4, 5>(b, tw.p2);
+    inv_two_stages<4, 5>(a, t2);
+    inv_two_stages<4, 5>(b, t2);
     tmem_unswap2_pair(a, b, taddr);       // regs (j7 j6 j5): layout A
 }
 

@@ -153,6 +153,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         tquarter = *tmem_ptr + ((team * 32u) << 16);
         taddr = tquarter + sub * TMEM_SUB_COLS;
         twx = load_tmem_tw(a.tw.twX, lane);
+#if TFHE_TMEM_TWSTORE
+        static_assert(K::P * TMEM_SUB_COLS + K::P * TMEM_TW_COLS <= 512, "tensor-memory columns");
+        if (team < active) tmem_tw_setup(twx, tquarter + (uint32_t)K::P * TMEM_SUB_COLS + sub * TMEM_TW_COLS);
+#endif
     }
 
     if (team >= active) {
