@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     FftRegs<K> R;
     double maxfrac = 0.0;
     uint32_t it = 0;   // position in the key stream (the same sequence in every warp)
+    uint32_t pre_row = 0xFFFFFFFFu;   // ring row whose `full` barrier was tested ahead of time, and the outcome
+    bool pre_ok = false;
     // the 2E words of acc[sub] this thread decomposes are the ones it updates: they cross the step boundary in registers
     // (not with the single exchange buffer of N = 2048, which is out of registers)
 #ifndef TFHE_FFT_ACCREG_G
@@ -286,6 +288,8 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     };
     // lane 0 of a warp that is done with ring row r.  SELF_REFILL: the slot's use u = r / NSLOT is complete once every warp
     // has arrived; whoever sees that first (at the latest the last arriver, right after its own arrival) claims the refill.
+    // (looking at the outcome of the test one row later, to hide its ~100 cycles behind the next multiply-accumulate, was measured with
+    // the 6-row ring of the tensor-memory configuration: 97.3 -> 105.0 ms -- the refill that waits starves the ring)
     auto release_slot = [&](uint32_t r) {
         const uint32_t s = r % K::NSLOT;
         mbar_arrive(empty + s);
@@ -323,12 +327,23 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
         zero_acc<K>(R);
         if constexpr (OWN_FIRST) {
+#ifndef TFHE_FFT_PRETEST
+#define TFHE_FFT_PRETEST 1
+#endif
             auto mac_slot = [&](auto own_c, uint32_t d) {   // ring row it + d: slot d of this level = row of polynomial (sub + d) mod P
                 constexpr bool OWN = decltype(own_c)::value;
                 const uint32_t ir = it + d, s = ir % K::NSLOT, p = (sub + d) % (uint32_t)K::P;
                 if constexpr (!SELF_REFILL) { if (producer) pump(ir + 1, ir); }
                 if constexpr (K::XCHG && !OWN && TFHE_TMEM_LOADFIRST) tmem_load_row(R.x, tquarter + p * TMEM_SUB_COLS + TMEM_PUB_COL + 32u * pubsel);
+#if TFHE_FFT_PRETEST
+                // the barrier of this row was tested while the previous row was being multiplied (the test has a latency of its own,
+                // ~100 cycles even when the row has long arrived: 18 of them per step were 5 % of the P0 kernel's time)
+                if (!(pre_row == ir && pre_ok)) mbar_wait(full + s, (ir / K::NSLOT) & 1u, a.err_flag);
+                pre_row = ir + 1u;
+                pre_ok = mbar_test(full + pre_row % K::NSLOT, (pre_row / K::NSLOT) & 1u);
+#else
                 mbar_wait(full + s, (ir / K::NSLOT) & 1u, a.err_flag);
+#endif
                 if constexpr (K::XCHG && !OWN && !TFHE_TMEM_LOADFIRST) tmem_load_row(R.x, tquarter + p * TMEM_SUB_COLS + TMEM_PUB_COL + 32u * pubsel);   // the peer's row: same lane, its columns
                 const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
                 const cplx *peer = reinterpret_cast<const cplx *>(tm + K::TM_SUB + p * K::SUB_BYTES + K::STASH_BYTES);
