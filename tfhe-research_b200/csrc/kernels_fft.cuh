@@ -93,6 +93,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 #ifndef TFHE_FFT_ACCREG
 #define TFHE_FFT_ACCREG 1
 #endif
+#ifndef TFHE_FFT_PRETEST
+#define TFHE_FFT_PRETEST 1
+#endif
 template <class K, bool BMMP = false>
 __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_constant__ FftArgs a) {
     using C = typename K::F;
@@ -327,9 +330,6 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
         zero_acc<K>(R);
         if constexpr (OWN_FIRST) {
-#ifndef TFHE_FFT_PRETEST
-#define TFHE_FFT_PRETEST 1
-#endif
             auto mac_slot = [&](auto own_c, uint32_t d) {   // ring row it + d: slot d of this level = row of polynomial (sub + d) mod P
                 constexpr bool OWN = decltype(own_c)::value;
                 const uint32_t ir = it + d, s = ir % K::NSLOT, p = (sub + d) % (uint32_t)K::P;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                     for (uint32_t kh = 0; kh < KEYS * K::HALVES; kh++, it++) {
                         const uint32_t which = kh / K::HALVES, half = kh % K::HALVES, s = it % K::NSLOT;
                         if constexpr (!SELF_REFILL) { if (producer) pump(it + 1, it); }
-                        mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);
+                        mbar_wait(full + s, (it / K::NSLOT) & 1u, a.err_flag);   // (testing one slot ahead as in mac_slot: P2 103.6 -> 105.9 ms, not kept here)
 #if !(TFHE_FFT_ABLATE & 2)
                         const cplx *slot = reinterpret_cast<const cplx *>(ring + s * K::SLOT_BYTES);
                         if constexpr (BMMP) phase_mac_bmmp<K, OWN>(R, t, sub, slot, peer, a.tw.ztab, which == 0 ? ex0 : which == 1 ? rot : rot1, which == 0 ? zb[0] : which == 1 ? zb[1] : zb[2]);
