@@ -420,7 +420,7 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
         }
         switch (ctx->pbs_id) {
         case 0:
-            if (a.mode == 0 && bk->d_bsk_fft_x && ctx->fft_tmem)
+            if (a.mode == 0 && bk->d_bsk_fft_x && ctx->fft_tmem && fft_smem_bytes<KF0T>(a.n) <= 227 * 1024)
                 return ctx->fft_check ? launch_pbs_fft_t<KF0TC>(ctx, a, bk->d_bsk_fft_x) : launch_pbs_fft_t<KF0T>(ctx, a, bk->d_bsk_fft_x);
             return ctx->fft_check ? launch_pbs_fft_t<KF0C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0>(ctx, a, bk->d_bsk_fft);
         case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
