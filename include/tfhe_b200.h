@@ -259,8 +259,9 @@ int tfhe_decompose(tfhe_ctx *ctx, int which, const uint32_t *values, size_t len,
 int tfhe_glwe_mul_monomial(tfhe_ctx *ctx, const uint32_t *glwe /* [B][k+1][N] */, const int64_t *index /* [B], host */,
                            size_t batch, uint32_t *out);
 /* utils.rs:155-160 poly_mul (the Toeplitz product) for a batch of pairs: out[b] = a[b] (*) g[b] in
- * Z_{2^32}[X]/(X^N+1).  a[b] holds SMALL SIGNED coefficients, |a| <= 1024 (the digit range of the path; larger
- * values would leave the exact range of the 2-prime transform and are rejected with TFHE_E_PARAM), g[b] any u32. */
+ * Z_{2^32}[X]/(X^N+1), both operands any words mod 2^32 as in the reference (a is read as u32 when a coefficient is
+ * outside [-1024, 1024]).  Small signed a (the digit range of the path) is one exact 2-prime transform product; otherwise the
+ * four byte limbs of a are multiplied separately and recombined with shifts mod 2^32 (the same bits). */
 int tfhe_negacyclic_mul(tfhe_ctx *ctx, const int32_t *a /* [B][N], host or device */, const uint32_t *g /* [B][N] */,
                         size_t batch, uint32_t *out /* [B][N] */);
 /* ggsw.rs:132-161: out[b] = external_product(BSK[ggsw_index[b]], glwe[b]) */

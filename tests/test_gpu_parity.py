@@ -249,9 +249,15 @@ def test_negacyclic_mul_utils_rs_155(preset, n):
         L.orc_poly_mul(a[b].astype(np.uint32), g[b], N, exp)
         assert np.array_equal(got[b], exp), b
     assert np.array_equal(got[1], np.concatenate([(-g[1, -1:].astype(np.int64) & 0xFFFFFFFF).astype(np.uint32), g[1, :-1]]))
-    with pytest.raises(T.TfheError) as ei:
-        e.ctx.negacyclic_mul(np.full((1, N), 5000, dtype=np.int32), g[:1])
-    assert ei.value.code == T.TFHE_E_PARAM
+    # arbitrary u32 x u32, as the reference's poly_mul takes them (extreme words included)
+    big = r32(rng, 4, N)
+    big[0, :3] = [0xFFFFFFFF, 0x80000000, 0x7FFFFFFF]
+    big[1] = 0xFFFFFFFF
+    got = e.ctx.negacyclic_mul(big.view(np.int32), g[:4])
+    for b in range(4):
+        exp = orc.z(N)
+        L.orc_poly_mul(big[b], g[b], N, exp)
+        assert np.array_equal(got[b], exp), b
 
 
 @pytest.mark.parametrize("preset,n", [("P0:ntt", 4), ("P1:ntt", 3), ("P1:fft", 3), ("P0:fft", 4)])

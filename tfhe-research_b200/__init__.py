@@ -560,7 +560,7 @@ class Context:
         return out
 
     def negacyclic_mul(self, a_small, g):
-        """utils.rs:155-160 poly_mul: a_small int32 [B, N] with |a| <= 1024, g uint32 [B, N]."""
+        """utils.rs:155-160 poly_mul: a int32 [B, N] (small signed digits, or any word mod 2^32), g uint32 [B, N]."""
         a_small = np.ascontiguousarray(a_small, dtype=np.int32)
         g = np.ascontiguousarray(g, dtype=np.uint32)
         if g.ndim != 2 or g.shape[1] != self.params.N or a_small.shape != g.shape:

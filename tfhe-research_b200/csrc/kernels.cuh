@@ -643,6 +643,16 @@ __global__ void gate_linear_kernel(const uint32_t *__restrict__ ct0, const uint3
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < len) out[i] = ct1[i] * 2u + ct0[i];
 }
+// general operand of tfhe_negacyclic_mul: byte `limb` of every word of a (unsigned, < 256: inside the exact range of the transform)
+__global__ void byte_limb_kernel(const int32_t *__restrict__ a, int32_t *__restrict__ out, int limb, size_t len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) out[i] = (int32_t)(((uint32_t)a[i] >> (8 * limb)) & 0xFFu);
+}
+// acc (+)= part << shift  (mod 2^32); first = 1 overwrites
+__global__ void shl_accumulate_kernel(uint32_t *__restrict__ acc, const uint32_t *__restrict__ part, int shift, int first, size_t len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < len) acc[i] = (first ? 0u : acc[i]) + (part[i] << shift);
+}
 // NAND/NOR/XNOR = trivial(1) - gate:  out[j] = -x[j];  out[n] += encode(1)   
 __global__ void gate_negate_kernel(uint32_t *__restrict__ x, const uint8_t *__restrict__ gates, int all, uint32_t n, uint32_t batch, uint32_t one) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1255,17 +1255,41 @@ int tfhe_negacyclic_mul(tfhe_ctx *ctx, const int32_t *a, const uint32_t *g, size
     // range check of the small operand (on a host copy: this is a parity-test entry point, not a hot path)
     std::vector<int32_t> ha(batch * ctx->N());
     CU(cudaMemcpy(ha.data(), a, bytes, cudaMemcpyDefault));
+    bool small = true;
     for (int32_t v : ha)
-        if (v > 1024 || v < -1024) return fail(ctx, TFHE_E_PARAM, "tfhe_negacyclic_mul: |a| > 1024 is outside the exact range");
+        if (v > 1024 || v < -1024) { small = false; break; }
     const void *d_a, *d_g; void *d_out; int rc;
     if ((rc = stage_in(ctx, a, bytes, ctx->in0, &d_a))) return rc;
     if ((rc = stage_in(ctx, g, bytes, ctx->in1, &d_g))) return rc;
     if ((rc = stage_out(ctx, out, bytes, ctx->out, &d_out))) return rc;
-    switch (ctx->pbs_id) {
-    case 0: rc = launch_polymul_t<K0>(ctx, (const int32_t *)d_a, (const uint32_t *)d_g, (uint32_t *)d_out, batch); break;
-    case 1: rc = launch_polymul_t<K1>(ctx, (const int32_t *)d_a, (const uint32_t *)d_g, (uint32_t *)d_out, batch); break;
-    case 2: rc = launch_polymul_t<K2>(ctx, (const int32_t *)d_a, (const uint32_t *)d_g, (uint32_t *)d_out, batch); break;
-    default: rc = fail(ctx, TFHE_E_PARAM, "no kernel instantiation");
+    auto mul = [&](const int32_t *aa, uint32_t *oo) {
+        switch (ctx->pbs_id) {
+        case 0: return launch_polymul_t<K0>(ctx, aa, (const uint32_t *)d_g, oo, batch);
+        case 1: return launch_polymul_t<K1>(ctx, aa, (const uint32_t *)d_g, oo, batch);
+        case 2: return launch_polymul_t<K2>(ctx, aa, (const uint32_t *)d_g, oo, batch);
+        }
+        return fail(ctx, TFHE_E_PARAM, "no kernel instantiation");
+    };
+    if (small) {
+        rc = mul((const int32_t *)d_a, (uint32_t *)d_out);
+    } else {
+        // any u32 operand (the reference's poly_mul takes u32 x u32): a = sum_i 2^(8 i) byte_i(a) as a word mod 2^32, so
+        // a (*) g = sum_i (byte_i(a) (*) g) << 8 i  mod 2^32 -- four products with an operand inside the exact range
+        const size_t len = batch * ctx->N();
+        CU(ctx->misc.ensure(2 * bytes));
+        int32_t *d_limb = (int32_t *)ctx->misc.p;
+        uint32_t *d_part = (uint32_t *)((uint8_t *)ctx->misc.p + bytes);
+        const unsigned blocks = (unsigned)((len + 255) / 256);
+        rc = TFHE_OK;
+        for (int limb = 0; limb < 4 && rc == TFHE_OK; limb++) {
+            byte_limb_kernel<<<blocks, 256, 0, ctx->stream>>>((const int32_t *)d_a, d_limb, limb, len);
+            CU(cudaGetLastError());
+            rc = mul(d_limb, d_part);
+            if (rc != TFHE_OK) break;
+            shl_accumulate_kernel<<<blocks, 256, 0, ctx->stream>>>((uint32_t *)d_out, d_part, 8 * limb, limb == 0, len);
+            CU(cudaGetLastError());
+            ctx->launches += 2;
+        }
     }
     if (rc) return rc;
     if ((rc = finish_out(ctx, out, bytes, d_out))) return rc;
