@@ -215,7 +215,7 @@ struct TwoStageTw {
         wa[1] = cmul_c(wa[0], RootOfUnity<KA>::c, RootOfUnity<KA>::s);
     }
     // the same from stored values (d[0] = wb[1][0], d[1] = wa[0], d[2] = wa[1]: what the constructor above computes)
-    __device__ __forceinline__ TwoStageTw(const cplx base, const cplx (&d)[3]) {
+    __device__ __forceinline__ TwoStageTw(const cplx base, const cplx (&d)[4]) {
         wb[0][0] = base;
         wb[0][1] = cmul_i(base);
         wb[1][0] = d[0];
@@ -250,7 +250,7 @@ struct LastStageTw {
         w[0][1] = cmul_c(base, RootOfUnity<7>::c, RootOfUnity<7>::s);
         w[1][1] = cmul_c(w[1][0], RootOfUnity<7>::c, RootOfUnity<7>::s);
     }
-    __device__ __forceinline__ LastStageTw(const cplx base, const cplx (&d)[3]) {   // d = w[1][0], w[0][1], w[1][1] as computed above
+    __device__ __forceinline__ LastStageTw(const cplx base, const cplx (&d)[4]) {   // d = w[1][0], w[0][1], w[1][1] as computed above (, base)
         w[0][0] = base;
         w[1][0] = d[0];
         w[0][1] = d[1];
@@ -288,8 +288,9 @@ __device__ __forceinline__ TmemTw load_tmem_tw(const cplx *table, uint32_t lane)
     return t;
 }
 // A thread's derived twiddles never change.  They do not fit in registers, but they fit in tensor memory: computed once per kernel,
-// stored in 36 of the warp's columns ([0, 12) pass 2: wb[1][0], wa[0], wa[1]; [12, 24) pass 3; [24, 36) last stage: w[1][0], w[0][1],
-// w[1][1]) and fetched with one tcgen05.ld.x16 per pass instead of 13 / 13 / 12 FP64 operations (the same values: same bits).
+// stored in 48 of the warp's columns ([0, 16) pass 2: wb[1][0], wa[0], wa[1], the table entry itself; [16, 32) pass 3; [32, 48) last
+// stage: w[1][0], w[0][1], w[1][1], entry) and fetched with one tcgen05.ld.x16 per pass instead of 13 / 13 / 12 FP64 operations (the
+// same values: same bits).  TFHE_TMEM_TWBASE: the table entries are taken from there too instead of 12 registers.
 __device__ __forceinline__ void tmem_store_cplx(uint32_t taddr, const cplx v) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"((uint32_t)__double2loint(v.re)), "r"((uint32_t)__double2hiint(v.re)),
                  "r"((uint32_t)__double2loint(v.im)), "r"((uint32_t)__double2hiint(v.im))
@@ -303,12 +304,15 @@ __device__ __forceinline__ void tmem_tw_setup(TmemTw &tw, uint32_t cols) {
     tmem_store_cplx(cols + 0u, a.wb[1][0]);
     tmem_store_cplx(cols + 4u, a.wa[0]);
     tmem_store_cplx(cols + 8u, a.wa[1]);
-    tmem_store_cplx(cols + 12u, b.wb[1][0]);
-    tmem_store_cplx(cols + 16u, b.wa[0]);
-    tmem_store_cplx(cols + 20u, b.wa[1]);
-    tmem_store_cplx(cols + 24u, l.w[1][0]);
-    tmem_store_cplx(cols + 28u, l.w[0][1]);
-    tmem_store_cplx(cols + 32u, l.w[1][1]);
+    tmem_store_cplx(cols + 12u, tw.p2);
+    tmem_store_cplx(cols + 16u, b.wb[1][0]);
+    tmem_store_cplx(cols + 20u, b.wa[0]);
+    tmem_store_cplx(cols + 24u, b.wa[1]);
+    tmem_store_cplx(cols + 28u, tw.p3);
+    tmem_store_cplx(cols + 32u, l.w[1][0]);
+    tmem_store_cplx(cols + 36u, l.w[0][1]);
+    tmem_store_cplx(cols + 40u, l.w[1][1]);
+    tmem_store_cplx(cols + 44u, tw.p4);
     tmem_wait_st();
 }
 struct TwRaw {
@@ -321,15 +325,15 @@ __device__ __forceinline__ void tmem_tw_request(TwRaw &r, uint32_t taddr) {   //
                  : "r"(taddr)
                  : "memory");
 }
-__device__ __forceinline__ void tmem_tw_claim(const TwRaw &r0, cplx (&d)[3]) {   // after a tcgen05.wait::ld that follows the request
+__device__ __forceinline__ void tmem_tw_claim(const TwRaw &r0, cplx (&d)[4]) {   // after a tcgen05.wait::ld that follows the request
     TwRaw r = r0;
     asm volatile("tcgen05.wait::ld.sync.aligned;"
                  : "+r"(r.u[0]), "+r"(r.u[1]), "+r"(r.u[2]), "+r"(r.u[3]), "+r"(r.u[4]), "+r"(r.u[5]), "+r"(r.u[6]), "+r"(r.u[7]), "+r"(r.u[8]), "+r"(r.u[9]),
-                   "+r"(r.u[10]), "+r"(r.u[11])
+                   "+r"(r.u[10]), "+r"(r.u[11]), "+r"(r.u[12]), "+r"(r.u[13]), "+r"(r.u[14]), "+r"(r.u[15])
                  :
                  : "memory");
 #pragma unroll
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 4; k++) {
         d[k].re = __hiloint2double((int)r.u[4 * k + 1], (int)r.u[4 * k]);
         d[k].im = __hiloint2double((int)r.u[4 * k + 3], (int)r.u[4 * k + 2]);
     }
@@ -337,32 +341,35 @@ __device__ __forceinline__ void tmem_tw_claim(const TwRaw &r0, cplx (&d)[3]) {  
 #ifndef TFHE_TMEM_TWSTORE
 #define TFHE_TMEM_TWSTORE 1
 #endif
-constexpr uint32_t TMEM_TW_COLS = 40;
+#ifndef TFHE_TMEM_TWBASE
+#define TFHE_TMEM_TWBASE 1
+#endif
+constexpr uint32_t TMEM_TW_COLS = 48;
 // forward transform after pass A (x in layout A: registers (j7 j6 j5), stages 0..2 done) -> layout F
 __device__ __forceinline__ void tmem_fwd_rest(cplx (&x)[8], uint32_t taddr, const TmemTw &tw) {
 #if TFHE_TMEM_TWSTORE
     TwRaw raw;
-    cplx d[3];
+    cplx d[4];
     tmem_swap2_store(x, taddr);           // j7 stays, (j6 j5) leave: regs (j4 j3 j7)
     tmem_tw_request(raw, tw.cols);          // x is dead here: the request costs no registers
     tmem_wait_st();
     tmem_swap2_load(x, taddr);
     tmem_tw_claim(raw, d);
-    fwd_two_stages<4, 5>(x, TwoStageTw<4, 5>(tw.p2, d));   // stages 3, 4
+    fwd_two_stages<4, 5>(x, TwoStageTw<4, 5>(TFHE_TMEM_TWBASE ? d[3] : tw.p2, d));   // stages 3, 4
     rename_out(x);                        // (j7 j4 j3)
     tmem_swap2_store(x, taddr);           // regs (j2 j1 j7)
-    tmem_tw_request(raw, tw.cols + 12u);          // x is dead here: the request costs no registers
+    tmem_tw_request(raw, tw.cols + 16u);          // x is dead here: the request costs no registers
     tmem_wait_st();
     tmem_swap2_load(x, taddr);
     tmem_tw_claim(raw, d);
-    fwd_two_stages<6, 7>(x, TwoStageTw<6, 7>(tw.p3, d));   // stages 5, 6
+    fwd_two_stages<6, 7>(x, TwoStageTw<6, 7>(TFHE_TMEM_TWBASE ? d[3] : tw.p3, d));   // stages 5, 6
     rename_out(x);                        // (j7 j2 j1)
     tmem_swap2_store(x, taddr);           // regs (j0 j6 j7)
-    tmem_tw_request(raw, tw.cols + 24u);          // x is dead here: the request costs no registers
+    tmem_tw_request(raw, tw.cols + 32u);          // x is dead here: the request costs no registers
     tmem_wait_st();
     tmem_swap2_load(x, taddr);
     tmem_tw_claim(raw, d);
-    const LastStageTw l(tw.p4, d);
+    const LastStageTw l(TFHE_TMEM_TWBASE ? d[3] : tw.p4, d);
 #else
     tmem_swap2(x, taddr);                 // j7 stays, (j6 j5) leave: regs (j4 j3 j7)
     fwd_two_stages<4, 5>(x, TwoStageTw<4, 5>(tw.p2));   // stages 3, 4
@@ -378,21 +385,22 @@ __device__ __forceinline__ void tmem_fwd_rest(cplx (&x)[8], uint32_t taddr, cons
 }
 // inverse of two accumulators (the low- and high-limb products of a column) from layout F back to layout A (stages 7..3 undone;
 // the caller finishes with the inverse of pass A); the two use disjoint column ranges so that their transfers overlap
-__device__ __forceinline__ void tmem_unswap2_pair(cplx (&a)[8], cplx (&b)[8], uint32_t taddr) {
+__device__ __forceinline__ void tmem_unswap2_pair(cplx (&a)[8], cplx (&b)[8], uint32_t taddr, uint32_t taddr_b) {
     tmem_unswap2_store(a, taddr);
-    tmem_unswap2_store(b, taddr + 32u);
+    tmem_unswap2_store(b, taddr_b);
     tmem_wait_st();
     tmem_unswap2_load(a, taddr);
-    tmem_unswap2_load(b, taddr + 32u);
+    tmem_unswap2_load(b, taddr_b);
 }
-__device__ __forceinline__ void tmem_inv_rest(cplx (&a)[8], cplx (&b)[8], uint32_t taddr, const TmemTw &tw) {
+// taddr_b: 32 more columns for the second accumulator -- the caller passes the publish buffer that is free at this point
+__device__ __forceinline__ void tmem_inv_rest(cplx (&a)[8], cplx (&b)[8], uint32_t taddr, uint32_t taddr_b, const TmemTw &tw) {
 #if TFHE_TMEM_TWSTORE
     TwRaw raw;
-    cplx d[3];
-    tmem_tw_request(raw, tw.cols + 24u);
+    cplx d[4];
+    tmem_tw_request(raw, tw.cols + 32u);
     tmem_tw_claim(raw, d);
     {
-        const LastStageTw l(tw.p4, d);
+        const LastStageTw l(TFHE_TMEM_TWBASE ? d[3] : tw.p4, d);
 #else
     {
         const LastStageTw l(tw.p4);
@@ -405,15 +413,15 @@ __device__ __forceinline__ void tmem_inv_rest(cplx (&a)[8], cplx (&b)[8], uint32
     }
 #if TFHE_TMEM_TWSTORE
     tmem_unswap2_store(a, taddr);         // regs (j7 j2 j1)
-    tmem_unswap2_store(b, taddr + 32u);
-    tmem_tw_request(raw, tw.cols + 12u);
+    tmem_unswap2_store(b, taddr_b);
+    tmem_tw_request(raw, tw.cols + 16u);
     tmem_wait_st();
     tmem_unswap2_load(a, taddr);
-    tmem_unswap2_load(b, taddr + 32u);
+    tmem_unswap2_load(b, taddr_b);
     tmem_tw_claim(raw, d);
-    const TwoStageTw<6, 7> t3(tw.p3, d);
+    const TwoStageTw<6, 7> t3(TFHE_TMEM_TWBASE ? d[3] : tw.p3, d);
 #else
-    tmem_unswap2_pair(a, b, taddr);       // regs (j7 j2 j1)
+    tmem_unswap2_pair(a, b, taddr, taddr_b);       // regs (j7 j2 j1)
     const TwoStageTw<6, 7> t3(tw.p3);
 #endif
     rename_in(a); rename_in(b);           // (j2 j1 j7)
@@ -421,21 +429,21 @@ __device__ __forceinline__ void tmem_inv_rest(cplx (&a)[8], cplx (&b)[8], uint32
     inv_two_stages<6, 7>(b, t3);
 #if TFHE_TMEM_TWSTORE
     tmem_unswap2_store(a, taddr);         // regs (j7 j4 j3)
-    tmem_unswap2_store(b, taddr + 32u);
+    tmem_unswap2_store(b, taddr_b);
     tmem_tw_request(raw, tw.cols);
     tmem_wait_st();
     tmem_unswap2_load(a, taddr);
-    tmem_unswap2_load(b, taddr + 32u);
+    tmem_unswap2_load(b, taddr_b);
     tmem_tw_claim(raw, d);
-    const TwoStageTw<4, 5> t2(tw.p2, d);
+    const TwoStageTw<4, 5> t2(TFHE_TMEM_TWBASE ? d[3] : tw.p2, d);
 #else
-    tmem_unswap2_pair(a, b, taddr);       // regs (j7 j4 j3)
+    tmem_unswap2_pair(a, b, taddr, taddr_b);       // regs (j7 j4 j3)
     const TwoStageTw<4, 5> t2(tw.p2);
 #endif
     rename_in(a); rename_in(b);           // (j4 j3 j7)
     inv_two_stages<4, 5>(a, t2);
     inv_two_stages<4, 5>(b, t2);
-    tmem_unswap2_pair(a, b, taddr);       // regs (j7 j6 j5): layout A
+    tmem_unswap2_pair(a, b, taddr, taddr_b);       // regs (j7 j6 j5): layout A
 }
 
 // ---- rows published through tensor memory.  With team = lane quarter (warp % 4) the P sub-teams (warps) of a ciphertext share
@@ -495,9 +503,9 @@ __device__ __forceinline__ void tmem_load_row(cplx (&x)[8], uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// tensor-memory columns of a sub-team (warp): [0, 64) exchanges of the transforms (32 per limb for the paired inverse),
-// [64, 96) and [96, 128) the published row, double buffered by level parity
-constexpr uint32_t TMEM_SUB_COLS = 128, TMEM_PUB_COL = 64;
+// tensor-memory columns of a sub-team (warp): [0, 32) exchanges of the transforms, [32, 64) and [64, 96) the published row, double
+// buffered by level parity (the paired inverse exchanges its second accumulator through the buffer that is free at that point)
+constexpr uint32_t TMEM_SUB_COLS = 96, TMEM_PUB_COL = 32;
 
 }  // namespace fft
 }  // namespace tfhe

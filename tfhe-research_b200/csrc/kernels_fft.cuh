@@ -137,8 +137,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // tensor-memory exchanges (fft_tmem.cuh): warp 0 allocates all 512 columns (one CTA per SM) -- every warp owns 128 columns
-    // (warp / 4) of its 32 lanes (warp % 4): 64 for the exchanges of its transforms, 2 x 32 for the rows it publishes
+    // tensor-memory exchanges (fft_tmem.cuh): warp 0 allocates all 512 columns (one CTA per SM) -- every warp owns 96 columns
+    // (warp / 4) of its 32 lanes (warp % 4): 32 for the exchanges of its transforms, 2 x 32 for the rows it publishes, and 48 more
+    // behind those of all sub-teams for its derived twiddles
     uint32_t *tmem_ptr = claimed + K::NSLOT;
     if constexpr (K::XCHG) {
         static_assert(K::P * TMEM_SUB_COLS <= 512, "tensor-memory columns");
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                     tmem_fence_before_sync();
                     team_bar_id(team_bar, K::TEAM_THREADS);  // all P transformed rows of this level are published
                     tmem_fence_after_sync();
-#pragma unroll 1
+#pragma unroll 1   // (unrolled: 112 bytes of spills, 95.3 -> 109.3 ms)
                     for (uint32_t d = 1; d < (uint32_t)K::P; d++) mac_slot(std::false_type{}, d);
                     it += (uint32_t)K::P;
                     pubsel ^= 1u;
@@ -489,7 +490,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             phase_K3_hi<K>(R, t, a.tw.twA, buf0, lo, acc + sub * K::N, maxfrac);
         } else {
             if constexpr (K::XCHG) {
-                tmem_inv_rest(R.acc[0], R.acc[1], taddr, twx);   // stages 7..3 of both limbs, exchanged through tensor memory: layout A
+                tmem_inv_rest(R.acc[0], R.acc[1], taddr, taddr + TMEM_PUB_COL + 32u * pubsel, twx);   // stages 7..3 of both limbs, exchanged through tensor memory: layout A
             } else if constexpr (OWN_FIRST) {
                 phase_J1v<K>(R, t, twC_base, buf0, buf1);
                 sub_sync();
