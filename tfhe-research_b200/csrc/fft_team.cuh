@@ -201,7 +201,8 @@ struct TwTablesF {
 // NSLOT: depth of the key ring.  Two slots feed a CTA whose 2-4 ciphertexts keep the SM busy; a CTA that holds ONE ciphertext
 // (small batches: latency) is bound by the round trip of each ring refill instead, and uses the idle shared memory for a deep ring.
 // XCHG: 0 = the register passes of a transform exchange through shared memory (store_A/load_B, ...); 1 = through tensor memory
-// (fft_tmem.cuh: warp-sized sub-teams, M = 256), which also changes the spectral layout of the stored key.
+// (fft_tmem.cuh: warp-sized sub-teams, M = 256), which also changes the spectral layout of the stored key; 2 = shared-memory
+// exchanges with the derived twiddles of passes B and C kept in tensor memory instead of being re-derived in every pass.
 template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true, bool SINGLE_BUF_ = false, int HALVES_ = 1, int NSLOT_ = TFHE_FFT_NSLOT, int XCHG_ = 0>
 struct FftPbsCfg {
     using F = FftCfg<LOGN_ - 1, LOGE_>;
@@ -209,7 +210,8 @@ struct FftPbsCfg {
     static constexpr int K = K_, P = K_ + 1, L = L_, LOGB = LOGB_, ROWS = P * L;
     static constexpr int E = F::E, T = F::T;
     static constexpr int CTS = CTS_;                    // ciphertexts (teams) per CTA, sharing one key stream
-    static constexpr bool CHECK = CHECK_, SINGLE_BUF = SINGLE_BUF_, XCHG = XCHG_ != 0;
+    static constexpr bool CHECK = CHECK_, SINGLE_BUF = SINGLE_BUF_, XCHG = XCHG_ == 1;
+    static constexpr bool TWT = XCHG_ == 2;   // shared-memory exchanges, but a thread's derived pass twiddles wait in tensor memory (own-row-first loop)
     static_assert(!XCHG || (LOGN_ == 9 && LOGE_ == 3 && !SINGLE_BUF_ && HALVES_ == 1 && CTS_ == 4 && K_ <= 3), "tensor-memory exchanges: M = 256, 8 points per thread, one warp per sub-team, one team per lane quarter");
     static constexpr int HALVES = HALVES_, EH = E / HALVES_, MH = M / HALVES_;   // points per thread / per polynomial in one slot
     static constexpr int WARPS_PER_SUB = T / 32, TEAM_THREADS = P * T, THREADS = CTS * TEAM_THREADS;
@@ -380,6 +382,36 @@ TFHE_HD void phase_F2v(FftRegs<K> &r, uint32_t jbB, const cplx twB_base, const c
     load_B<C>(r.x, buf0, jbB);
     fwd_pass<C::LOGE, C::QB>(r.x, tw);
     store_B<C>(r.x, buf1, jbB);
+}
+// (the *w variants take the pass's complete twiddle array, prepared by the caller)
+template <class K>
+TFHE_HD void phase_F2w(FftRegs<K> &r, uint32_t jbB, const cplx *tw, const cplx *buf0, cplx *buf1) {
+    using C = typename K::F;
+    load_B<C>(r.x, buf0, jbB);
+    fwd_pass<C::LOGE, C::QB>(r.x, tw);
+    store_B<C>(r.x, buf1, jbB);
+}
+template <class K>
+TFHE_HD void phase_F3w(FftRegs<K> &r, uint32_t t, const cplx *tw, const cplx *buf1) {
+    using C = typename K::F;
+    load_C<C>(r.x, buf1, t);
+    fwd_pass<C::LOGE, C::LOGE>(r.x, tw);
+}
+template <class K>
+TFHE_HD void phase_J1w(FftRegs<K> &r, uint32_t t, const cplx *tw, cplx *buf0, cplx *buf1) {
+    using C = typename K::F;
+    inv_pass<C::LOGE, C::LOGE>(r.acc[0], tw);
+    inv_pass<C::LOGE, C::LOGE>(r.acc[1], tw);
+    store_C<C>(r.acc[0], buf0, t);
+    store_C<C>(r.acc[1], buf1, t);
+}
+template <class K>
+TFHE_HD void phase_J2aw(FftRegs<K> &r, uint32_t jbB, const cplx *tw, const cplx *buf0, const cplx *buf1) {
+    using C = typename K::F;
+    load_B<C>(r.acc[0], buf0, jbB);
+    load_B<C>(r.acc[1], buf1, jbB);
+    inv_pass<C::LOGE, C::QB>(r.acc[0], tw);
+    inv_pass<C::LOGE, C::QB>(r.acc[1], tw);
 }
 template <class K>
 TFHE_HD void phase_F2(FftRegs<K> &r, uint32_t jbB, const cplx *twB_thread, const cplx *buf0, cplx *buf1) {

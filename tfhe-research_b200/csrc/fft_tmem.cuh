@@ -507,5 +507,38 @@ __device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.
 // buffered by level parity (the paired inverse exchanges its second accumulator through the buffer that is free at that point)
 constexpr uint32_t TMEM_SUB_COLS = 96, TMEM_PUB_COL = 32;
 
+// ---- derived pass twiddles kept in tensor memory (FftPbsCfg::TWT: kernels whose exchanges stay in shared memory).  A block = up to 8
+// complex values of a thread in 32 columns of its lane: written once per kernel, fetched with one tcgen05.ld.x32 per pass.
+struct TwRaw32 {
+    uint32_t u[32];
+};
+template <int N>
+__device__ __forceinline__ void tmem_tw_block_store(uint32_t taddr, const cplx *tw) {
+    static_assert(N <= 8, "one block holds 8 complex values");
+#pragma unroll
+    for (int k = 0; k < N; k++) tmem_store_cplx(taddr + 4u * k, tw[k]);
+}
+__device__ __forceinline__ void tmem_tw_block_request(TwRaw32 &r, uint32_t taddr) {   // asynchronous
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+        "%26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r.u[0]), "=r"(r.u[1]), "=r"(r.u[2]), "=r"(r.u[3]), "=r"(r.u[4]), "=r"(r.u[5]), "=r"(r.u[6]), "=r"(r.u[7]), "=r"(r.u[8]), "=r"(r.u[9]), "=r"(r.u[10]),
+          "=r"(r.u[11]), "=r"(r.u[12]), "=r"(r.u[13]), "=r"(r.u[14]), "=r"(r.u[15]), "=r"(r.u[16]), "=r"(r.u[17]), "=r"(r.u[18]), "=r"(r.u[19]), "=r"(r.u[20]),
+          "=r"(r.u[21]), "=r"(r.u[22]), "=r"(r.u[23]), "=r"(r.u[24]), "=r"(r.u[25]), "=r"(r.u[26]), "=r"(r.u[27]), "=r"(r.u[28]), "=r"(r.u[29]), "=r"(r.u[30]),
+          "=r"(r.u[31])
+        : "r"(taddr)
+        : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tmem_tw_block_claim(TwRaw32 &r, cplx *tw) {
+    tmem_wait_ld(r.u);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        tw[k].re = __hiloint2double((int)r.u[4 * k + 1], (int)r.u[4 * k]);
+        tw[k].im = __hiloint2double((int)r.u[4 * k + 3], (int)r.u[4 * k + 2]);
+    }
+}
+constexpr uint32_t TMEM_TWT_COLS = 64;   // per warp: pass B at +0, pass C at +32
+
 }  // namespace fft
 }  // namespace tfhe

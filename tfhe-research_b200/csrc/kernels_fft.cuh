@@ -141,10 +141,16 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     // (warp / 4) of its 32 lanes (warp % 4): 32 for the exchanges of its transforms, 2 x 32 for the rows it publishes, and 48 more
     // behind those of all sub-teams for its derived twiddles
     uint32_t *tmem_ptr = claimed + K::NSLOT;
-    if constexpr (K::XCHG) {
-        static_assert(K::P * TMEM_SUB_COLS <= 512, "tensor-memory columns");
+    // TWT (P1): 256 columns, 64 per warp (warp / 4) of its lanes, for the derived twiddles of passes B and C
+    constexpr bool TWT = K::TWT && OWN_FIRST;
+    constexpr bool USE_TMEM = K::XCHG || TWT;
+    constexpr uint32_t TMEM_ALLOC = K::XCHG ? 512u : 256u;
+    static_assert(!TWT || ((K::THREADS / 32 + 3) / 4) * TMEM_TWT_COLS <= TMEM_ALLOC, "tensor-memory columns");
+    static_assert(!TWT || (K::F::NB_TW <= 8 && K::F::NC_TW <= 8), "one 32-column block per pass");
+    if constexpr (USE_TMEM) {
+        static_assert(!K::XCHG || K::P * TMEM_SUB_COLS <= 512, "tensor-memory columns");
         if (tid < 32) {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_ALLOC) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -152,6 +158,11 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     __syncthreads();   // the only CTA-wide barrier: teams are independent below
     uint32_t taddr = 0, tquarter = 0, pubsel = 0;   // own columns / first column of the team's lanes / publish buffer of the next level
     TmemTw twx = {};
+    uint32_t twt_cols = 0;
+    if constexpr (TWT) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        twt_cols = *tmem_ptr + ((((tid >> 5) & 3u) * 32u) << 16) + (tid >> 7) * TMEM_TWT_COLS;
+    }
     if constexpr (K::XCHG) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         tquarter = *tmem_ptr + ((team * 32u) << 16);
@@ -164,9 +175,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     }
 
     if (team >= active) {
-        if constexpr (K::XCHG) {   // warp 0 releases tensor memory once every warp has arrived here or at the end of the kernel
+        if constexpr (USE_TMEM) {   // warp 0 releases tensor memory once every warp has arrived here or at the end of the kernel
             if (active == 0) {
-                if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_ptr) : "memory");
+                if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_ptr), "n"(TMEM_ALLOC) : "memory");
             } else {
                 asm volatile("bar.arrive 15, %0;" ::"n"(K::THREADS) : "memory");
             }
@@ -198,6 +209,14 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     if constexpr (OWN_FIRST) {
         twB_base = pass_tw_base<C::QB>(twB, 1);
         twC_base = pass_tw_base<C::LOGE>(twC + t, C::T);
+        if constexpr (TWT) {   // derive once, keep in tensor memory: 14 FP64 operations per pass and 8 registers less
+            cplx tw[8];
+            derive_pass_tw<C::QB>(tw, twB_base);
+            tmem_tw_block_store<C::NB_TW>(twt_cols, tw);
+            derive_pass_tw<C::LOGE>(tw, twC_base);
+            tmem_tw_block_store<C::NC_TW>(twt_cols + 32u, tw);
+            tmem_wait_st();
+        }
     }
     // operands of the decomposed difference  minuend(p, (j - rot)) - subtrahend(p, j)
     const uint32_t *mbase = acc, *sbase = acc;
@@ -380,10 +399,23 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 } else {
                     if (!FIRST) team_bar_id(team_bar, K::TEAM_THREADS);   // the row published at the previous level has been read
                     store_A<C>(R.x, buf0, t);
-                    sub_sync();
-                    phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
-                    sub_sync();
-                    phase_F3v<K>(R, t, twC_base, buf1);
+                    if constexpr (TWT) {
+                        TwRaw32 raw;
+                        cplx tw[8];
+                        tmem_tw_block_request(raw, twt_cols);         // R.x is dead here: the request costs no registers
+                        sub_sync();
+                        tmem_tw_block_claim<C::NB_TW>(raw, tw);
+                        phase_F2w<K>(R, jbB, tw, buf0, buf1);
+                        tmem_tw_block_request(raw, twt_cols + 32u);
+                        sub_sync();
+                        tmem_tw_block_claim<C::NC_TW>(raw, tw);
+                        phase_F3w<K>(R, t, tw, buf1);
+                    } else {
+                        sub_sync();
+                        phase_F2v<K>(R, jbB, twB_base, buf0, buf1);
+                        sub_sync();
+                        phase_F3v<K>(R, t, twC_base, buf1);
+                    }
                 }
                 phase_xstore<K>(R, t, buf0);             // buf0 is free: every thread of the sub-team is past its loads from it
                 mac_slot(std::true_type{}, 0u);
@@ -491,6 +523,16 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         } else {
             if constexpr (K::XCHG) {
                 tmem_inv_rest(R.acc[0], R.acc[1], taddr, taddr + TMEM_PUB_COL + 32u * pubsel, twx);   // stages 7..3 of both limbs, exchanged through tensor memory: layout A
+            } else if constexpr (TWT) {
+                TwRaw32 raw;
+                cplx tw[8];
+                tmem_tw_block_request(raw, twt_cols + 32u);
+                tmem_tw_block_claim<C::NC_TW>(raw, tw);
+                phase_J1w<K>(R, t, tw, buf0, buf1);
+                tmem_tw_block_request(raw, twt_cols);             // the accumulators are stored: dead registers
+                sub_sync();
+                tmem_tw_block_claim<C::NB_TW>(raw, tw);
+                phase_J2aw<K>(R, jbB, tw, buf0, buf1);
             } else if constexpr (OWN_FIRST) {
                 phase_J1v<K>(R, t, twC_base, buf0, buf1);
                 sub_sync();
@@ -521,12 +563,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         for (int o = 16; o > 0; o >>= 1) maxfrac = fmax(maxfrac, __shfl_xor_sync(0xFFFFFFFFu, maxfrac, o));
         if (lane == 0) atomicMax(a.margin, (unsigned long long)__double_as_longlong(maxfrac));
     }
-    if constexpr (K::XCHG) {
+    if constexpr (USE_TMEM) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 15, %0;" ::"n"(K::THREADS) : "memory");   // every warp of the CTA (idle teams arrive before they exit)
         if (tid < 32) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(*tmem_ptr) : "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_ptr), "n"(TMEM_ALLOC) : "memory");
         }
     }
 }

@@ -185,8 +185,11 @@ int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
 #ifndef TFHE_FFT_P1_SINGLE
 #define TFHE_FFT_P1_SINGLE 0
 #endif
-using KF1 = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, false, TFHE_FFT_P1_SINGLE != 0>;   // production: a-priori exactness bound only
-using KF1C = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, true, TFHE_FFT_P1_SINGLE != 0>;   // + records the rounding margin (tests, validation)
+#ifndef TFHE_FFT_P1_TWT
+#define TFHE_FFT_P1_TWT 0   // 2: derived pass twiddles of P1 wait in tensor memory (bit-identical, measured neutral: 64.80 vs 64.93 ms -- P1 is bound by the shared-memory pipe, not by FP64 issue); 0: re-derived per pass
+#endif
+using KF1 = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, false, TFHE_FFT_P1_SINGLE != 0, 1, TFHE_FFT_NSLOT, TFHE_FFT_P1_TWT>;   // production: a-priori exactness bound only
+using KF1C = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, true, TFHE_FFT_P1_SINGLE != 0, 1, TFHE_FFT_NSLOT, TFHE_FFT_P1_TWT>;   // + records the rounding margin (tests, validation)
 #ifndef TFHE_FFT_CTS_P0
 #define TFHE_FFT_CTS_P0 4
 #endif
