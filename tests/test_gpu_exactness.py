@@ -216,12 +216,14 @@ def test_latency_configuration_same_bits_as_throughput_configuration(preset):
     bk.free(); ctx.close()
 
 
-def test_tensor_memory_exchange_same_bits_as_shared_memory_exchange():
+@pytest.mark.parametrize("preset", ["P0", "P1"])
+def test_tensor_memory_exchange_same_bits_as_shared_memory_exchange(preset):
     """N = 512 (the reference's default set, lib.rs:101-123): the throughput kernel exchanges the register passes of its transforms
-    through tensor memory (fft_tmem.cuh, another butterfly order and spectral layout, twiddles derived per lane).  Same bits as
+    through tensor memory (fft_tmem.cuh, another butterfly order and spectral layout, twiddles derived per lane); N = 1024 (P1): the
+    last three stages of every transform run on tensor-memory swaps inside each warp.  Same bits as
     the shared-memory kernel, the NTT path and the oracle -- at full n, over partially filled CTAs and several waves, with skipped
     steps -- and a rounding margin of the same size."""
-    p = T.TfheParams.preset("P0")
+    p = T.TfheParams.preset(preset)
     lwe_sk, glwe_sk, bsk, ksk = T.bootstrapping_key_gen(p, 0xB200)
     pm = 1 << p.log_p
     ctx = T.Context(p, 0, path=T.PATH_FFT)
@@ -235,7 +237,7 @@ def test_tensor_memory_exchange_same_bits_as_shared_memory_exchange():
     rng = np.random.default_rng(3)
     cts[9] = rng.integers(0, 1 << 32, p.n + 1, dtype=np.uint64).astype(np.uint32)   # not a valid encryption: any bits must agree
     margins = {}
-    for B in (1, 3, 150, 593, 700):
+    for B in (1, 3, 150, 445 if preset == "P1" else 593, 700):
         outs = {}
         for tm in (True, False):
             ctx.set_fft_exchange(tm)

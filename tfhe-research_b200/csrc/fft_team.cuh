@@ -147,6 +147,29 @@ template <class C> TFHE_HD void load_B(cplx *x, const cplx *buf, uint32_t jbB) {
     const cplx *b = buf + cphys<C>(jbB);
     static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = b[cphys<C>(e << C::QB)]; });
 }
+// ---- the one shared-memory exchange of the tensor-memory-tail transform (M = 512, T = 64; fft_tmem.cuh).  Layout A as above;
+// layout B'': registers <-> mid (j5 j4 j3), warp <-> j8, lane (L4..L0) <-> (j2 j1 j0 j6 j7) -- the bits the two tensor-memory swaps
+// take next, (j2 j1) and then j0, are the top lane bits.  Elements sit unpadded at swz(j) = j ^ (((j >> 6) & 3) << 1): a quarter-warp
+// covers 8 distinct 16-byte bank groups in layout A (lanes <-> j2 j1 j0) and in layout B'' (lanes <-> j0 j6 j7).
+TFHE_HD constexpr uint32_t swz9(uint32_t j) { return j ^ (((j >> 6) & 3u) << 1); }
+TFHE_HD constexpr uint32_t jbase_Bsw(uint32_t t) {   // t = warp << 5 | lane
+    return (((t >> 5) & 1u) << 8) | ((t & 1u) << 7) | (((t >> 1) & 1u) << 6) | (((t >> 4) & 1u) << 2) | (((t >> 3) & 1u) << 1) | ((t >> 2) & 1u);
+}
+TFHE_HD constexpr uint32_t hA_Bsw(uint32_t t) { return jbase_Bsw(t) >> 6; }
+template <class C> TFHE_HD void store_Asw(const cplx *x, cplx *buf, uint32_t t) {
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; buf[(e << C::LOGT) + (t ^ ((e & 3u) << 1))] = x[e]; });
+}
+template <class C> TFHE_HD void load_Asw(cplx *x, const cplx *buf, uint32_t t) {
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = buf[(e << C::LOGT) + (t ^ ((e & 3u) << 1))]; });
+}
+template <class C> TFHE_HD void store_Bsw(const cplx *x, cplx *buf, uint32_t jb_swz) {   // jb_swz = swz9(jbase_Bsw(t))
+    cplx *b = buf + jb_swz;
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; b[e << C::QB] = x[e]; });
+}
+template <class C> TFHE_HD void load_Bsw(cplx *x, const cplx *buf, uint32_t jb_swz) {
+    const cplx *b = buf + jb_swz;
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = b[e << C::QB]; });
+}
 template <class C> TFHE_HD void store_C(const cplx *x, cplx *buf, uint32_t t) {
     cplx *b = buf + cphys<C>(t << C::LOGE);
     static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; b[cphys<C>(e)] = x[e]; });
@@ -202,7 +225,8 @@ struct TwTablesF {
 // (small batches: latency) is bound by the round trip of each ring refill instead, and uses the idle shared memory for a deep ring.
 // XCHG: 0 = the register passes of a transform exchange through shared memory (store_A/load_B, ...); 1 = through tensor memory
 // (fft_tmem.cuh: warp-sized sub-teams, M = 256), which also changes the spectral layout of the stored key; 2 = shared-memory
-// exchanges with the derived twiddles of passes B and C kept in tensor memory instead of being re-derived in every pass.
+// exchanges with the derived twiddles of passes B and C kept in tensor memory instead of being re-derived in every pass;
+// 3 = the second shared-memory exchange and pass C replaced by tensor-memory swaps (another spectral layout of the key).
 template <int LOGN_, int LOGE_, int K_, int L_, int LOGB_, int CTS_, bool CHECK_ = true, bool SINGLE_BUF_ = false, int HALVES_ = 1, int NSLOT_ = TFHE_FFT_NSLOT, int XCHG_ = 0>
 struct FftPbsCfg {
     using F = FftCfg<LOGN_ - 1, LOGE_>;
@@ -211,7 +235,9 @@ struct FftPbsCfg {
     static constexpr int E = F::E, T = F::T;
     static constexpr int CTS = CTS_;                    // ciphertexts (teams) per CTA, sharing one key stream
     static constexpr bool CHECK = CHECK_, SINGLE_BUF = SINGLE_BUF_, XCHG = XCHG_ == 1;
-    static constexpr bool TWT = XCHG_ == 2;   // shared-memory exchanges, but a thread's derived pass twiddles wait in tensor memory (own-row-first loop)
+    static constexpr bool TWT = XCHG_ == 2;
+    static constexpr bool TAIL = XCHG_ == 3;  // M = 512, two warps per sub-team: pass A, ONE shared-memory exchange, pass B, then the last three stages with tensor-memory swaps inside each warp (fft_tmem.cuh)
+    static_assert(!TAIL || (LOGN_ == 10 && LOGE_ == 3 && !SINGLE_BUF_ && HALVES_ == 1), "tensor-memory tail: M = 512, 8 points per thread");   // shared-memory exchanges, but a thread's derived pass twiddles wait in tensor memory (own-row-first loop)
     static_assert(!XCHG || (LOGN_ == 9 && LOGE_ == 3 && !SINGLE_BUF_ && HALVES_ == 1 && CTS_ == 4 && K_ <= 3), "tensor-memory exchanges: M = 256, 8 points per thread, one warp per sub-team, one team per lane quarter");
     static constexpr int HALVES = HALVES_, EH = E / HALVES_, MH = M / HALVES_;   // points per thread / per polynomial in one slot
     static constexpr int WARPS_PER_SUB = T / 32, TEAM_THREADS = P * T, THREADS = CTS * TEAM_THREADS;
@@ -611,6 +637,14 @@ TFHE_HD void phase_J3r_regs(FftRegs<K> &r, uint32_t t, const cplx *twA, uint32_t
         acc_c[j] = accv[2 * e];
         acc_c[j + K::M] = accv[2 * e + 1];
     }
+}
+// the same after the swizzled exchange of the tensor-memory-tail transform
+template <class K>
+TFHE_HD void phase_J3r_sw(FftRegs<K> &r, uint32_t t, const cplx *twA, const cplx *buf0, const cplx *buf1, uint32_t *acc_c, uint32_t *accv, double &maxfrac) {
+    using C = typename K::F;
+    load_Asw<C>(r.acc[0], buf0, t);
+    load_Asw<C>(r.acc[1], buf1, t);
+    phase_J3r_regs<K>(r, t, twA, acc_c, accv, maxfrac);
 }
 // single-buffer inverse of ONE limb, in place in its accumulator registers:
 //   K1: pass C, store_C | barrier | K2a: load_B, pass B | barrier | K2b: store_B | barrier | K3: load_A, pass A

@@ -55,6 +55,12 @@ __host__ __device__ constexpr uint32_t tmem_slot_of_index(uint32_t j) {
     return r * 32u + lane;
 }
 
+// the same for layout F9 (M = 512): thread warp j8, lane (j7 j4 j3 j2 j1), register (j0 j6 j5) -> r * 64 + thread
+__host__ __device__ constexpr uint32_t tail9_slot_of_index(uint32_t j) {
+    const uint32_t th = (((j >> 8) & 1u) << 5) | (((j >> 7) & 1u) << 4) | ((j >> 1) & 15u), r = ((j & 1u) << 2) | (((j >> 6) & 1u) << 1) | ((j >> 5) & 1u);
+    return r * 64u + th;
+}
+
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // tcgen05.ld is asynchronous: its destination registers may only be read after tcgen05.wait::ld.  The words are passed through the
 // wait as in/out operands so that the compiler cannot schedule a use of them above it.
@@ -539,6 +545,127 @@ __device__ __forceinline__ void tmem_tw_block_claim(TwRaw32 &r, cplx *tw) {
     }
 }
 constexpr uint32_t TMEM_TWT_COLS = 64;   // per warp: pass B at +0, pass C at +32
+
+// ---- M = 512, two warps per sub-team (FftPbsCfg::TAIL).  Pass A and pass B run as in fft_team.cuh with ONE shared-memory exchange
+// between them (layout A -> layout B'': fft_team.cuh store_Asw / load_Bsw); the last three stages stay inside each warp:
+//   layout B''  warp j8, lane (j2 j1 j0 j6 j7)  regs (j5 j4 j3)   stages 3 4 5
+//   swap  ->    warp j8, lane (j0 j6 j7 j4 j3)  regs (j2 j1 j5)   stages 6 7      (TwoStageTw<4, 5>: j5 rides along, 3 bits above j2)
+//   swap  ->    warp j8, lane (j7 j4 j3 j2 j1)  regs (j0 j6 j5)   stage  8        = layout F9: the spectral layout of this path
+// A bit of the block index at position k (from the LSB) contributes the factor exp(2 pi i / 2^(k + 2)) to a twiddle, whatever the stage
+// (host_tables_fft.hpp fft_twiddle): j5 at stage 8 sits at k = 4 (root 2^6), j6 at k = 5 (root 2^7).
+template <int K0, int K1>   // roots contributed by register bit 0 / register bit 1
+struct LastStageTwT {
+    cplx w[2][2];   // [r0][r1]
+    __device__ __forceinline__ explicit LastStageTwT(const cplx base) {
+        w[0][0] = base;
+        w[1][0] = cmul_c(base, RootOfUnity<K0>::c, RootOfUnity<K0>::s);
+        w[0][1] = cmul_c(base, RootOfUnity<K1>::c, RootOfUnity<K1>::s);
+        w[1][1] = cmul_c(w[1][0], RootOfUnity<K1>::c, RootOfUnity<K1>::s);
+    }
+    __device__ __forceinline__ explicit LastStageTwT(const cplx (&d)[4]) {   // stored: w[1][0], w[0][1], w[1][1], base
+        w[0][0] = d[3];
+        w[1][0] = d[0];
+        w[0][1] = d[1];
+        w[1][1] = d[2];
+    }
+};
+struct TailTw {
+    cplx p67, p8;    // w(7, (j8 j7 j6 0 j4 j3 0)), w(8, (j8 j7 0 0 j4 j3 j2 j1)) of this thread
+    uint32_t cols;   // tensor-memory address of the stored copies (TFHE_TMEM_TAIL_TWSTORE): [0, 16) stages 6 7, [16, 32) stage 8
+};
+#ifndef TFHE_TMEM_TAIL_TWSTORE
+#define TFHE_TMEM_TAIL_TWSTORE 1
+#endif
+__device__ __forceinline__ void tmem_tail_tw_setup(TailTw &tw, uint32_t cols) {
+    tw.cols = cols;
+    const TwoStageTw<4, 5> a(tw.p67);
+    const LastStageTwT<6, 7> l(tw.p8);
+    tmem_store_cplx(cols + 0u, a.wb[1][0]);
+    tmem_store_cplx(cols + 4u, a.wa[0]);
+    tmem_store_cplx(cols + 8u, a.wa[1]);
+    tmem_store_cplx(cols + 12u, tw.p67);
+    tmem_store_cplx(cols + 16u, l.w[1][0]);
+    tmem_store_cplx(cols + 20u, l.w[0][1]);
+    tmem_store_cplx(cols + 24u, l.w[1][1]);
+    tmem_store_cplx(cols + 28u, tw.p8);
+    tmem_wait_st();
+}
+// table (host_tables_fft.hpp build_fft_tail_table): [0..31] by (j8 j7 j6 j4 j3), [32..95] by (j8 j7 j4 j3 j2 j1); t = warp << 5 | lane
+__device__ __forceinline__ TailTw load_tail_tw(const cplx *table, uint32_t t) {
+    const uint32_t w = t >> 5, l = t & 31u;
+    TailTw tw;
+    // after the first swap: lane (j0 j6 j7 j4 j3)
+    tw.p67 = table[(w << 4) | (((l >> 2) & 1u) << 3) | (((l >> 3) & 1u) << 2) | (l & 3u)];
+    // after the second swap: lane (j7 j4 j3 j2 j1)
+    tw.p8 = table[32u + ((w << 5) | l)];
+    tw.cols = 0;
+    return tw;
+}
+__device__ __forceinline__ void tmem_fwd_tail9(cplx (&x)[8], uint32_t taddr, const TailTw &tw) {
+#if TFHE_TMEM_TAIL_TWSTORE
+    TwRaw raw;
+    cplx d[4];
+    tmem_swap2_store(x, taddr);                             // regs (j2 j1 j5)
+    tmem_tw_request(raw, tw.cols);
+    tmem_wait_st();
+    tmem_swap2_load(x, taddr);
+    tmem_tw_claim(raw, d);
+    fwd_two_stages<4, 5>(x, TwoStageTw<4, 5>(d[3], d));     // stages 6, 7
+    rename_out(x);                                          // (j5 j2 j1)
+    tmem_swap2_store(x, taddr);                             // regs (j0 j6 j5)
+    tmem_tw_request(raw, tw.cols + 16u);
+    tmem_wait_st();
+    tmem_swap2_load(x, taddr);
+    tmem_tw_claim(raw, d);
+    const LastStageTwT<6, 7> l(d);
+#else
+    tmem_swap2(x, taddr);                                   // regs (j2 j1 j5)
+    fwd_two_stages<4, 5>(x, TwoStageTw<4, 5>(tw.p67));      // stages 6, 7
+    rename_out(x);                                          // (j5 j2 j1)
+    tmem_swap2(x, taddr);                                   // regs (j0 j6 j5)
+    const LastStageTwT<6, 7> l(tw.p8);
+#endif
+#pragma unroll
+    for (int r = 0; r < 4; r++) ct_bfly(x[r], x[r + 4], l.w[r & 1][(r >> 1) & 1]);   // stage 8
+}
+__device__ __forceinline__ void tmem_inv_tail9(cplx (&a)[8], cplx (&b)[8], uint32_t taddr, const TailTw &tw) {
+#if TFHE_TMEM_TAIL_TWSTORE
+    TwRaw raw;
+    cplx d[4];
+    tmem_tw_request(raw, tw.cols + 16u);
+    tmem_tw_claim(raw, d);
+    {
+        const LastStageTwT<6, 7> l(d);
+#else
+    {
+        const LastStageTwT<6, 7> l(tw.p8);
+#endif
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            gs_bfly(a[r], a[r + 4], l.w[r & 1][(r >> 1) & 1]);
+            gs_bfly(b[r], b[r + 4], l.w[r & 1][(r >> 1) & 1]);
+        }
+    }
+#if TFHE_TMEM_TAIL_TWSTORE
+    tmem_unswap2_store(a, taddr);                           // regs (j5 j2 j1)
+    tmem_unswap2_store(b, taddr + 32u);
+    tmem_tw_request(raw, tw.cols);
+    tmem_wait_st();
+    tmem_unswap2_load(a, taddr);
+    tmem_unswap2_load(b, taddr + 32u);
+    tmem_tw_claim(raw, d);
+    const TwoStageTw<4, 5> t2(d[3], d);
+#else
+    tmem_unswap2_pair(a, b, taddr, taddr + 32u);            // regs (j5 j2 j1)
+    const TwoStageTw<4, 5> t2(tw.p67);
+#endif
+    rename_in(a); rename_in(b);                             // (j2 j1 j5)
+    inv_two_stages<4, 5>(a, t2);
+    inv_two_stages<4, 5>(b, t2);
+    tmem_unswap2_pair(a, b, taddr, taddr + 32u);            // regs (j5 j4 j3): layout B''
+}
+constexpr uint32_t TMEM_TAIL_COLS = 64;   // per warp: 32 per accumulator of the paired inverse
+constexpr uint32_t TMEM_TAIL_TW_COLS = 32; // per warp, behind the swap columns of all warps of a lane quarter
 
 }  // namespace fft
 }  // namespace tfhe

@@ -51,5 +51,18 @@ inline void build_fft_tmem_table(std::vector<cplx> &out) {
     for (uint32_t i = 0; i < 32; i++) out.push_back(fft_twiddle(8, 7, i));         // w(7, (0 0 j5 j4 j3 j2 j1)), lane      = (j5 j4 j3 j2 j1)
 }
 
+// per-thread entries of the tensor-memory tail of the M = 512 transform (fft_tmem.cuh TailTw)
+inline void build_fft_tail_table(std::vector<cplx> &out) {
+    out.clear();
+    for (uint32_t i = 0; i < 32; i++) {   // i = (j8 j7 j6 j4 j3): w(7, (j8 j7 j6 0 j4 j3 0))
+        const uint32_t b = ((i >> 2) << 4) | ((i & 3u) << 1);
+        out.push_back(fft_twiddle(9, 7, b));
+    }
+    for (uint32_t i = 0; i < 64; i++) {   // i = (j8 j7 j4 j3 j2 j1): w(8, (j8 j7 0 0 j4 j3 j2 j1))
+        const uint32_t b = ((i >> 4) << 6) | (i & 15u);
+        out.push_back(fft_twiddle(9, 8, b));
+    }
+}
+
 }  // namespace fft
 }  // namespace tfhe

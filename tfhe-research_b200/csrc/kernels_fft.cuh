@@ -143,8 +143,11 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     uint32_t *tmem_ptr = claimed + K::NSLOT;
     // TWT (P1): 256 columns, 64 per warp (warp / 4) of its lanes, for the derived twiddles of passes B and C
     constexpr bool TWT = K::TWT && OWN_FIRST;
-    constexpr bool USE_TMEM = K::XCHG || TWT;
-    constexpr uint32_t TMEM_ALLOC = K::XCHG ? 512u : 256u;
+    // TAIL (P1): 256 columns, 64 per warp, for the tensor-memory swaps of the last three stages of every transform
+    constexpr bool TAIL = K::TAIL && OWN_FIRST;
+    static_assert(!TAIL || ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL_COLS + TMEM_TAIL_TW_COLS) <= 512, "tensor-memory columns");
+    constexpr bool USE_TMEM = K::XCHG || TWT || TAIL;
+    constexpr uint32_t TMEM_ALLOC = (K::XCHG || TAIL) ? 512u : 256u;
     static_assert(!TWT || ((K::THREADS / 32 + 3) / 4) * TMEM_TWT_COLS <= TMEM_ALLOC, "tensor-memory columns");
     static_assert(!TWT || (K::F::NB_TW <= 8 && K::F::NC_TW <= 8), "one 32-column block per pass");
     if constexpr (USE_TMEM) {
@@ -159,9 +162,18 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     uint32_t taddr = 0, tquarter = 0, pubsel = 0;   // own columns / first column of the team's lanes / publish buffer of the next level
     TmemTw twx = {};
     uint32_t twt_cols = 0;
-    if constexpr (TWT) {
+    if constexpr (TWT || TAIL) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         twt_cols = *tmem_ptr + ((((tid >> 5) & 3u) * 32u) << 16) + (tid >> 7) * TMEM_TWT_COLS;
+        static_assert(TMEM_TWT_COLS == TMEM_TAIL_COLS, "same column budget per warp");
+    }
+    TailTw tailtw = {};
+    if constexpr (TAIL) {
+        tailtw = load_tail_tw(a.tw.twX, t);
+#if TFHE_TMEM_TAIL_TWSTORE
+        if (team < active)
+            tmem_tail_tw_setup(tailtw, *tmem_ptr + ((((tid >> 5) & 3u) * 32u) << 16) + ((K::THREADS / 32 + 3) / 4) * TMEM_TAIL_COLS + (tid >> 7) * TMEM_TAIL_TW_COLS);
+#endif
     }
     if constexpr (K::XCHG) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -206,7 +218,25 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     // (P1: 71.4 -> 69.8 ms); with the ring-order loop the 8 registers cost more than the loads after every barrier
     // (P1: 74.8 -> 79.9 ms, P0 and the BMMP variant alike), so that loop fetches them per pass.
     cplx twB_base = {}, twC_base = {};
-    if constexpr (OWN_FIRST) {
+    uint32_t jb_swz = 0;
+#ifndef TFHE_TMEM_TAIL_TWB
+#define TFHE_TMEM_TAIL_TWB 1
+#endif
+    uint32_t tail_twb_cols = 0;
+    if constexpr (TAIL) {   // pass B of layout B'': the table row of this thread's (j8 j7 j6); no pass C
+        twB_base = pass_tw_base<C::QB>(a.tw.twB + hA_Bsw(t) * C::NB_TW, 1);
+        jb_swz = swz9(jbase_Bsw(t));
+#if TFHE_TMEM_TAIL_TWB
+        {   // its derived twiddles wait in tensor memory as well (one more 32-column block per warp)
+            static_assert(((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL_COLS + TMEM_TAIL_TW_COLS + 32u) <= 512, "tensor-memory columns");
+            tail_twb_cols = *tmem_ptr + ((((tid >> 5) & 3u) * 32u) << 16) + ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL_COLS + TMEM_TAIL_TW_COLS) + (tid >> 7) * 32u;
+            cplx tw[8];
+            derive_pass_tw<C::QB>(tw, twB_base);
+            tmem_tw_block_store<C::NB_TW>(tail_twb_cols, tw);
+            tmem_wait_st();
+        }
+#endif
+    } else if constexpr (OWN_FIRST) {
         twB_base = pass_tw_base<C::QB>(twB, 1);
         twC_base = pass_tw_base<C::LOGE>(twC + t, C::T);
         if constexpr (TWT) {   // derive once, keep in tensor memory: 14 FP64 operations per pass and 8 registers less
@@ -396,6 +426,29 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                     it += (uint32_t)K::P;
                     pubsel ^= 1u;
                     return;
+                } else if constexpr (TAIL) {
+                    store_Asw<C>(R.x, buf1, t);              // the one shared-memory exchange goes through buf1: buf0 still holds the published row
+#if TFHE_TMEM_TAIL_TWB
+                    {
+                        TwRaw32 raw;
+                        cplx tw[8];
+                        tmem_tw_block_request(raw, tail_twb_cols);   // R.x is dead here
+                        sub_sync();
+                        tmem_tw_block_claim<C::NB_TW>(raw, tw);
+                        load_Bsw<C>(R.x, buf1, jb_swz);
+                        fwd_pass<C::LOGE, C::QB>(R.x, tw);
+                    }
+#else
+                    sub_sync();
+                    {
+                        cplx tw[C::NB_TW];
+                        derive_pass_tw<C::QB>(tw, twB_base);
+                        load_Bsw<C>(R.x, buf1, jb_swz);
+                        fwd_pass<C::LOGE, C::QB>(R.x, tw);
+                    }
+#endif
+                    tmem_fwd_tail9(R.x, twt_cols, tailtw);   // stages 6..8 inside the warp: layout F9
+                    if (!FIRST) team_bar_id(team_bar, K::TEAM_THREADS);   // the row published at the previous level has been read
                 } else {
                     if (!FIRST) team_bar_id(team_bar, K::TEAM_THREADS);   // the row published at the previous level has been read
                     store_A<C>(R.x, buf0, t);
@@ -523,6 +576,19 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         } else {
             if constexpr (K::XCHG) {
                 tmem_inv_rest(R.acc[0], R.acc[1], taddr, taddr + TMEM_PUB_COL + 32u * pubsel, twx);   // stages 7..3 of both limbs, exchanged through tensor memory: layout A
+            } else if constexpr (TAIL) {
+                tmem_inv_tail9(R.acc[0], R.acc[1], twt_cols, tailtw);   // stages 8..6 of both limbs inside the warp: layout B''
+#if TFHE_TMEM_TAIL_TWB
+                TwRaw32 raw;
+                cplx tw[8];
+                tmem_tw_block_request(raw, tail_twb_cols);
+                tmem_tw_block_claim<C::NB_TW>(raw, tw);
+#else
+                cplx tw[C::NB_TW];
+                derive_pass_tw<C::QB>(tw, twB_base);
+#endif
+                inv_pass<C::LOGE, C::QB>(R.acc[0], tw);
+                inv_pass<C::LOGE, C::QB>(R.acc[1], tw);
             } else if constexpr (TWT) {
                 TwRaw32 raw;
                 cplx tw[8];
@@ -545,6 +611,11 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             }
             if constexpr (K::XCHG) {
                 phase_J3r_regs<K>(R, t, a.tw.twA, acc + sub * K::N, accv, maxfrac);
+            } else if constexpr (TAIL) {
+                store_Bsw<C>(R.acc[0], buf0, jb_swz);
+                store_Bsw<C>(R.acc[1], buf1, jb_swz);
+                sub_sync();
+                phase_J3r_sw<K>(R, t, a.tw.twA, buf0, buf1, acc + sub * K::N, accv, maxfrac);
             } else {
                 sub_sync();
                 phase_J2b<K>(R, jbB, buf0, buf1);
@@ -581,6 +652,15 @@ __global__ void bsk_fft_reslot_kernel(const cplx *__restrict__ in, cplx *__restr
     const uint32_t idx = threadIdx.x;                    // position in slot order: e * 32 + t
     const uint32_t j = ((idx & 31u) << 3) | (idx >> 5);   // the point it holds
     out[poly * 256 + tmem_slot_of_index(j)] = in[poly * 256 + idx];
+}
+
+// the same for the tensor-memory-tail path (M = 512): slot order (point (t << 3) | e at e * 64 + t) -> layout F9
+__global__ void bsk_fft_reslot9_kernel(const cplx *__restrict__ in, cplx *__restrict__ out, size_t polys) {
+    const size_t poly = blockIdx.x;
+    if (poly >= polys) return;
+    const uint32_t idx = threadIdx.x;                    // position in slot order: e * 64 + t
+    const uint32_t j = ((idx & 63u) << 3) | (idx >> 6);   // the point it holds
+    out[poly * 512 + tail9_slot_of_index(j)] = in[poly * 512 + idx];
 }
 
 // ------------------------------------------------------------------------------------------ key transform

@@ -189,7 +189,10 @@ int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
 #define TFHE_FFT_P1_TWT 0   // 2: derived pass twiddles of P1 wait in tensor memory (bit-identical, measured neutral: 64.80 vs 64.93 ms -- P1 is bound by the shared-memory pipe, not by FP64 issue); 0: re-derived per pass
 #endif
 using KF1 = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, false, TFHE_FFT_P1_SINGLE != 0, 1, TFHE_FFT_NSLOT, TFHE_FFT_P1_TWT>;   // production: a-priori exactness bound only
-using KF1C = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, true, TFHE_FFT_P1_SINGLE != 0, 1, TFHE_FFT_NSLOT, TFHE_FFT_P1_TWT>;   // + records the rounding margin (tests, validation)
+using KF1C = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, true, TFHE_FFT_P1_SINGLE != 0, 1, TFHE_FFT_NSLOT, TFHE_FFT_P1_TWT>;
+// P1 with the last three stages of every transform in tensor memory (one shared-memory exchange instead of two; fft_tmem.cuh tail9)
+using KF1T = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, false, false, 1, TFHE_FFT_NSLOT, 3>;
+using KF1TC = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true, false, 1, TFHE_FFT_NSLOT, 3>;   // + records the rounding margin (tests, validation)
 #ifndef TFHE_FFT_CTS_P0
 #define TFHE_FFT_CTS_P0 4
 #endif
@@ -426,7 +429,10 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
             if (a.mode == 0 && bk->d_bsk_fft_x && ctx->fft_tmem && fft_smem_bytes<KF0T>(a.n) <= 227 * 1024)
                 return ctx->fft_check ? launch_pbs_fft_t<KF0TC>(ctx, a, bk->d_bsk_fft_x) : launch_pbs_fft_t<KF0T>(ctx, a, bk->d_bsk_fft_x);
             return ctx->fft_check ? launch_pbs_fft_t<KF0C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF0>(ctx, a, bk->d_bsk_fft);
-        case 1: return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
+        case 1:
+            if (a.mode == 0 && bk->d_bsk_fft_x && ctx->fft_tmem && fft_smem_bytes<KF1T>(a.n) <= 227 * 1024)
+                return ctx->fft_check ? launch_pbs_fft_t<KF1TC>(ctx, a, bk->d_bsk_fft_x) : launch_pbs_fft_t<KF1T>(ctx, a, bk->d_bsk_fft_x);
+            return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
         case 2: return ctx->fft_check ? launch_pbs_fft_t<KF2C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF2>(ctx, a, bk->d_bsk_fft);
         }
         return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
@@ -687,6 +693,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         for (size_t i = 0; i < ft.A.size(); i++) ctx->ftw.twA[i] = ft.A[i];
         std::vector<fft::cplx> fx;
         if (logm == 8) fft::build_fft_tmem_table(fx);
+        if (logm == 9 && floge == 3) fft::build_fft_tail_table(fx);
         const std::vector<fft::cplx> *fsrc[4] = {&ft.B, &ft.C, &ft.Z, &fx};
         for (int i = 0; i < 4; i++) {
             if (fsrc[i]->empty()) continue;
@@ -821,11 +828,12 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     if (e != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
     else if (bk->path == TFHE_PATH_FFT) {
         rc = launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, ctx->n(), 1);
-        if (rc == TFHE_OK && ctx->pbs_id == 0 && ctx->fft_tmem) {   // second copy in the order of the tensor-memory-exchange kernel
+        if (rc == TFHE_OK && (ctx->pbs_id == 0 || (ctx->pbs_id == 1 && TFHE_FFT_P1_LOGE == 3)) && ctx->fft_tmem) {   // second copy in the order of the tensor-memory kernels
             if ((e = cudaMalloc(&bk->d_bsk_fft_x, fft_key_bytes(ctx))) != cudaSuccess) rc = fail(ctx, TFHE_E_OOM, cudaGetErrorString(e));
             else {
-                const size_t polys = fft_key_bytes(ctx) / (256 * sizeof(fft::cplx));
-                fft::bsk_fft_reslot_kernel<<<(unsigned)polys, 256, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, polys);
+                const size_t M = ctx->N() / 2, polys = fft_key_bytes(ctx) / (M * sizeof(fft::cplx));
+                if (ctx->pbs_id == 0) fft::bsk_fft_reslot_kernel<<<(unsigned)polys, 256, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, polys);
+                else fft::bsk_fft_reslot9_kernel<<<(unsigned)polys, 512, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, polys);
                 ctx->launches++;
                 if ((e = cudaGetLastError()) != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
             }
