@@ -141,10 +141,12 @@ int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on);
  *   0            always the throughput configuration (2-4 ciphertexts per CTA, two-slot ring).
  * Same bits in every mode. */
 int tfhe_ctx_set_latency_config(tfhe_ctx *ctx, int mode);
-/* FFT path, N = 512 (the reference's default set), throughput kernel: where the register passes of the transforms exchange their
- * data.  1 (default; env TFHE_B200_FFT_TMEM=0|1): tensor memory (tcgen05.st / tcgen05.ld of different shapes transpose a warp's
- * registers on a data path of their own, fft_tmem.cuh) -- keys uploaded while this is on carry a second copy of the transformed
- * BSK in that kernel's spectral order; 0: shared memory.  Switching it on only affects keys uploaded afterwards.  Same bits. */
+/* FFT path, throughput kernels of N = 512 (the reference's default set) and N = 1024: where the register passes of the transforms
+ * exchange their data.  1 (default; env TFHE_B200_FFT_TMEM=0|1): tensor memory -- tcgen05.st / tcgen05.ld of different shapes transpose a
+ * warp's registers on a data path of their own (fft_tmem.cuh); N = 512 moves every exchange and the published rows there, N = 1024 the
+ * last three stages of every transform (one shared-memory exchange instead of two).  Keys uploaded while this is on carry a second
+ * copy of the transformed BSK in that kernel's spectral order.  0: shared memory.  Switching it on only affects keys uploaded
+ * afterwards.  Same bits. */
 int tfhe_ctx_set_fft_exchange(tfhe_ctx *ctx, int tensor_memory);
 int tfhe_fft_rounding_margin(tfhe_ctx *ctx, double *out);
 

@@ -170,6 +170,26 @@ template <class C> TFHE_HD void load_Bsw(cplx *x, const cplx *buf, uint32_t jb_s
     const cplx *b = buf + jb_swz;
     static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = b[e << C::QB]; });
 }
+// ---- the same for M = 1024 at 16 points per thread.  Layout B''16: registers <-> (j5 j4 j3 j2), warp <-> j9, lane (L4..L0) <->
+// (j1 j0 j8 j7 j6); elements at swz10(j) = j ^ ((j >> 6) & 7).  Bit 2 of that XOR (j8, a thread bit) flips register bit j2: a thread
+// addresses its even and its odd registers from two bases.
+TFHE_HD constexpr uint32_t swz10(uint32_t j) { return j ^ ((j >> 6) & 7u); }
+TFHE_HD constexpr uint32_t jbase_Bsw16(uint32_t t) {   // t = warp << 5 | lane
+    return (((t >> 5) & 1u) << 9) | (((t >> 2) & 1u) << 8) | (((t >> 1) & 1u) << 7) | ((t & 1u) << 6) | (((t >> 4) & 1u) << 1) | ((t >> 3) & 1u);
+}
+template <class C> TFHE_HD void store_Asw16(const cplx *x, cplx *buf, uint32_t t) {
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; buf[(e << C::LOGT) + (t ^ (e & 7u))] = x[e]; });
+}
+template <class C> TFHE_HD void load_Asw16(cplx *x, const cplx *buf, uint32_t t) {
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = buf[(e << C::LOGT) + (t ^ (e & 7u))]; });
+}
+// even / odd: buf + swz10(jbase) for register 0, and the same with bit 2 flipped back for the odd registers (see above)
+template <class C> TFHE_HD void store_Bsw16(const cplx *x, cplx *even, cplx *odd) {
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; ((e & 1u) ? odd : even)[(e >> 1) << 3] = x[e]; });
+}
+template <class C> TFHE_HD void load_Bsw16(cplx *x, const cplx *even, const cplx *odd) {
+    static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; x[e] = ((e & 1u) ? odd : even)[(e >> 1) << 3]; });
+}
 template <class C> TFHE_HD void store_C(const cplx *x, cplx *buf, uint32_t t) {
     cplx *b = buf + cphys<C>(t << C::LOGE);
     static_for<0, C::E>([&](auto ei) { constexpr uint32_t e = decltype(ei)::value; b[cphys<C>(e)] = x[e]; });
@@ -237,7 +257,8 @@ struct FftPbsCfg {
     static constexpr bool CHECK = CHECK_, SINGLE_BUF = SINGLE_BUF_, XCHG = XCHG_ == 1;
     static constexpr bool TWT = XCHG_ == 2;
     static constexpr bool TAIL = XCHG_ == 3;  // M = 512, two warps per sub-team: pass A, ONE shared-memory exchange, pass B, then the last three stages with tensor-memory swaps inside each warp (fft_tmem.cuh)
-    static_assert(!TAIL || (LOGN_ == 10 && LOGE_ == 3 && !SINGLE_BUF_ && HALVES_ == 1), "tensor-memory tail: M = 512, 8 points per thread");   // shared-memory exchanges, but a thread's derived pass twiddles wait in tensor memory (own-row-first loop)
+    static_assert(!TAIL || (LOGN_ == 10 && LOGE_ == 3 && !SINGLE_BUF_ && HALVES_ == 1) || (LOGN_ == 11 && LOGE_ == 4 && SINGLE_BUF_), "tensor-memory tail: M = 512 at 8 points per thread, or M = 1024 at 16 points per thread with the single exchange buffer");
+    static constexpr bool TAIL16 = TAIL && LOGE_ == 4;   // shared-memory exchanges, but a thread's derived pass twiddles wait in tensor memory (own-row-first loop)
     static_assert(!XCHG || (LOGN_ == 9 && LOGE_ == 3 && !SINGLE_BUF_ && HALVES_ == 1 && CTS_ == 4 && K_ <= 3), "tensor-memory exchanges: M = 256, 8 points per thread, one warp per sub-team, one team per lane quarter");
     static constexpr int HALVES = HALVES_, EH = E / HALVES_, MH = M / HALVES_;   // points per thread / per polynomial in one slot
     static constexpr int WARPS_PER_SUB = T / 32, TEAM_THREADS = P * T, THREADS = CTS * TEAM_THREADS;

@@ -61,6 +61,10 @@ __host__ __device__ constexpr uint32_t tail9_slot_of_index(uint32_t j) {
     return r * 64u + th;
 }
 
+// the same for layout F10 (M = 1024, 16 points per thread): thread warp j9, lane (j8 j7 j6 j3 j2), register (j5 j1 j0 j4)
+__host__ __device__ constexpr uint32_t tail10_thread_of_index(uint32_t j) { return (((j >> 9) & 1u) << 5) | (((j >> 6) & 7u) << 2) | ((j >> 2) & 3u); }
+__host__ __device__ constexpr uint32_t tail10_reg_of_index(uint32_t j) { return (((j >> 5) & 1u) << 3) | (((j >> 1) & 1u) << 2) | ((j & 1u) << 1) | ((j >> 4) & 1u); }
+
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // tcgen05.ld is asynchronous: its destination registers may only be read after tcgen05.wait::ld.  The words are passed through the
 // wait as in/out operands so that the compiler cannot schedule a use of them above it.
@@ -666,6 +670,73 @@ __device__ __forceinline__ void tmem_inv_tail9(cplx (&a)[8], cplx (&b)[8], uint3
 }
 constexpr uint32_t TMEM_TAIL_COLS = 64;   // per warp: 32 per accumulator of the paired inverse
 constexpr uint32_t TMEM_TAIL_TW_COLS = 32; // per warp, behind the swap columns of all warps of a lane quarter
+
+// ---- M = 1024, 16 points per thread, two warps per sub-team (FftPbsCfg::TAIL16).  Pass A (stages 0..3) -> ONE shared-memory exchange
+// (fft_team.cuh store_Asw16 / load_Bsw16) -> pass B'' (stages 4..7 on registers (j5 j4 j3 j2)) -> one swap inside the warp -> stages 8, 9:
+//   layout B''16  warp j9, lane (j1 j0 j8 j7 j6)  regs (j5; j4 j3 j2)
+//   swap  ->      warp j9, lane (j8 j7 j6 j3 j2)  regs (j5; j1 j0 j4)   stages 8 9     = layout F10
+// The 16 registers are two halves (j5 = 0 / 1) swapped side by side in 2 x 32 columns; each half is the 8-register pass of the M = 256 /
+// 512 kernels with j4 riding along (TwoStageTw<4, 5>), and j5 contributes the root 2^6 to the stage-9 twiddle of its half.
+struct Tail16Tw {
+    cplx pB;         // w(7, hA << 3): base of pass B''
+    cplx p9;         // w(9, (j9 j8 j7 j6 0 0 j3 j2 0)): base of the last two stages, half j5 = 0
+    uint32_t cols;   // tensor-memory address of the parked stage-8/9 twiddles: 2 halves x (wb[1][0], wa[0], wa[1], base) = 32 columns
+};
+// table (host_tables_fft.hpp build_fft_tail16_table): [0..15] by hA = (j9 j8 j7 j6), [16..79] by (j9 j8 j7 j6 j3 j2); t = warp << 5 | lane
+__device__ __forceinline__ Tail16Tw load_tail16_tw(const cplx *table, uint32_t t, uint32_t hA) {
+    Tail16Tw tw;
+    tw.pB = table[hA];
+    tw.p9 = table[16u + t];   // after the swap: warp j9, lane (j8 j7 j6 j3 j2)
+    tw.cols = 0;
+    return tw;
+}
+__device__ __forceinline__ void tmem_tail16_tw_setup(Tail16Tw &tw, uint32_t cols) {
+    tw.cols = cols;
+    const cplx b1 = cmul_c(tw.p9, RootOfUnity<6>::c, RootOfUnity<6>::s);
+    const TwoStageTw<4, 5> h0(tw.p9), h1(b1);
+    tmem_store_cplx(cols + 0u, h0.wb[1][0]);
+    tmem_store_cplx(cols + 4u, h0.wa[0]);
+    tmem_store_cplx(cols + 8u, h0.wa[1]);
+    tmem_store_cplx(cols + 12u, tw.p9);
+    tmem_store_cplx(cols + 16u, h1.wb[1][0]);
+    tmem_store_cplx(cols + 20u, h1.wa[0]);
+    tmem_store_cplx(cols + 24u, h1.wa[1]);
+    tmem_store_cplx(cols + 28u, b1);
+    tmem_wait_st();
+}
+__device__ __forceinline__ void tmem_fwd_tail16(cplx (&x)[16], uint32_t taddr, const Tail16Tw &tw) {
+    cplx(&lo)[8] = *reinterpret_cast<cplx(*)[8]>(&x[0]);
+    cplx(&hi)[8] = *reinterpret_cast<cplx(*)[8]>(&x[8]);
+    TwRaw32 raw;
+    cplx d[8];
+    tmem_swap2_store(lo, taddr);
+    tmem_swap2_store(hi, taddr + 32u);
+    tmem_tw_block_request(raw, tw.cols);      // x is dead here
+    tmem_wait_st();
+    tmem_swap2_load(lo, taddr);
+    tmem_swap2_load(hi, taddr + 32u);
+    tmem_tw_block_claim<8>(raw, d);
+    const cplx d0[4] = {d[0], d[1], d[2], d[3]}, d1[4] = {d[4], d[5], d[6], d[7]};
+    fwd_two_stages<4, 5>(lo, TwoStageTw<4, 5>(d0[3], d0));   // stages 8, 9, half j5 = 0
+    fwd_two_stages<4, 5>(hi, TwoStageTw<4, 5>(d1[3], d1));   // half j5 = 1
+}
+__device__ __forceinline__ void tmem_inv_tail16(cplx (&x)[16], uint32_t taddr, const Tail16Tw &tw) {
+    cplx(&lo)[8] = *reinterpret_cast<cplx(*)[8]>(&x[0]);
+    cplx(&hi)[8] = *reinterpret_cast<cplx(*)[8]>(&x[8]);
+    TwRaw32 raw;
+    cplx d[8];
+    tmem_tw_block_request(raw, tw.cols);
+    tmem_tw_block_claim<8>(raw, d);
+    const cplx d0[4] = {d[0], d[1], d[2], d[3]}, d1[4] = {d[4], d[5], d[6], d[7]};
+    inv_two_stages<4, 5>(lo, TwoStageTw<4, 5>(d0[3], d0));
+    inv_two_stages<4, 5>(hi, TwoStageTw<4, 5>(d1[3], d1));
+    tmem_unswap2_store(lo, taddr);
+    tmem_unswap2_store(hi, taddr + 32u);
+    tmem_wait_st();
+    tmem_unswap2_load(lo, taddr);
+    tmem_unswap2_load(hi, taddr + 32u);   // regs (j5; j4 j3 j2): layout B''16
+}
+constexpr uint32_t TMEM_TAIL16_COLS = 64, TMEM_TAIL16_TW_COLS = 32;   // per warp
 
 }  // namespace fft
 }  // namespace tfhe

@@ -64,5 +64,15 @@ inline void build_fft_tail_table(std::vector<cplx> &out) {
     }
 }
 
+// per-thread entries of the M = 1024 transform with a tensor-memory tail (fft_tmem.cuh Tail16Tw)
+inline void build_fft_tail16_table(std::vector<cplx> &out) {
+    out.clear();
+    for (uint32_t hA = 0; hA < 16; hA++) out.push_back(fft_twiddle(10, 7, hA << 3));   // pass B'': stages 4..7, block hA
+    for (uint32_t i = 0; i < 64; i++) {   // i = (j9 j8 j7 j6 j3 j2): w(9, (j9 j8 j7 j6 0 0 j3 j2 0))
+        const uint32_t b = ((i >> 2) << 5) | ((i & 3u) << 1);
+        out.push_back(fft_twiddle(10, 9, b));
+    }
+}
+
 }  // namespace fft
 }  // namespace tfhe

@@ -144,9 +144,12 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     // TWT (P1): 256 columns, 64 per warp (warp / 4) of its lanes, for the derived twiddles of passes B and C
     constexpr bool TWT = K::TWT && OWN_FIRST;
     // TAIL (P1): 256 columns, 64 per warp, for the tensor-memory swaps of the last three stages of every transform
-    constexpr bool TAIL = K::TAIL && OWN_FIRST;
+    constexpr bool TAIL = K::TAIL && !K::TAIL16 && OWN_FIRST;
+    // TAIL16 (N = 2048): ring-order loop, single exchange buffer; 96 columns per warp (64 swap + 32 parked twiddles)
+    constexpr bool TAIL16 = K::TAIL16 && !OWN_FIRST && !BMMP;
+    static_assert(!TAIL16 || ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL16_COLS + TMEM_TAIL16_TW_COLS) <= 256, "tensor-memory columns");
     static_assert(!TAIL || ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL_COLS + TMEM_TAIL_TW_COLS) <= 512, "tensor-memory columns");
-    constexpr bool USE_TMEM = K::XCHG || TWT || TAIL;
+    constexpr bool USE_TMEM = K::XCHG || TWT || TAIL || TAIL16;
     constexpr uint32_t TMEM_ALLOC = (K::XCHG || TAIL) ? 512u : 256u;
     static_assert(!TWT || ((K::THREADS / 32 + 3) / 4) * TMEM_TWT_COLS <= TMEM_ALLOC, "tensor-memory columns");
     static_assert(!TWT || (K::F::NB_TW <= 8 && K::F::NC_TW <= 8), "one 32-column block per pass");
@@ -219,6 +222,19 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     // (P1: 74.8 -> 79.9 ms, P0 and the BMMP variant alike), so that loop fetches them per pass.
     cplx twB_base = {}, twC_base = {};
     uint32_t jb_swz = 0;
+    Tail16Tw t16 = {};
+    uint32_t t16_swap = 0;
+    cplx *b16_even = nullptr, *b16_odd = nullptr;   // this thread's even / odd registers in layout B''16 (fft_team.cuh store_Bsw16)
+    if constexpr (TAIL16) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t jb = jbase_Bsw16(t), x3 = (jb >> 6) & 7u, low = jb ^ (x3 & 3u), j8 = (x3 >> 2) & 1u;
+        b16_even = buf0 + low + (j8 ? 4u : 0u);
+        b16_odd = buf0 + low + (j8 ? 0u : 4u);
+        const uint32_t q0 = *tmem_ptr + ((((tid >> 5) & 3u) * 32u) << 16);
+        t16_swap = q0 + (tid >> 7) * TMEM_TAIL16_COLS;
+        t16 = load_tail16_tw(a.tw.twX, t, jb >> 6);
+        tmem_tail16_tw_setup(t16, q0 + ((K::THREADS / 32 + 3) / 4) * TMEM_TAIL16_COLS + (tid >> 7) * TMEM_TAIL16_TW_COLS);
+    }
 #ifndef TFHE_TMEM_TAIL_TWB
 #define TFHE_TMEM_TAIL_TWB 1
 #endif
@@ -500,9 +516,23 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 else if constexpr (ACC_REG) phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j, int k) { return rot_coeff(mbase + pp * K::N, j, rot, K::LOGN) - accv[k]; });
                 else phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
+                if constexpr (TAIL16) {
+                    store_Asw16<C>(R.x, buf0, t);        // the one shared-memory exchange
+                    sub_sync();
+                    {
+                        cplx tw[15];
+                        derive_pass_tw<4>(tw, t16.pB);
+                        load_Bsw16<C>(R.x, b16_even, b16_odd);
+                        fwd_pass<4, 4>(R.x, tw);         // stages 4..7
+                    }
+                    tmem_fwd_tail16(R.x, t16_swap, t16);  // stages 8, 9 inside the warp: layout F10
+                    sub_sync();                          // every thread of the sub-team is past its loads from buf0
+                } else {
                 store_A<C>(R.x, buf0, t);
                 sub_sync();
-                if constexpr (K::SINGLE_BUF) {           // one buffer: a barrier between every load and the next store
+                }
+                if constexpr (TAIL16) {
+                } else if constexpr (K::SINGLE_BUF) {           // one buffer: a barrier between every load and the next store
                     phase_F2a<K>(R, jbB, twB, buf0);
                     sub_sync();
                     phase_F2b<K>(R, jbB, buf0);
@@ -555,7 +585,39 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         }
 #if !(TFHE_FFT_ABLATE & 16)
         // inverse transforms of this sub-team's column: the low- and high-limb products together (fft_team.cuh phase_J*)
-        if constexpr (K::SINGLE_BUF) {   // one limb after the other through the single buffer
+        if constexpr (TAIL16) {          // one limb after the other: tail in tensor memory, pass B'', the one exchange, pass A
+            uint32_t lo[2 * K::E];
+            static_for<0, 2>([&](auto li) {
+                constexpr int LIMB = decltype(li)::value;
+                tmem_inv_tail16(R.acc[LIMB], t16_swap, t16);
+                {
+                    cplx tw[15];
+                    derive_pass_tw<4>(tw, t16.pB);
+                    inv_pass<4, 4>(R.acc[LIMB], tw);
+                }
+                if constexpr (LIMB == 1) sub_sync();   // the low limb's loads from buf0 are done
+                store_Bsw16<C>(R.acc[LIMB], b16_even, b16_odd);
+                sub_sync();
+                load_Asw16<C>(R.acc[LIMB], buf0, t);
+                inv_pass<C::LOGE, C::LOGE>(R.acc[LIMB], a.tw.twA);
+                if constexpr (LIMB == 0) {
+#pragma unroll
+                    for (int e = 0; e < K::E; e++) {
+                        lo[2 * e] = round_u32<K::CHECK>(R.acc[0][e].re, maxfrac);
+                        lo[2 * e + 1] = round_u32<K::CHECK>(R.acc[0][e].im, maxfrac);
+                    }
+                } else {
+                    uint32_t *acc_c = acc + sub * K::N;
+#pragma unroll
+                    for (int e = 0; e < K::E; e++) {
+                        const uint32_t j = ((uint32_t)e << C::LOGT) | t;
+                        acc_c[j] += lo[2 * e] + (round_u32<K::CHECK>(R.acc[1][e].re, maxfrac) << 16);
+                        acc_c[j + K::M] += lo[2 * e + 1] + (round_u32<K::CHECK>(R.acc[1][e].im, maxfrac) << 16);
+                    }
+                }
+            });
+            if constexpr (!SELF_REFILL) { if (producer) pump(0, it); }
+        } else if constexpr (K::SINGLE_BUF) {   // one limb after the other through the single buffer
             uint32_t lo[2 * K::E];
             phase_K1<K, 0>(R, t, twC, buf0);
             sub_sync();
@@ -663,6 +725,19 @@ __global__ void bsk_fft_reslot9_kernel(const cplx *__restrict__ in, cplx *__rest
     const uint32_t idx = threadIdx.x;                    // position in slot order: e * 64 + t
     const uint32_t j = ((idx & 63u) << 3) | (idx >> 6);   // the point it holds
     out[poly * 512 + tail9_slot_of_index(j)] = in[poly * 512 + idx];
+}
+
+// the same for N = 2048 (M = 1024, 16 points per thread, key slots of half a row): the polynomial of (row, limb, column) lives in two
+// slots, point (t << 4) | e at slot e / 8, position (e % 8) * 64 + t; layout F10 puts point j into slot j5, position (j1 j0 j4) * 64 +
+// thread(j).  grid = (rows, 2 * P polynomials per row), 1024 threads = one per point.
+__global__ void bsk_fft_reslot10_kernel(const cplx *__restrict__ in, cplx *__restrict__ out, uint32_t polys_per_slot) {
+    const size_t row = blockIdx.x, poly = blockIdx.y;                  // poly = limb * P + column
+    const size_t slot_elems = (size_t)polys_per_slot * 512;
+    const uint32_t idx = threadIdx.x, e = ((idx >> 9) << 3) | ((idx >> 6) & 7u), t = idx & 63u, j = (t << 4) | e;
+    const uint32_t r = tail10_reg_of_index(j);
+    const size_t src = (row * 2 + (idx >> 9)) * slot_elems + poly * 512 + (idx & 511u);
+    const size_t dst = (row * 2 + (r >> 3)) * slot_elems + poly * 512 + (r & 7u) * 64u + tail10_thread_of_index(j);
+    out[dst] = in[src];
 }
 
 // ------------------------------------------------------------------------------------------ key transform
