@@ -209,6 +209,9 @@ using KF0TC = fft::FftPbsCfg<9, 3, 2, 6, 4, 4, true, false, 1, TFHE_FFT_TMEM_NSL
 // N = 2048: 16 points per thread, one exchange buffer per sub-team, half-row key slots (fft_team.cuh FftPbsCfg)
 using KF2 = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, false, true, 2>;
 using KF2C = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2>;
+// N = 2048 with one shared-memory exchange per transform and the last two stages on a tensor-memory swap (fft_tmem.cuh tail16)
+using KF2T = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, false, true, 2, TFHE_FFT_NSLOT, 3>;
+using KF2TC = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2, TFHE_FFT_NSLOT, 3>;
 static_assert(fft::key_slot_layout_ok<KF0>() && fft::key_slot_layout_ok<KF1>() && fft::key_slot_layout_ok<KF2>(), "diagonal-major key layout");
 // latency configurations: ONE ciphertext per CTA, the rest of the shared memory is a deep key ring (batches of at most one
 // ciphertext per SM; the production two-slot ring would leave such a CTA waiting for the round trip of every refill)
@@ -433,7 +436,10 @@ int launch_pbs(tfhe_ctx *ctx, const PbsArgs &a, const tfhe_bk *bk) {
             if (a.mode == 0 && bk->d_bsk_fft_x && ctx->fft_tmem && fft_smem_bytes<KF1T>(a.n) <= 227 * 1024)
                 return ctx->fft_check ? launch_pbs_fft_t<KF1TC>(ctx, a, bk->d_bsk_fft_x) : launch_pbs_fft_t<KF1T>(ctx, a, bk->d_bsk_fft_x);
             return ctx->fft_check ? launch_pbs_fft_t<KF1C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF1>(ctx, a, bk->d_bsk_fft);
-        case 2: return ctx->fft_check ? launch_pbs_fft_t<KF2C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF2>(ctx, a, bk->d_bsk_fft);
+        case 2:
+            if (a.mode == 0 && bk->d_bsk_fft_x && ctx->fft_tmem && fft_smem_bytes<KF2T>(a.n) <= 227 * 1024)
+                return ctx->fft_check ? launch_pbs_fft_t<KF2TC>(ctx, a, bk->d_bsk_fft_x) : launch_pbs_fft_t<KF2T>(ctx, a, bk->d_bsk_fft_x);
+            return ctx->fft_check ? launch_pbs_fft_t<KF2C>(ctx, a, bk->d_bsk_fft) : launch_pbs_fft_t<KF2>(ctx, a, bk->d_bsk_fft);
         }
         return fail(ctx, TFHE_E_PARAM, "no FFT-path instantiation for this parameter set");
     }
@@ -694,6 +700,7 @@ int tfhe_ctx_create(const tfhe_params *p, int device, tfhe_ctx **out) {
         std::vector<fft::cplx> fx;
         if (logm == 8) fft::build_fft_tmem_table(fx);
         if (logm == 9 && floge == 3) fft::build_fft_tail_table(fx);
+        if (logm == 10 && floge == 4) fft::build_fft_tail16_table(fx);
         const std::vector<fft::cplx> *fsrc[4] = {&ft.B, &ft.C, &ft.Z, &fx};
         for (int i = 0; i < 4; i++) {
             if (fsrc[i]->empty()) continue;
@@ -828,12 +835,15 @@ int tfhe_bk_upload(tfhe_ctx *ctx, const uint32_t *bsk, const uint32_t *ksk, tfhe
     if (e != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
     else if (bk->path == TFHE_PATH_FFT) {
         rc = launch_fft_transform(ctx, raw_dev, bk->d_bsk_fft, ctx->n(), 1);
-        if (rc == TFHE_OK && (ctx->pbs_id == 0 || (ctx->pbs_id == 1 && TFHE_FFT_P1_LOGE == 3)) && ctx->fft_tmem) {   // second copy in the order of the tensor-memory kernels
+        if (rc == TFHE_OK && (ctx->pbs_id == 0 || (ctx->pbs_id == 1 && TFHE_FFT_P1_LOGE == 3) || ctx->pbs_id == 2) && ctx->fft_tmem) {   // second copy in the order of the tensor-memory kernels
             if ((e = cudaMalloc(&bk->d_bsk_fft_x, fft_key_bytes(ctx))) != cudaSuccess) rc = fail(ctx, TFHE_E_OOM, cudaGetErrorString(e));
             else {
                 const size_t M = ctx->N() / 2, polys = fft_key_bytes(ctx) / (M * sizeof(fft::cplx));
                 if (ctx->pbs_id == 0) fft::bsk_fft_reslot_kernel<<<(unsigned)polys, 256, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, polys);
-                else fft::bsk_fft_reslot9_kernel<<<(unsigned)polys, 512, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, polys);
+                else if (ctx->pbs_id == 2) {
+                    const unsigned rows = (unsigned)(ctx->n() * KF2T::ROWS), pps = 2u * KF2T::P;
+                    fft::bsk_fft_reslot10_kernel<<<dim3(rows, pps), 1024, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, pps);
+                } else fft::bsk_fft_reslot9_kernel<<<(unsigned)polys, 512, 0, ctx->stream>>>(bk->d_bsk_fft, bk->d_bsk_fft_x, polys);
                 ctx->launches++;
                 if ((e = cudaGetLastError()) != cudaSuccess) rc = fail(ctx, TFHE_E_CUDA, cudaGetErrorString(e));
             }
