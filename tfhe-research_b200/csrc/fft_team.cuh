@@ -211,6 +211,29 @@ TFHE_HD void fwd_pass(cplx *x, const cplx *tw) {
         });
     });
 }
+// stages [U0, U1) of a pass (same twiddle indexing): lets a caller fetch the twiddles of the late stages late
+template <int LOGE, int U0, int U1>
+TFHE_HD void fwd_pass_range(cplx *x, const cplx *tw) {
+    static_for<U0, U1>([&](auto ui) {
+        constexpr int u = decltype(ui)::value;
+        constexpr int bit = 1 << (LOGE - 1 - u);
+        static_for<0, (1 << LOGE)>([&](auto ei) {
+            constexpr int e = decltype(ei)::value;
+            if constexpr ((e & bit) == 0) ct_bfly(x[e], x[e + bit], tw[(1 << u) - 1 + (e >> (LOGE - u))]);
+        });
+    });
+}
+template <int LOGE, int U0, int U1>
+TFHE_HD void inv_pass_range(cplx *x, const cplx *tw) {   // stages U1-1 down to U0
+    static_for<0, U1 - U0>([&](auto ui) {
+        constexpr int u = U1 - 1 - decltype(ui)::value;
+        constexpr int bit = 1 << (LOGE - 1 - u);
+        static_for<0, (1 << LOGE)>([&](auto ei) {
+            constexpr int e = decltype(ei)::value;
+            if constexpr ((e & bit) == 0) gs_bfly(x[e], x[e + bit], tw[(1 << u) - 1 + (e >> (LOGE - u))]);
+        });
+    });
+}
 template <int LOGE, int NST>
 TFHE_HD void inv_pass(cplx *x, const cplx *tw) {
     static_for<0, NST>([&](auto ui) {

@@ -147,10 +147,13 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     constexpr bool TAIL = K::TAIL && !K::TAIL16 && OWN_FIRST;
     // TAIL16 (N = 2048): ring-order loop, single exchange buffer; 96 columns per warp (64 swap + 32 parked twiddles)
     constexpr bool TAIL16 = K::TAIL16 && !OWN_FIRST && !BMMP;
-    static_assert(!TAIL16 || ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL16_COLS + TMEM_TAIL16_TW_COLS) <= 256, "tensor-memory columns");
+#ifndef TFHE_TMEM_TAIL16_TWB
+#define TFHE_TMEM_TAIL16_TWB 1   // the 15 derived twiddles of pass B'' wait in tensor memory too (two 32-column blocks per warp)
+#endif
+    static_assert(!TAIL16 || ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL16_COLS + TMEM_TAIL16_TW_COLS + 64u) <= 512, "tensor-memory columns");
     static_assert(!TAIL || ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL_COLS + TMEM_TAIL_TW_COLS) <= 512, "tensor-memory columns");
     constexpr bool USE_TMEM = K::XCHG || TWT || TAIL || TAIL16;
-    constexpr uint32_t TMEM_ALLOC = (K::XCHG || TAIL) ? 512u : 256u;
+    constexpr uint32_t TMEM_ALLOC = (K::XCHG || TAIL || TAIL16) ? 512u : 256u;
     static_assert(!TWT || ((K::THREADS / 32 + 3) / 4) * TMEM_TWT_COLS <= TMEM_ALLOC, "tensor-memory columns");
     static_assert(!TWT || (K::F::NB_TW <= 8 && K::F::NC_TW <= 8), "one 32-column block per pass");
     if constexpr (USE_TMEM) {
@@ -223,7 +226,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     cplx twB_base = {}, twC_base = {};
     uint32_t jb_swz = 0;
     Tail16Tw t16 = {};
-    uint32_t t16_swap = 0;
+    uint32_t t16_swap = 0, t16_twb = 0;
     cplx *b16_even = nullptr, *b16_odd = nullptr;   // this thread's even / odd registers in layout B''16 (fft_team.cuh store_Bsw16)
     if constexpr (TAIL16) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -234,6 +237,16 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
         t16_swap = q0 + (tid >> 7) * TMEM_TAIL16_COLS;
         t16 = load_tail16_tw(a.tw.twX, t, jb >> 6);
         tmem_tail16_tw_setup(t16, q0 + ((K::THREADS / 32 + 3) / 4) * TMEM_TAIL16_COLS + (tid >> 7) * TMEM_TAIL16_TW_COLS);
+#if TFHE_TMEM_TAIL16_TWB
+        {
+            t16_twb = q0 + ((K::THREADS / 32 + 3) / 4) * (TMEM_TAIL16_COLS + TMEM_TAIL16_TW_COLS) + (tid >> 7) * 64u;
+            cplx tw[16];
+            derive_pass_tw<4>(tw, t16.pB);
+            tmem_tw_block_store<7>(t16_twb, tw);            // stages 4, 5, 6
+            tmem_tw_block_store<8>(t16_twb + 32u, tw + 7);  // stage 7
+            tmem_wait_st();
+        }
+#endif
     }
 #ifndef TFHE_TMEM_TAIL_TWB
 #define TFHE_TMEM_TAIL_TWB 1
@@ -518,6 +531,20 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #endif
                 if constexpr (TAIL16) {
                     store_Asw16<C>(R.x, buf0, t);        // the one shared-memory exchange
+#if TFHE_TMEM_TAIL16_TWB
+                    {
+                        TwRaw32 r0;
+                        cplx tw[8];
+                        tmem_tw_block_request(r0, t16_twb);          // R.x is dead here
+                        sub_sync();
+                        tmem_tw_block_claim<7>(r0, tw);
+                        load_Bsw16<C>(R.x, b16_even, b16_odd);
+                        fwd_pass_range<4, 0, 3>(R.x, tw);            // stages 4, 5, 6
+                        tmem_tw_block_request(r0, t16_twb + 32u);
+                        tmem_tw_block_claim<8>(r0, tw);
+                        fwd_pass_range<4, 3, 4>(R.x, tw - 7);        // stage 7
+                    }
+#else
                     sub_sync();
                     {
                         cplx tw[15];
@@ -525,6 +552,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                         load_Bsw16<C>(R.x, b16_even, b16_odd);
                         fwd_pass<4, 4>(R.x, tw);         // stages 4..7
                     }
+#endif
                     tmem_fwd_tail16(R.x, t16_swap, t16);  // stages 8, 9 inside the warp: layout F10
                     sub_sync();                          // every thread of the sub-team is past its loads from buf0
                 } else {
@@ -590,11 +618,24 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             static_for<0, 2>([&](auto li) {
                 constexpr int LIMB = decltype(li)::value;
                 tmem_inv_tail16(R.acc[LIMB], t16_swap, t16);
+#if TFHE_TMEM_TAIL16_TWB
+                {
+                    TwRaw32 r0;
+                    cplx tw[8];
+                    tmem_tw_block_request(r0, t16_twb + 32u);
+                    tmem_tw_block_claim<8>(r0, tw);
+                    inv_pass_range<4, 3, 4>(R.acc[LIMB], tw - 7);    // stage 7
+                    tmem_tw_block_request(r0, t16_twb);
+                    tmem_tw_block_claim<7>(r0, tw);
+                    inv_pass_range<4, 0, 3>(R.acc[LIMB], tw);        // stages 6, 5, 4
+                }
+#else
                 {
                     cplx tw[15];
                     derive_pass_tw<4>(tw, t16.pB);
                     inv_pass<4, 4>(R.acc[LIMB], tw);
                 }
+#endif
                 if constexpr (LIMB == 1) sub_sync();   // the low limb's loads from buf0 are done
                 store_Bsw16<C>(R.acc[LIMB], b16_even, b16_odd);
                 sub_sync();
