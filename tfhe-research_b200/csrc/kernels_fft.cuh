@@ -147,6 +147,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     constexpr bool TAIL = K::TAIL && !K::TAIL16 && OWN_FIRST;
     // TAIL16 (N = 2048): ring-order loop, single exchange buffer; 96 columns per warp (64 swap + 32 parked twiddles)
     constexpr bool TAIL16 = K::TAIL16 && !OWN_FIRST && !BMMP;
+#ifndef TFHE_TMEM_TAIL16_LATEBAR
+#define TFHE_TMEM_TAIL16_LATEBAR 1
+#endif
 #ifndef TFHE_TMEM_TAIL16_TWB
 #define TFHE_TMEM_TAIL16_TWB 1   // the 15 derived twiddles of pass B'' wait in tensor memory too (two 32-column blocks per warp)
 #endif
@@ -530,6 +533,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
                 else phase_F1a<K, 1>(R, t, sub, 0u, stash, a.tw.twA, [&](uint32_t pp, uint32_t j) { return diff(pp, j, rot); });
 #endif
                 if constexpr (TAIL16) {
+#if TFHE_TMEM_TAIL16_LATEBAR
+                    if constexpr (!FIRST) team_bar_id(team_bar, K::TEAM_THREADS);   // the rows published at the previous level have been read (after this level's digits and pass A)
+#endif
                     store_Asw16<C>(R.x, buf0, t);        // the one shared-memory exchange
 #if TFHE_TMEM_TAIL16_TWB
                     {
@@ -605,7 +611,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
 #endif
 #pragma unroll 1
                 for (uint32_t d = 1; d < (uint32_t)K::P; d++) row_slots(std::false_type{}, d);
-                team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
+                if constexpr (!(TAIL16 && TFHE_TMEM_TAIL16_LATEBAR)) team_bar_id(team_bar, K::TEAM_THREADS);  // the published rows have been read: buf0 may be overwritten
             };
             level(std::true_type{}, 0u);
 #pragma unroll 1
@@ -618,6 +624,9 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
             static_for<0, 2>([&](auto li) {
                 constexpr int LIMB = decltype(li)::value;
                 tmem_inv_tail16(R.acc[LIMB], t16_swap, t16);
+#if TFHE_TMEM_TAIL16_LATEBAR
+                if constexpr (LIMB == 0) team_bar_id(team_bar, K::TEAM_THREADS);   // the rows published at the last level have been read: buf0 may be overwritten
+#endif
 #if TFHE_TMEM_TAIL16_TWB
                 {
                     TwRaw32 r0;
