@@ -660,19 +660,26 @@ def main():
                             "peak_fft_butterfly_T": fp64_peaks["fft_butterfly"] / 1e12,
                             "frac_of_dfma_peak": B * p.n * dp_ops / (t_br * 1e-3) / fp64_peaks["dfma"],
                             "frac_pipe_cycles": B * p.n * dp_cycles_equiv / (t_br * 1e-3) / fp64_peaks["dfma"],
-                            "note": "frac_pipe_cycles weights three-register DFMAs by their measured issue cost; the binding resource "
-                                    "of this kernel is the shared-memory data pipe, see roofline.smem"}
+                            "note": "frac_pipe_cycles weights three-register DFMAs by their measured issue cost; with the tensor-memory "
+                                    "exchanges the kernels are bound by FP64 issue / dependent latency at 8-12 warps per SM rather than by "
+                                    "the shared-memory pipe (ncu: profiles/r02_v15_pbs_fft_kernel_*_ncu_summary.txt), see roofline.smem"}
         # shared-memory / L1 data-pipe bytes the kernel moves per CMUX step and ciphertext (128-bit accesses, E = 8 points per
         # thread): transform exchanges, key rows read from the TMA ring, published/peer transformed rows, twiddles, digits
+        # tensor-memory kernels (default): N = 512 has no shared-memory exchange and publishes rows in tensor memory; N = 1024 / 2048
+        # keep one of the two exchanges per transform
+        tmem = os.environ.get("TFHE_B200_FFT_TMEM", "1") != "0"
+        xchg_ops = 32 if not tmem else {9: 0, 10: 16, 11: 16}.get(p.glwe_poly_degree, 32)     # LDS/STS.128 per transform and thread
+        rows_in_smem = 0 if (tmem and p.glwe_poly_degree == 9) else 1
         E_, T_ = 8, M_ // 8
-        per_thread = ((l_ + 2) * 32 * 16 + l_ * P_ * 2 * E_ * 16 + l_ * (P_ - 1) * E_ * 16 + l_ * E_ * 16 + (l_ + 2) * 2 * 16
+        per_thread = ((l_ + 2) * xchg_ops * 16 + l_ * P_ * 2 * E_ * 16 + rows_in_smem * (l_ * (P_ - 1) * E_ * 16 + l_ * E_ * 16) + (l_ + 2) * 2 * 16
                       + 2 * E_ * 4 * 2 + (l_ - 1) * 2 * E_ * 2 * 2 + 2 * E_ * 4 * 2)
         smem_bytes = B * p.n * per_thread * P_ * T_
         smem_peak = 148 * 128 * clocks["sm_mhz"] * 1e6 if clocks.get("sm_mhz") else 148 * 128 * 1.965e9
         roofline["smem"] = {"bytes_per_launch": smem_bytes, "achieved_TBs": smem_bytes / (t_br * 1e-3) / 1e12, "peak_TBs": smem_peak / 1e12,
                             "frac": smem_bytes / (t_br * 1e-3) / smem_peak,
-                            "note": "peak = 128 B/clk/SM x 148 SMs at the sampled SM clock; a barrier-synchronised pass loop of the same shape "
-                                    "(8 LDS.128 + 36 butterflies + 8 STS.128 per thread, 12 warps per SM) reaches 0.83 of it "
+                            "exchange": ("tensor memory (tcgen05.st/ld)" + ("" if p.glwe_poly_degree == 9 else " for the last stages, one shared-memory exchange per transform")) if tmem else "shared memory",
+                            "note": "model of the LDS/STS bytes of one step; peak = 128 B/clk/SM x 148 SMs at the sampled SM clock; a barrier-synchronised "
+                                    "pass loop (8 LDS.128 + 36 butterflies + 8 STS.128 per thread, 12 warps per SM) reaches 0.83 of it "
                                     "(profiles/r01_fp64_peak.json pass_loop_384thr_cycles)"}
     cfg = config_dict(args.preset, B, p)
     line = {"metric": "PBS/sec", "value": value, "unit": "PBS/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
