@@ -1,5 +1,9 @@
-// fft_tmem.cuh -- the register passes of the folded FFT exchanged through TENSOR MEMORY instead of shared memory
-// (sub-teams of one warp: M = 256 points, 8 per thread -- the reference's default parameter set).
+// fft_tmem.cuh -- the register passes of the folded FFT exchanged through TENSOR MEMORY instead of shared memory.
+//   M = 256  (N = 512, the reference's default set; sub-team = one warp): every exchange, and the rows the sub-teams publish to each other
+//   M = 512  (N = 1024; sub-team = two warps): the last three stages ("tail9"), after pass A, one shared-memory exchange and pass B
+//   M = 1024 (N = 2048; 16 points per thread): the last two stages ("tail16"), after pass A, one shared-memory exchange and a 4-stage pass B''
+// plus per-thread derived twiddles parked in spare tensor-memory columns (they never change, and do not fit in registers).
+// The first part of this file describes the primitive and the M = 256 transform; the tails are at the end.
 //
 // Why: the blind rotation is bound by the shared-memory data pipe (128 B/clk/SM), and a third of its bytes are the exchanges
 // between the register passes of the transforms.  Tensor memory has its own data path: a warp that stores its registers with

@@ -213,6 +213,25 @@ using KF2C = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2>;
 using KF2T = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, false, true, 2, TFHE_FFT_NSLOT, 3>;
 using KF2TC = fft::FftPbsCfg<11, 4, 1, 3, 8, TFHE_FFT_CTS_P2, true, true, 2, TFHE_FFT_NSLOT, 3>;
 static_assert(fft::key_slot_layout_ok<KF0>() && fft::key_slot_layout_ok<KF1>() && fft::key_slot_layout_ok<KF2>(), "diagonal-major key layout");
+// the spectral layouts of the tensor-memory kernels are permutations of a polynomial's points (the key re-ordering kernels rely on it)
+constexpr bool tmem_layouts_are_permutations() {
+    bool seen8[256] = {}, seen9[512] = {}, seen10[1024] = {};
+    for (uint32_t j = 0; j < 256; j++) { const uint32_t s = fft::tmem_slot_of_index(j); if (s >= 256 || seen8[s]) return false; seen8[s] = true; }
+    for (uint32_t j = 0; j < 512; j++) { const uint32_t s = fft::tail9_slot_of_index(j); if (s >= 512 || seen9[s]) return false; seen9[s] = true; }
+    for (uint32_t j = 0; j < 1024; j++) {
+        const uint32_t s = fft::tail10_reg_of_index(j) * 64u + fft::tail10_thread_of_index(j);
+        if (s >= 1024 || seen10[s]) return false;
+        seen10[s] = true;
+    }
+    // the swizzles of the one shared-memory exchange are permutations too, and layout B'' covers every point exactly once
+    bool b9[512] = {}, b10[1024] = {};
+    for (uint32_t t = 0; t < 64; t++)
+        for (uint32_t e = 0; e < 8; e++) { const uint32_t a = fft::swz9(fft::jbase_Bsw(t) | (e << 3)); if (a >= 512 || b9[a]) return false; b9[a] = true; }
+    for (uint32_t t = 0; t < 64; t++)
+        for (uint32_t e = 0; e < 16; e++) { const uint32_t a = fft::swz10(fft::jbase_Bsw16(t) | (e << 2)); if (a >= 1024 || b10[a]) return false; b10[a] = true; }
+    return true;
+}
+static_assert(tmem_layouts_are_permutations(), "tensor-memory spectral layouts");
 // latency configurations: ONE ciphertext per CTA, the rest of the shared memory is a deep key ring (batches of at most one
 // ciphertext per SM; the production two-slot ring would leave such a CTA waiting for the round trip of every refill)
 using KF0L = fft::FftPbsCfg<9, 3, 2, 6, 4, 1, false, false, 1, 7>;
