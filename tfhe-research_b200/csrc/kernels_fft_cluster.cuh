@@ -296,8 +296,25 @@ struct ClusterSplitLayout {
     static constexpr int SUBBUF_BYTES = 2 * C::MPAD * 16;
     static constexpr int AT = BUFS + SUBS * SUBBUF_BYTES;                // u16 at[n+1]
     static constexpr size_t ring_offset(size_t n) { return ((size_t)AT + (n + 1) * 2 + 127) & ~(size_t)127; }
-    static constexpr size_t smem_bytes(size_t n) { return ring_offset(n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 4 * K::NSLOT + 16; }
+    // ring slots, their full / empty barriers, the two barriers of the partial-result exchange, the refill claims
+    static constexpr size_t smem_bytes(size_t n) { return ring_offset(n) + (size_t)K::NSLOT * K::SLOT_BYTES + 2 * K::NSLOT * 8 + 2 * 8 + 4 * K::NSLOT + 16; }
 };
+#ifndef TFHE_CLUSTER_ASYNC_PUSH
+#define TFHE_CLUSTER_ASYNC_PUSH 1
+#endif
+// st.async: a remote shared-memory store that reports its bytes to an mbarrier of the DESTINATION CTA.  With it the exchange of the
+// partial results needs no cluster-wide rendezvous: every CTA waits on its own barrier until the (L - 1) peers' words have landed.
+__device__ __forceinline__ void st_async_u32(uint32_t remote_addr, uint32_t v, uint32_t remote_bar) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.u32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v), "r"(remote_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return done != 0;
+}
 
 template <class K>
 __global__ void __launch_bounds__(ClusterSplitLayout<K>::THREADS, 1) pbs_fft_cluster_split_kernel(const __grid_constant__ FftArgs a) {
@@ -315,7 +332,8 @@ __global__ void __launch_bounds__(ClusterSplitLayout<K>::THREADS, 1) pbs_fft_clu
     uint16_t *at = reinterpret_cast<uint16_t *>(smem + LL::AT);
     uint8_t *ring = smem + LL::ring_offset(a.n);
     uint64_t *full = reinterpret_cast<uint64_t *>(ring + K::NSLOT * K::SLOT_BYTES), *empty = full + K::NSLOT;
-    uint32_t *claimed = reinterpret_cast<uint32_t *>(empty + K::NSLOT);
+    uint64_t *pbar = empty + K::NSLOT;                 // [2] partial results of an executed step have landed (TFHE_CLUSTER_ASYNC_PUSH)
+    uint32_t *claimed = reinterpret_cast<uint32_t *>(pbar + 2);
     constexpr bool WARP_SUB = K::T == 32;
     const uint32_t sub_bar = 1 + sub2;
     static_assert(WARP_SUB || LL::SUBS <= 15, "named barrier ids");
@@ -334,6 +352,8 @@ __global__ void __launch_bounds__(ClusterSplitLayout<K>::THREADS, 1) pbs_fft_clu
             mbar_init(empty + s, LL::SUBS * K::WARPS_PER_SUB);   // every warp of the CTA consumes every ring entry
             claimed[s] = 0;
         }
+        mbar_init(pbar + 0, 1);
+        mbar_init(pbar + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const uint32_t *lwe = a.lwe_in + (size_t)ct * (a.n + 1);
@@ -515,21 +535,55 @@ __global__ void __launch_bounds__(ClusterSplitLayout<K>::THREADS, 1) pbs_fft_clu
             for (int k = 0; k < 2 * K::E; k++) pv[k] += hand[k * K::T + t];
             uint32_t *mine = stepbuf + ((size_t)lev * K::P + col) * K::N;
             const uint32_t mine_addr = smem_u32(mine);
+#if TFHE_CLUSTER_ASYNC_PUSH
+            const uint32_t bar_addr = smem_u32(pbar + ((nexec - 1u) & 1u));
+#endif
 #pragma unroll
             for (uint32_t r = 1; r < (uint32_t)K::L; r++) {   // push to the peers (same offset in their shared memory)
                 uint32_t peer = lev + r;
                 peer = peer >= (uint32_t)K::L ? peer - (uint32_t)K::L : peer;
                 uint32_t remote;
                 asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(mine_addr), "r"(peer));
+#if TFHE_CLUSTER_ASYNC_PUSH
+                uint32_t remote_bar;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote_bar) : "r"(bar_addr), "r"(peer));
+#endif
 #pragma unroll
                 for (int k = 0; k < 2 * K::E; k++) {
                     const uint32_t j = (((uint32_t)(k >> 1) << C::LOGT) | t) + (uint32_t)(k & 1) * K::M;
+#if TFHE_CLUSTER_ASYNC_PUSH
+                    st_async_u32(remote + j * 4u, pv[k], remote_bar);
+#else
                     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(remote + j * 4u), "r"(pv[k]) : "memory");
+#endif
                 }
             }
         }
         tick(6);
+#if TFHE_CLUSTER_ASYNC_PUSH
+        {
+            // this CTA's barrier of the step: armed with the bytes the L - 1 peers send (every word of P polynomials from each), waited
+            // for by the threads that accumulate.  The two barriers alternate with the two partial-result buffers; a peer cannot be two
+            // executed steps ahead (its next push needs this CTA's words of the step between), so neither a buffer nor a barrier phase
+            // is reused early, and no cluster-wide barrier is needed inside the loop.
+            uint64_t *bar = pbar + ((nexec - 1u) & 1u);
+            if (tid == 0) mbar_expect_tx(bar, (uint32_t)(K::L - 1) * (uint32_t)K::P * (uint32_t)K::N * 4u);
+            if (limb == 0) {
+                const uint32_t par = ((nexec - 1u) >> 1) & 1u;
+                unsigned long long t0 = 0;
+                for (uint32_t spin = 1; !mbar_try_cluster(bar, par); spin++) {
+                    if ((spin & 255u) == 0u) {
+                        if (*(volatile uint32_t *)a.err_flag & 2u) break;
+                        const unsigned long long now = global_timer_ns();
+                        if (t0 == 0) t0 = now;
+                        else if (now - t0 > 10000000000ull) { atomicOr(a.err_flag, 2u); break; }
+                    }
+                }
+            }
+        }
+#else
         cluster_sync_all();
+#endif
         tick(7);
         if (limb == 0) {
 #pragma unroll
