@@ -252,14 +252,23 @@ __global__ void __launch_bounds__(K::TEAM_THREADS, 1) pbs_fft_cluster_kernel(con
         cluster_sync_all();   // the partial results of this step are visible in every CTA (and every peer is done reading those of two steps ago)
         tick(7);
         // acc += sum over the levels (own partial from registers, the others from local shared memory)
+        // the peers' words: all loads of a peer are issued before the first sum (a run-time `l != lev` test per word made the
+        // compiler wait for every load in turn: 1.0 k of the step's 8 k cycles)
+#pragma unroll
+        for (uint32_t r = 1; r < (uint32_t)K::L; r++) {
+            uint32_t l = lev + r;
+            l = l >= (uint32_t)K::L ? l - (uint32_t)K::L : l;
+            const uint32_t *src = stepbuf + ((size_t)l * K::P + sub) * K::N + t;
+            uint32_t v[2 * K::E];
+#pragma unroll
+            for (int k = 0; k < 2 * K::E; k++) v[k] = src[((uint32_t)(k >> 1) << C::LOGT) + (uint32_t)(k & 1) * K::M];
+#pragma unroll
+            for (int k = 0; k < 2 * K::E; k++) pv[k] += v[k];
+        }
 #pragma unroll
         for (int k = 0; k < 2 * K::E; k++) {
             const uint32_t j = (((uint32_t)(k >> 1) << C::LOGT) | t) + (uint32_t)(k & 1) * K::M;
-            uint32_t sum = pv[k];
-#pragma unroll
-            for (uint32_t l = 0; l < (uint32_t)K::L; l++)
-                if (l != lev) sum += stepbuf[((size_t)l * K::P + sub) * K::N + j];
-            accv[k] += sum;
+            accv[k] += pv[k];
             acc[sub * K::N + j] = accv[k];
         }
         sub_sync();   // acc[sub] (read with a rotation by this sub-team only) is up to date before the next step's digits
@@ -586,14 +595,22 @@ __global__ void __launch_bounds__(ClusterSplitLayout<K>::THREADS, 1) pbs_fft_clu
 #endif
         tick(7);
         if (limb == 0) {
+            // the peers' words: all loads of a peer are issued before the first sum (see pbs_fft_cluster_kernel)
+#pragma unroll
+            for (uint32_t r = 1; r < (uint32_t)K::L; r++) {
+                uint32_t l = lev + r;
+                l = l >= (uint32_t)K::L ? l - (uint32_t)K::L : l;
+                const uint32_t *src = stepbuf + ((size_t)l * K::P + col) * K::N + t;
+                uint32_t v[2 * K::E];
+#pragma unroll
+                for (int k = 0; k < 2 * K::E; k++) v[k] = src[((uint32_t)(k >> 1) << C::LOGT) + (uint32_t)(k & 1) * K::M];
+#pragma unroll
+                for (int k = 0; k < 2 * K::E; k++) pv[k] += v[k];
+            }
 #pragma unroll
             for (int k = 0; k < 2 * K::E; k++) {
                 const uint32_t j = (((uint32_t)(k >> 1) << C::LOGT) | t) + (uint32_t)(k & 1) * K::M;
-                uint32_t sum = pv[k];
-#pragma unroll
-                for (uint32_t l = 0; l < (uint32_t)K::L; l++)
-                    if (l != lev) sum += stepbuf[((size_t)l * K::P + col) * K::N + j];
-                accv[k] += sum;
+                accv[k] += pv[k];
                 acc[col * K::N + j] = accv[k];
             }
             sub_sync();   // acc[col] (read with a rotation by this sub-team only) is up to date before the next step's digits
