@@ -129,7 +129,8 @@ int tfhe_ctx_set_ks_path(tfhe_ctx *ctx, int path);
 int tfhe_ctx_set_fft_check(tfhe_ctx *ctx, int on);
 /* FFT path, blind rotations of at most one ciphertext per SM (small batches, single-PBS latency); env
  * TFHE_B200_LATENCY_CFG=0|1|2|3|4.  A lone ciphertext on an SM is a chain of n dependent CMUX steps, each L levels + one inverse:
- *   4 (default)  like 3, with every CTA's multiply-accumulate and inverse transform split by key limb over twice the warps;
+ *   4 (default)  like 3, with every CTA's multiply-accumulate and inverse transform split by key limb over twice the warps, and the
+ *                partial results exchanged with st.async onto the destination CTA's mbarrier instead of a cluster barrier;
  *   3            batches that fit co-resident clusters (at most about sm_count / L ciphertexts): one thread-block CLUSTER of L CTAs per ciphertext, one gadget
  *                level per CTA (own accumulator replica, own key ring, own inverse transform; the exact u32 partial results
  *                are exchanged through distributed shared memory, one cluster barrier per step; kernels_fft_cluster.cuh;
