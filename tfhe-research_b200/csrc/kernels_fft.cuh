@@ -375,6 +375,7 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     // has arrived; whoever sees that first (at the latest the last arriver, right after its own arrival) claims the refill.
     // (looking at the outcome of the test one row later, to hide its ~100 cycles behind the next multiply-accumulate, was measured with
     // the 6-row ring of the tensor-memory configuration: 97.3 -> 105.0 ms -- the refill that waits starves the ring)
+    // (testing the rows of a level together at the end of the level, one round trip per level: 95.0 -> 95.7 ms, not kept either)
     auto release_slot = [&](uint32_t r) {
         const uint32_t s = r % K::NSLOT;
         mbar_arrive(empty + s);
