@@ -33,15 +33,10 @@
 #include "fft_team.cuh"
 
 // measured choices (tools/gpu_call8.sh, P0 batch 4096): the swap stores as 4 x tcgen05.st.x8 (fewer register moves than one x32:
-// 102.95 -> 99.49 ms), 16x256b loads / stores as .x4 (104.26 -> 102.18 ms), a peer's row requested before the wait for the key slot
+// 102.95 -> 99.49 ms), 16x256b loads / stores as .x4 (104.26 -> 102.18 ms), a peer's row requested before the wait
+// for the key slot; publishing / fetching a row as 4 x .x8 instead of one .x32 was slower (100.3 / 100.0 vs 99.5 ms)
 #ifndef TFHE_TMEM_ST8
 #define TFHE_TMEM_ST8 1
-#endif
-#ifndef TFHE_TMEM_PUB8
-#define TFHE_TMEM_PUB8 0
-#endif
-#ifndef TFHE_TMEM_ROWLD8
-#define TFHE_TMEM_ROWLD8 0
 #endif
 #ifndef TFHE_TMEM_LOADFIRST
 #define TFHE_TMEM_LOADFIRST 1
@@ -473,13 +468,6 @@ __device__ __forceinline__ void tmem_store_row(const cplx (&x)[8], uint32_t tadd
         v[4 * e + 2] = (uint32_t)__double2loint(x[e].im);
         v[4 * e + 3] = (uint32_t)__double2hiint(x[e].im);
     }
-#if TFHE_TMEM_PUB8
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr + 8u * q), "r"(v[8 * q]), "r"(v[8 * q + 1]), "r"(v[8 * q + 2]),
-                     "r"(v[8 * q + 3]), "r"(v[8 * q + 4]), "r"(v[8 * q + 5]), "r"(v[8 * q + 6]), "r"(v[8 * q + 7])
-                     : "memory");
-#else
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
         "%25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
@@ -487,18 +475,10 @@ __device__ __forceinline__ void tmem_store_row(const cplx (&x)[8], uint32_t tadd
         "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
         "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
-#endif   // the caller waits (tmem_wait_st) before it tells its peers
+  // the caller waits (tmem_wait_st) before it tells its peers
 }
 __device__ __forceinline__ void tmem_load_row(cplx (&x)[8], uint32_t taddr) {
     uint32_t v[32];
-#if TFHE_TMEM_ROWLD8
-#pragma unroll
-    for (int q = 0; q < 4; q++)
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(v[8 * q]), "=r"(v[8 * q + 1]), "=r"(v[8 * q + 2]), "=r"(v[8 * q + 3]), "=r"(v[8 * q + 4]), "=r"(v[8 * q + 5]), "=r"(v[8 * q + 6]), "=r"(v[8 * q + 7])
-                     : "r"(taddr + 8u * q)
-                     : "memory");
-#else
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
         "%26, %27, %28, %29, %30, %31}, [%32];"
@@ -507,7 +487,6 @@ __device__ __forceinline__ void tmem_load_row(cplx (&x)[8], uint32_t taddr) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-#endif
     tmem_wait_ld(v);
 #pragma unroll
     for (int e = 0; e < 8; e++) {
