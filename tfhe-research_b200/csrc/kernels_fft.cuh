@@ -143,9 +143,10 @@ __global__ void __launch_bounds__(K::THREADS, 1) pbs_fft_kernel(const __grid_con
     uint32_t *tmem_ptr = claimed + K::NSLOT;
     // TWT (P1): 256 columns, 64 per warp (warp / 4) of its lanes, for the derived twiddles of passes B and C
     constexpr bool TWT = K::TWT && OWN_FIRST;
-    // TAIL (P1): 256 columns, 64 per warp, for the tensor-memory swaps of the last three stages of every transform
+    // TAIL (P1): per warp 64 columns for the tensor-memory swaps of the last three stages of every transform (2 x 32 for the paired
+    // inverse) + 32 for the parked twiddles of those stages + 32 for pass B's: 3 warps per lane quarter = 384 of the 512 columns
     constexpr bool TAIL = K::TAIL && !K::TAIL16 && OWN_FIRST;
-    // TAIL16 (N = 2048): ring-order loop, single exchange buffer; 96 columns per warp (64 swap + 32 parked twiddles)
+    // TAIL16 (N = 2048): ring-order loop, single exchange buffer; per warp 64 swap columns + 32 + 64 of parked twiddles, 2 warps per quarter
     constexpr bool TAIL16 = K::TAIL16 && !OWN_FIRST && !BMMP;
 #ifndef TFHE_TMEM_TAIL16_LATEBAR
 #define TFHE_TMEM_TAIL16_LATEBAR 1
