@@ -191,8 +191,11 @@ int launch_pbs_t(tfhe_ctx *ctx, const PbsArgs &a) {
 using KF1 = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, false, TFHE_FFT_P1_SINGLE != 0, 1, TFHE_FFT_NSLOT, TFHE_FFT_P1_TWT>;   // production: a-priori exactness bound only
 using KF1C = fft::FftPbsCfg<10, TFHE_FFT_P1_LOGE, 1, 3, 8, TFHE_FFT_CTS_P1, true, TFHE_FFT_P1_SINGLE != 0, 1, TFHE_FFT_NSLOT, TFHE_FFT_P1_TWT>;
 // P1 with the last three stages of every transform in tensor memory (one shared-memory exchange instead of two; fft_tmem.cuh tail9)
-using KF1T = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, false, false, 1, TFHE_FFT_NSLOT, 3>;
-using KF1TC = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true, false, 1, TFHE_FFT_NSLOT, 3>;   // + records the rounding margin (tests, validation)
+#ifndef TFHE_FFT_P1T_NSLOT
+#define TFHE_FFT_P1T_NSLOT TFHE_FFT_NSLOT
+#endif
+using KF1T = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, false, false, 1, TFHE_FFT_P1T_NSLOT, 3>;
+using KF1TC = fft::FftPbsCfg<10, 3, 1, 3, 8, TFHE_FFT_CTS_P1, true, false, 1, TFHE_FFT_P1T_NSLOT, 3>;   // + records the rounding margin (tests, validation)
 #ifndef TFHE_FFT_CTS_P0
 #define TFHE_FFT_CTS_P0 4
 #endif
