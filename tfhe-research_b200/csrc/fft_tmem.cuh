@@ -35,6 +35,7 @@
 // measured choices (tools/gpu_call8.sh, P0 batch 4096): the swap stores as 4 x tcgen05.st.x8 (fewer register moves than one x32:
 // 102.95 -> 99.49 ms), 16x256b loads / stores as .x4 (104.26 -> 102.18 ms), a peer's row requested before the wait
 // for the key slot; publishing / fetching a row as 4 x .x8 instead of one .x32 was slower (100.3 / 100.0 vs 99.5 ms)
+// (the same two choices hold for the tails: P1 61.3 vs 62.9 (x32 store) / 61.8 (x1 shapes) ms, P2 94.9 vs 99.1 / 96.2 ms)
 #ifndef TFHE_TMEM_ST8
 #define TFHE_TMEM_ST8 1
 #endif
